@@ -1,0 +1,5 @@
+"""gumbi_b200 -- B200-native exact-GP inference core behind Gumbi's Regressor backend API."""
+from ._lib import BackendUnavailable, lib_path  # noqa: F401
+from .engine import GPEngine  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,151 @@
+// fp64 tensor-core contraction  C (-)= A * B^T  on DMMA (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4).
+//
+// tcgen05.mma has no fp64 kind, so the fp64 dense contractions of the path -- the Cholesky
+// trailing SYRK/GEMM update, the panel TRSM (as a product with the inverted diagonal block) and the
+// predict solve L^-1 K(X,X*) -- all run through this one kernel.  Measured B200 ceiling for this
+// instruction: 37.0 TFLOP/s (tools/micro_fp64.cu; cuBLAS DGEMM reaches 35.5).
+//
+// Both operands are "K-contiguous": A is (rows x k) row-major, B is (cols x k) row-major, which is what
+// a row-major lower-triangular factor gives for L_ik L_jk^T without any transposition.
+// CTA tile BM x BN (128x64 or 64x128), 8 warps of 32x32, BK = 16, 3-stage cp.async ring.
+// Shared rows are padded to 20 doubles (160 B): the 8x4 DMMA fragment then reads 16 lanes x 8 B from 32
+// distinct banks per half-warp (row stride = 8 banks mod 32), i.e. conflict-free LDS.64.
+// All extents are multiples of the tile (the host pads N and M to 128), so the main loop has no bounds checks.
+#pragma once
+#include "gb2_internal.cuh"
+
+namespace gb2 {
+
+constexpr int GM_BK = 16;
+constexpr int GM_LDS = 20;  // padded shared row, doubles
+constexpr int GM_STAGES = 3;
+constexpr int GM_THREADS = 256;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+enum { GM_SUB = 0, GM_SET = 1 };
+
+template <int BM, int BN>
+constexpr size_t dgemm_smem_bytes() { return (size_t)GM_STAGES * (BM + BN) * GM_LDS * sizeof(double); }
+
+// C[bi*BM.., bj*BN..] (MODE==GM_SUB: -=, GM_SET: =) sum_k A[bi*BM + r, k] * B[bj*BN + c, k],  k < kdepth.
+// lower_only: skip tiles lying strictly above the diagonal of the global matrix, where tile (0,0) sits at
+// global (row_off, col_off).  In GM_SET mode C may alias A (in-place right-multiplication of a row panel):
+// each CTA owns complete rows and has consumed all of its A rows before the epilogue stores.
+template <int BM, int BN, int MODE>
+__global__ void __launch_bounds__(GM_THREADS, 2)
+dgemm_nt_kernel(const double* A, int64_t lda, const double* __restrict__ B, int64_t ldb, double* C, int64_t ldc,
+                int kdepth, int lower_only, int64_t row_off, int64_t col_off) {
+    static_assert((BM / 32) * (BN / 32) == GM_THREADS / 32, "8 warps of 32x32");
+    const int bi = blockIdx.x, bj = blockIdx.y;
+    if (lower_only && col_off + (int64_t)bj * BN > row_off + (int64_t)bi * BM + (BM - 1)) return;
+
+    extern __shared__ __align__(16) unsigned char gm_smem[];
+    double* sA = reinterpret_cast<double*>(gm_smem);
+    double* sB = sA + GM_STAGES * BM * GM_LDS;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp % (BM / 32), wn = warp / (BM / 32);
+    const int g = lane >> 2, t = lane & 3;
+
+    const double* Ag = A + (int64_t)bi * BM * lda;
+    const double* Bg = B + (int64_t)bj * BN * ldb;
+
+    auto load_stage = [&](int stage, int kt) {
+        const int k0 = kt * GM_BK;
+        double* dA = sA + stage * BM * GM_LDS;
+        double* dB = sB + stage * BN * GM_LDS;
+#pragma unroll
+        for (int c = tid; c < BM * 8; c += GM_THREADS) {
+            const int r = c >> 3, ch = c & 7;
+            cp_async16(dA + r * GM_LDS + ch * 2, Ag + (int64_t)r * lda + k0 + ch * 2);
+        }
+#pragma unroll
+        for (int c = tid; c < BN * 8; c += GM_THREADS) {
+            const int r = c >> 3, ch = c & 7;
+            cp_async16(dB + r * GM_LDS + ch * 2, Bg + (int64_t)r * ldb + k0 + ch * 2);
+        }
+    };
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+    const int nk = kdepth / GM_BK;
+#pragma unroll
+    for (int s = 0; s < GM_STAGES - 1; s++) {
+        if (s < nk) load_stage(s, s);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < nk; kt++) {
+        cp_async_wait<GM_STAGES - 2>();
+        __syncthreads();
+        const int nxt = kt + GM_STAGES - 1;
+        if (nxt < nk) load_stage(nxt % GM_STAGES, nxt);
+        cp_async_commit();
+        const double* cA = sA + (kt % GM_STAGES) * BM * GM_LDS + (wm * 32 + g) * GM_LDS + t;
+        const double* cB = sB + (kt % GM_STAGES) * BN * GM_LDS + (wn * 32 + g) * GM_LDS + t;
+#pragma unroll
+        for (int kk = 0; kk < GM_BK / 4; kk++) {
+            double a[4], b[4];
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++) a[mi] = cA[mi * 8 * GM_LDS + kk * 4];
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) b[ni] = cB[ni * 8 * GM_LDS + kk * 4];
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
+    }
+    cp_async_wait<0>();
+
+    double* Cg = C + ((int64_t)bi * BM + wm * 32 + g) * ldc + (int64_t)bj * BN + wn * 32 + 2 * t;
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+            double2* p = reinterpret_cast<double2*>(Cg + (int64_t)mi * 8 * ldc + ni * 8);
+            if (MODE == GM_SUB) {
+                double2 c = *p;
+                c.x -= acc[mi][ni][0];
+                c.y -= acc[mi][ni][1];
+                *p = c;
+            } else {
+                *p = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+            }
+        }
+}
+
+template <int BM, int BN, int MODE>
+inline cudaError_t dgemm_nt_configure() {
+    return cudaFuncSetAttribute(dgemm_nt_kernel<BM, BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)dgemm_smem_bytes<BM, BN>());
+}
+
+// rows x cols output, both multiples of the tile.
+template <int BM, int BN, int MODE>
+inline void dgemm_nt_launch(cudaStream_t s, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+                            int64_t ldc, int64_t rows, int64_t cols, int kdepth, int lower_only, int64_t row_off,
+                            int64_t col_off) {
+    if (rows <= 0 || cols <= 0 || kdepth <= 0) return;
+    dim3 grid((unsigned)(rows / BM), (unsigned)(cols / BN));
+    dgemm_nt_kernel<BM, BN, MODE><<<grid, GM_THREADS, dgemm_smem_bytes<BM, BN>(), s>>>(A, lda, B, ldb, C, ldc, kdepth,
+                                                                                      lower_only, row_off, col_off);
+}
+
+}  // namespace gb2

@@ -1,0 +1,403 @@
+// extern "C" boundary of the gumbi_b200 core (declared in include/gumbi_b200.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC gb2_abi.cu -o libgumbi_b200.so
+#include "predict.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <new>
+
+using namespace gb2;
+
+static std::string g_create_err;
+
+namespace {
+
+template <typename T>
+int ensure(gb2_handle* h, T*& p, int64_t& cap, int64_t need) {
+    if (need <= cap && p) return 0;
+    if (p) GB2_CUDA(h, cudaFree(p));
+    p = nullptr; cap = 0;
+    GB2_CUDA(h, cudaMalloc(&p, (size_t)need * sizeof(T)));
+    cap = need;
+    return 0;
+}
+
+int set_train_common(gb2_handle* h, const double* X, int64_t N, int32_t D_in, const double* y, cudaMemcpyKind kind) {
+    GB2_ARG(h, X && y, "X and y must be non-null");
+    GB2_ARG(h, N >= 1, "N must be >= 1");
+    GB2_ARG(h, D_in >= 1 && D_in <= 64, "D_in must be in [1, 64]");
+    GB2_CUDA(h, cudaSetDevice(h->device));
+    const int64_t Np = round_up(N + 1, TILE);
+    if (h->dX) { GB2_CUDA(h, cudaFree(h->dX)); h->dX = nullptr; }
+    if (h->dy) { GB2_CUDA(h, cudaFree(h->dy)); h->dy = nullptr; }
+    GB2_CUDA(h, cudaMalloc(&h->dX, (size_t)N * D_in * sizeof(double)));
+    GB2_CUDA(h, cudaMalloc(&h->dy, (size_t)N * sizeof(double)));
+    GB2_CUDA(h, cudaMemcpyAsync(h->dX, X, (size_t)N * D_in * sizeof(double), kind, h->s_main));
+    GB2_CUDA(h, cudaMemcpyAsync(h->dy, y, (size_t)N * sizeof(double), kind, h->s_main));
+    GB2_CUDA(h, cudaStreamSynchronize(h->s_main));
+    h->N = N; h->Np = Np; h->D_in = D_in;
+    h->have_train = true; h->factorized = false;
+    return 0;
+}
+
+// (re)build PrepParams/KParams feature offsets; needs D_in for index validation
+int validate_against_train(gb2_handle* h) {
+    const PrepParams& pp = h->pp;
+    for (int t = 0; t < pp.n_terms; t++) {
+        for (int k = 0; k < pp.d[t]; k++) GB2_ARG(h, pp.cont_idx[t][k] >= 0 && pp.cont_idx[t][k] < h->D_in, "cont_idx out of range for D_in");
+        for (int l = 0; l < pp.n_lin[t]; l++) GB2_ARG(h, pp.lin_idx[t][l] >= 0 && pp.lin_idx[t][l] < h->D_in, "lin_idx out of range for D_in");
+    }
+    for (int f = 0; f < pp.n_cat; f++) GB2_ARG(h, pp.cat_col[f] >= 0 && pp.cat_col[f] < h->D_in, "coregion column out of range for D_in");
+    return 0;
+}
+
+double ms_between(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    return (double)ms;
+}
+
+int predict_common(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_noise, double* mean, double* var, bool dev) {
+    GB2_ARG(h, h->factorized, "gb2_predict called before a successful gb2_factorize");
+    GB2_ARG(h, Xs && mean && var, "null pointer");
+    GB2_ARG(h, M >= 0, "M must be >= 0");
+    if (M == 0) return 0;
+    GB2_CUDA(h, cudaSetDevice(h->device));
+    const int64_t Np = h->Np, N = h->N;
+    // chunk the prediction points so that the (chunk x Np) solve panel stays within ~8 GiB
+    int64_t chunk = std::max<int64_t>(TILE, ((int64_t)8 << 30) / (Np * (int64_t)sizeof(double)) / TILE * TILE);
+    chunk = std::min<int64_t>(chunk, round_up(M, TILE));
+    const int ncols = (int)((N + TILE - 1) / TILE);  // column blocks that carry training points
+    int rc;
+    if ((rc = ensure(h, h->dAt, h->At_cap, chunk * Np))) return rc;
+    if ((rc = ensure(h, h->dFs, h->Fs_cap, (int64_t)std::max(1, h->kp.n_feat) * chunk))) return rc;
+    if ((rc = ensure(h, h->dCs, h->Cs_cap, (int64_t)std::max(1, h->kp.n_cat) * chunk))) return rc;
+    const double* dXs_all = Xs;
+    double* dmean_all = mean; double* dvar_all = var;
+    if (!dev) {
+        if ((rc = ensure(h, h->dXs, h->Xs_cap, M * h->D_in))) return rc;
+        int64_t oc = h->out_cap;
+        if ((rc = ensure(h, h->dMean, oc, M))) return rc;
+        if ((rc = ensure(h, h->dVar, h->out_cap, M))) return rc;
+        GB2_CUDA(h, cudaMemcpyAsync(h->dXs, Xs, (size_t)M * h->D_in * sizeof(double), cudaMemcpyHostToDevice, h->s_main));
+        dXs_all = h->dXs; dmean_all = h->dMean; dvar_all = h->dVar;
+    }
+    cudaStream_t s = h->s_main;
+    double t_prep = 0, t_ks = 0, t_solve = 0, t_red = 0;
+    int launches = 0;
+    GB2_CUDA(h, cudaMemsetAsync(h->dInfo + 1, 0, sizeof(int), s));
+    for (int64_t m0 = 0; m0 < M; m0 += chunk) {
+        const int64_t Mc = std::min(chunk, M - m0);
+        const int64_t Mp = round_up(Mc, TILE);
+        GB2_CUDA(h, cudaEventRecord(h->ev[0], s));
+        prep_features<<<(unsigned)((Mp + 255) / 256), 256, 0, s>>>(dXs_all + m0 * h->D_in, Mc, Mp, h->pp, h->dFs, h->dCs, h->dInfo + 1);
+        GB2_CUDA(h, cudaEventRecord(h->ev[1], s));
+        dim3 grid((unsigned)(Np / KB_T), (unsigned)(Mp / KB_T));
+        kbuild_kernel<false><<<grid, KB_THREADS, kbuild_smem_bytes(h->kp), s>>>(h->kp, h->dBtab, h->dFs, h->dCs, Mp, Mc, h->dF, h->dC, Np, N,
+                                                                                 nullptr, h->dAt, Np);
+        GB2_CUDA(h, cudaEventRecord(h->ev[2], s));
+        launches += 2;
+        trsm_rec(s, h->dA, Np, h->dDinv, h->dAt, Np, Mp, 0, ncols, launches);
+        GB2_CUDA(h, cudaEventRecord(h->ev[3], s));
+        posterior_reduce_kernel<<<(unsigned)((Mc + 7) / 8), 256, 0, s>>>(h->kp, h->dBtab, h->dFs, h->dCs, Mp, h->dAt, Np, h->dA + N * Np, N, Mc,
+                                                                        pred_noise, dmean_all + m0, dvar_all + m0);
+        launches++;
+        GB2_CUDA(h, cudaEventRecord(h->ev[4], s));
+        GB2_CUDA(h, cudaGetLastError());
+        GB2_CUDA(h, cudaStreamSynchronize(s));
+        t_prep += ms_between(h->ev[0], h->ev[1]);
+        t_ks += ms_between(h->ev[1], h->ev[2]);
+        t_solve += ms_between(h->ev[2], h->ev[3]);
+        t_red += ms_between(h->ev[3], h->ev[4]);
+    }
+    if (!dev) {
+        GB2_CUDA(h, cudaMemcpyAsync(mean, h->dMean, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, s));
+        GB2_CUDA(h, cudaMemcpyAsync(var, h->dVar, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    int bad = 0;
+    GB2_CUDA(h, cudaMemcpyAsync(&bad, h->dInfo + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
+    GB2_CUDA(h, cudaStreamSynchronize(s));
+    h->timings[3] = t_prep + t_ks; h->timings[4] = t_solve; h->timings[5] = t_red; h->timings[7] = launches;
+    GB2_ARG(h, bad == 0, "a Coregion column of Xs holds a level index outside [0, P)");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gb2_abi_version(void) { return GB2_ABI_VERSION; }
+
+const char* gb2_last_error(const gb2_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int gb2_create(gb2_handle** out, int device, int precision) {
+    if (!out) { g_create_err = "invalid argument: out is null"; return -1; }
+    *out = nullptr;
+    if (precision != GB2_FP64 && precision != GB2_TF32) { g_create_err = "invalid argument: precision"; return -1; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_err = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); the gumbi_b200 core has no CPU fallback";
+        return -2;
+    }
+    if (device < 0 || device >= ndev) { g_create_err = "invalid argument: device ordinal out of range"; return -1; }
+    gb2_handle* h = new (std::nothrow) gb2_handle();
+    if (!h) { g_create_err = "out of host memory"; return -3; }
+    h->device = device; h->precision = precision;
+    auto fail = [&](cudaError_t ce, const char* what) {
+        g_create_err = std::string(what) + ": " + cudaGetErrorString(ce);
+        delete h;
+        return -100 - (int)ce;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(e, "cudaGetDeviceProperties");
+    if (prop.major < 10) {
+        g_create_err = "this library is built for sm_100a (B200) only; found compute capability " + std::to_string(prop.major) + "." + std::to_string(prop.minor);
+        delete h;
+        return -4;
+    }
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if ((e = cudaStreamCreateWithPriority(&h->s_main, cudaStreamNonBlocking, lo)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithPriority(&h->s_panel, cudaStreamNonBlocking, hi)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+    for (auto& ev : h->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail(e, "cudaEventCreate");
+    if ((e = cudaMalloc(&h->dInfo, 4 * sizeof(int))) != cudaSuccess) return fail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&h->dScal, 4 * sizeof(double))) != cudaSuccess) return fail(e, "cudaMalloc");
+    if ((e = cholesky_configure()) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
+    if ((e = cudaFuncSetAttribute(kbuild_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
+    if ((e = cudaFuncSetAttribute(kbuild_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
+    *out = h;
+    return 0;
+}
+
+int gb2_destroy(gb2_handle* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    cudaFree(h->dX); cudaFree(h->dy); cudaFree(h->dBtab); cudaFree(h->dF); cudaFree(h->dC); cudaFree(h->dA);
+    cudaFree(h->dDinv); cudaFree(h->dInfo); cudaFree(h->dScal); cudaFree(h->dXs); cudaFree(h->dFs); cudaFree(h->dCs);
+    cudaFree(h->dAt); cudaFree(h->dMean); cudaFree(h->dVar);
+    for (auto ev : h->ev) if (ev) cudaEventDestroy(ev);
+    for (auto ev : h->ev_pool) cudaEventDestroy(ev);
+    if (h->s_main) cudaStreamDestroy(h->s_main);
+    if (h->s_panel) cudaStreamDestroy(h->s_panel);
+    delete h;
+    return 0;
+}
+
+int gb2_set_train(gb2_handle* h, const double* X, int64_t N, int32_t D_in, const double* y) {
+    if (!h) return -1;
+    return set_train_common(h, X, N, D_in, y, cudaMemcpyHostToDevice);
+}
+
+int gb2_set_train_dev(gb2_handle* h, const double* dX, int64_t N, int32_t D_in, const double* dy) {
+    if (!h) return -1;
+    return set_train_common(h, dX, N, D_in, dy, cudaMemcpyDeviceToDevice);
+}
+
+int gb2_set_kernel(gb2_handle* h, const gb2_kernel* k) {
+    if (!h) return -1;
+    GB2_ARG(h, k != nullptr, "kernel is null");
+    GB2_ARG(h, k->n_terms >= 1 && k->n_terms <= GB2_MAX_TERMS, "n_terms must be in [1, GB2_MAX_TERMS]");
+    GB2_ARG(h, std::isfinite(k->sigma), "sigma must be finite");
+    GB2_ARG(h, std::isfinite(k->jitter) && k->jitter >= 0, "jitter must be finite and >= 0");
+    KParams kp{};
+    PrepParams pp{};
+    std::vector<double> btab;
+    kp.n_terms = pp.n_terms = k->n_terms;
+    int n_feat = 0, n_cat = 0;
+    auto cat_row = [&](int col, int P) -> int {
+        for (int f = 0; f < n_cat; f++)
+            if (pp.cat_col[f] == col) { pp.cat_P[f] = std::min(pp.cat_P[f], P); return f; }
+        pp.cat_col[n_cat] = col; pp.cat_P[n_cat] = P;
+        return n_cat++;
+    };
+    for (int t = 0; t < k->n_terms; t++) {
+        const gb2_term& T = k->terms[t];
+        TermDev& D = kp.t[t];
+        GB2_ARG(h, T.kind >= GB2_EXPQUAD && T.kind <= GB2_EXPONENTIAL, "unknown continuous kernel kind");
+        GB2_ARG(h, T.d >= 0 && T.d <= GB2_MAX_D, "d must be in [0, GB2_MAX_D]");
+        GB2_ARG(h, T.n_lin >= 0 && T.n_lin <= GB2_MAX_LIN, "n_lin must be in [0, GB2_MAX_LIN]");
+        GB2_ARG(h, T.n_coreg >= 0 && T.n_coreg <= GB2_MAX_COREG, "n_coreg must be in [0, GB2_MAX_COREG]");
+        GB2_ARG(h, std::isfinite(T.eta) && std::isfinite(T.tau), "eta/tau must be finite");
+        D.kind = T.kind; D.d = T.d; D.n_lin = T.n_lin; D.n_coreg = T.n_coreg;
+        D.eta2 = T.eta * T.eta; D.tau = T.n_lin > 0 ? T.tau : 0.0;
+        D.feat_off = n_feat;
+        pp.d[t] = T.d; pp.n_lin[t] = T.n_lin; pp.feat_off[t] = n_feat;
+        for (int i = 0; i < T.d; i++) {
+            GB2_ARG(h, T.ls[i] > 0 && std::isfinite(T.ls[i]), "lengthscales must be positive and finite");
+            GB2_ARG(h, T.cont_idx[i] >= 0, "negative cont_idx");
+            pp.cont_idx[t][i] = T.cont_idx[i];
+            pp.inv_ls[t][i] = 1.0 / T.ls[i];
+        }
+        for (int l = 0; l < T.n_lin; l++) {
+            GB2_ARG(h, T.lin_idx[l] >= 0 && std::isfinite(T.c[l]), "bad linear kernel parameters");
+            pp.lin_idx[t][l] = T.lin_idx[l];
+            pp.c[t][l] = T.c[l];
+        }
+        n_feat += T.d + 1 + T.n_lin;
+        for (int f = 0; f < T.n_coreg; f++) {
+            GB2_ARG(h, T.coreg_P[f] >= 1 && T.coreg_P[f] <= GB2_MAX_P && T.coreg_B[f] && T.coreg_col[f] >= 0, "bad Coregion factor");
+            D.cg_cat[f] = cat_row(T.coreg_col[f], T.coreg_P[f]);
+            D.cg_P[f] = T.coreg_P[f];
+            D.cg_Boff[f] = (int)btab.size();
+            btab.insert(btab.end(), T.coreg_B[f], T.coreg_B[f] + T.coreg_P[f] * T.coreg_P[f]);
+        }
+    }
+    kp.sigma2 = k->sigma * k->sigma;
+    kp.jitter = k->jitter;
+    kp.noise_cat = -1;
+    if (k->noise_col >= 0) {
+        GB2_ARG(h, k->noise_P >= 1 && k->noise_P <= GB2_MAX_P && k->noise_B, "bad noise Coregion");
+        kp.noise_cat = cat_row(k->noise_col, k->noise_P);
+        kp.noise_P = k->noise_P;
+        kp.noise_Boff = (int)btab.size();
+        btab.insert(btab.end(), k->noise_B, k->noise_B + k->noise_P * k->noise_P);
+    }
+    for (double b : btab) GB2_ARG(h, std::isfinite(b), "Coregion table holds a non-finite value");
+    kp.n_feat = n_feat; kp.n_cat = n_cat;
+    pp.n_cat = n_cat;
+    GB2_ARG(h, kbuild_smem_bytes(kp) <= 160 * 1024, "too many features per point for the K-build tile");
+    GB2_CUDA(h, cudaSetDevice(h->device));
+    if (btab.empty()) btab.push_back(1.0);
+    if ((int)btab.size() > h->btab_len) {
+        if (h->dBtab) GB2_CUDA(h, cudaFree(h->dBtab));
+        h->dBtab = nullptr;
+        GB2_CUDA(h, cudaMalloc(&h->dBtab, btab.size() * sizeof(double)));
+        h->btab_len = (int)btab.size();
+    }
+    GB2_CUDA(h, cudaMemcpyAsync(h->dBtab, btab.data(), btab.size() * sizeof(double), cudaMemcpyHostToDevice, h->s_main));
+    GB2_CUDA(h, cudaStreamSynchronize(h->s_main));
+    h->kp = kp; h->pp = pp;
+    h->have_kernel = true; h->factorized = false;
+    return 0;
+}
+
+static int build_K(gb2_handle* h, int& launches) {
+    const int64_t Np = h->Np, N = h->N;
+    cudaStream_t s = h->s_main;
+    h->pp.D_in = h->D_in;
+    int rc;
+    if ((rc = validate_against_train(h))) return rc;
+    if ((rc = ensure(h, h->dF, h->F_cap, (int64_t)std::max(1, h->kp.n_feat) * Np))) return rc;
+    if ((rc = ensure(h, h->dC, h->C_cap, (int64_t)std::max(1, h->kp.n_cat) * Np))) return rc;
+    if (h->A_cap < Np) {
+        if (h->dA) GB2_CUDA(h, cudaFree(h->dA));
+        if (h->dDinv) GB2_CUDA(h, cudaFree(h->dDinv));
+        h->dA = nullptr; h->dDinv = nullptr; h->A_cap = 0;
+        GB2_CUDA(h, cudaMalloc(&h->dA, (size_t)Np * Np * sizeof(double)));
+        GB2_CUDA(h, cudaMalloc(&h->dDinv, (size_t)Np * TILE * sizeof(double)));
+        h->A_cap = Np;
+    }
+    GB2_CUDA(h, cudaMemsetAsync(h->dInfo, 0, 4 * sizeof(int), s));
+    GB2_CUDA(h, cudaEventRecord(h->ev[0], s));
+    prep_features<<<(unsigned)((Np + 255) / 256), 256, 0, s>>>(h->dX, N, Np, h->pp, h->dF, h->dC, h->dInfo + 1);
+    GB2_CUDA(h, cudaEventRecord(h->ev[1], s));
+    dim3 grid((unsigned)(Np / KB_T), (unsigned)(Np / KB_T));
+    kbuild_kernel<true><<<grid, KB_THREADS, kbuild_smem_bytes(h->kp), s>>>(h->kp, h->dBtab, h->dF, h->dC, Np, N, h->dF, h->dC, Np, N, h->dy,
+                                                                            h->dA, Np);
+    GB2_CUDA(h, cudaEventRecord(h->ev[2], s));
+    launches += 2;
+    return 0;
+}
+
+int gb2_factorize(gb2_handle* h) {
+    if (!h) return -1;
+    GB2_ARG(h, h->have_train, "gb2_factorize: no training data (call gb2_set_train)");
+    GB2_ARG(h, h->have_kernel, "gb2_factorize: no kernel (call gb2_set_kernel)");
+    GB2_CUDA(h, cudaSetDevice(h->device));
+    h->factorized = false;
+    int launches = 0, rc;
+    if ((rc = build_K(h, launches))) return rc;
+    launches += cholesky_enqueue(h);
+    GB2_CUDA(h, cudaEventRecord(h->ev[3], h->s_main));
+    int info[2] = {0, 0};
+    GB2_CUDA(h, cudaMemcpyAsync(info, h->dInfo, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->s_main));
+    GB2_CUDA(h, cudaGetLastError());
+    GB2_CUDA(h, cudaStreamSynchronize(h->s_main));
+    h->timings[0] = ms_between(h->ev[0], h->ev[1]);
+    h->timings[1] = ms_between(h->ev[1], h->ev[2]);
+    h->timings[2] = ms_between(h->ev[2], h->ev[3]);
+    h->timings[6] = launches;
+    GB2_ARG(h, info[1] == 0, "a Coregion column of X holds a level index outside [0, P)");
+    if (info[0] != 0) {
+        h->err = "matrix is not positive definite: leading minor of order " + std::to_string(info[0]);
+        return info[0];
+    }
+    h->factorized = true;
+    return 0;
+}
+
+int gb2_mll(gb2_handle* h, double* out) {
+    if (!h) return -1;
+    GB2_ARG(h, out, "out is null");
+    GB2_ARG(h, h->factorized, "gb2_mll called before a successful gb2_factorize");
+    GB2_CUDA(h, cudaSetDevice(h->device));
+    double sc[2];
+    GB2_CUDA(h, cudaMemcpy(sc, h->dScal, 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    *out = -0.5 * (double)h->N * 1.8378770664093454836 - sc[0] - 0.5 * sc[1];
+    return 0;
+}
+
+int gb2_predict(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_noise, double* mean, double* var) {
+    if (!h) return -1;
+    return predict_common(h, Xs, M, pred_noise, mean, var, false);
+}
+
+int gb2_predict_dev(gb2_handle* h, const double* dXs, int64_t M, int32_t pred_noise, double* dmean, double* dvar) {
+    if (!h) return -1;
+    return predict_common(h, dXs, M, pred_noise, dmean, dvar, true);
+}
+
+int gb2_get_K(gb2_handle* h, double* K_out) {
+    if (!h) return -1;
+    GB2_ARG(h, K_out, "null pointer");
+    GB2_ARG(h, h->have_train && h->have_kernel, "gb2_get_K needs training data and a kernel");
+    GB2_CUDA(h, cudaSetDevice(h->device));
+    int launches = 0, rc;
+    h->factorized = false;  // the factor storage is overwritten
+    if ((rc = build_K(h, launches))) return rc;
+    const int64_t N = h->N, Np = h->Np;
+    GB2_CUDA(h, cudaMemcpy2DAsync(K_out, N * sizeof(double), h->dA, Np * sizeof(double), N * sizeof(double), N, cudaMemcpyDeviceToHost, h->s_main));
+    GB2_CUDA(h, cudaStreamSynchronize(h->s_main));
+    for (int64_t i = 0; i < N; i++)
+        for (int64_t j = i + 1; j < N; j++) K_out[i * N + j] = K_out[j * N + i];
+    return 0;
+}
+
+int gb2_get_L(gb2_handle* h, double* L_out) {
+    if (!h) return -1;
+    GB2_ARG(h, L_out, "null pointer");
+    GB2_ARG(h, h->factorized, "gb2_get_L called before a successful gb2_factorize");
+    GB2_CUDA(h, cudaSetDevice(h->device));
+    const int64_t N = h->N, Np = h->Np;
+    GB2_CUDA(h, cudaMemcpy2D(L_out, N * sizeof(double), h->dA, Np * sizeof(double), N * sizeof(double), N, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < N; i++)
+        for (int64_t j = i + 1; j < N; j++) L_out[i * N + j] = 0.0;
+    return 0;
+}
+
+int gb2_get_v(gb2_handle* h, double* v_out) {
+    if (!h) return -1;
+    GB2_ARG(h, v_out, "null pointer");
+    GB2_ARG(h, h->factorized, "gb2_get_v called before a successful gb2_factorize");
+    GB2_CUDA(h, cudaSetDevice(h->device));
+    GB2_CUDA(h, cudaMemcpy(v_out, h->dA + h->N * h->Np, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int gb2_get_timings(gb2_handle* h, double* out) {
+    if (!h || !out) return -1;
+    for (int i = 0; i < GB2_N_TIMINGS; i++) out[i] = h->timings[i];
+    return 0;
+}
+
+int gb2_set_option(gb2_handle* h, const char* name, int value) {
+    if (!h || !name) return -1;
+    if (!strcmp(name, "lookahead")) { h->opt_lookahead = value ? 1 : 0; return 0; }
+    h->err = std::string("unknown option: ") + name;
+    return -1;
+}
+
+}  // extern "C"

@@ -1,0 +1,117 @@
+// Internal declarations shared by the kernels of the gumbi_b200 core (one translation unit).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/gumbi_b200.h"
+
+namespace gb2 {
+
+constexpr int TILE = 128;  // matrix padding granule and Cholesky block size (rows/cols)
+
+// ---------------------------------------------------------------------------------------------
+// Device-side description of the covariance function.  Passed by value as a kernel parameter.
+// Per point i the "feature table" F (doubles, one row per feature, point index contiguous) holds,
+// for every term: d scaled coordinates x/ls, the squared norm of those, and n_lin centred linear
+// coordinates x-c.  The "category table" C (int32) holds one row per distinct Coregion column.
+// ---------------------------------------------------------------------------------------------
+struct TermDev {
+    int kind, d, n_lin, n_coreg;
+    int feat_off;                   // first feature row of this term
+    int cg_cat[GB2_MAX_COREG];      // category-table row used by Coregion factor f
+    int cg_P[GB2_MAX_COREG];
+    int cg_Boff[GB2_MAX_COREG];     // offset (doubles) of its P*P table in Btab
+    double eta2, tau;
+};
+
+struct KParams {
+    int n_terms, n_feat, n_cat;
+    int noise_cat, noise_P, noise_Boff;   // noise_cat < 0: homoskedastic
+    double sigma2, jitter;
+    TermDev t[GB2_MAX_TERMS];
+};
+
+// Host-built recipe for the feature-prep kernel (column gathers + scaling).
+struct PrepParams {
+    int n_terms, n_cat, D_in;
+    int d[GB2_MAX_TERMS], n_lin[GB2_MAX_TERMS], feat_off[GB2_MAX_TERMS];
+    int cont_idx[GB2_MAX_TERMS][GB2_MAX_D];
+    double inv_ls[GB2_MAX_TERMS][GB2_MAX_D];
+    int lin_idx[GB2_MAX_TERMS][GB2_MAX_LIN];
+    double c[GB2_MAX_TERMS][GB2_MAX_LIN];
+    int cat_col[GB2_MAX_TERMS * GB2_MAX_COREG + 1];
+    int cat_P[GB2_MAX_TERMS * GB2_MAX_COREG + 1];
+};
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+}  // namespace gb2
+
+struct gb2_handle {
+    int device = 0;
+    int precision = GB2_FP64;
+    cudaStream_t s_main = nullptr, s_panel = nullptr;
+    std::string err;
+
+    // training set
+    int64_t N = 0, Np = 0;   // Np = round_up(N+1, TILE): row N carries y (augmented system), rest is identity padding
+    int D_in = 0;
+    double* dX = nullptr;    // (N, D_in) row-major
+    double* dy = nullptr;    // (N)
+    bool have_train = false, have_kernel = false, factorized = false;
+
+    // kernel description
+    gb2::KParams kp{};
+    gb2::PrepParams pp{};
+    double* dBtab = nullptr;
+    int btab_len = 0;
+
+    // derived per-train-point tables
+    double* dF = nullptr;    // (n_feat, Np)
+    int* dC = nullptr;       // (n_cat, Np)
+    int64_t F_cap = 0, C_cap = 0;
+
+    // factor storage
+    double* dA = nullptr;    // (Np, Np) row-major; lower triangle holds K then L; row N holds y then v
+    int64_t A_cap = 0;       // allocated Np
+    double* dDinv = nullptr; // (Np/TILE, TILE, TILE) inverses of the diagonal blocks of L
+    int* dInfo = nullptr;    // first failing pivot (1-based), 0 if none
+    double* dScal = nullptr; // [0]=sum log L_ii, [1]=|v|^2
+
+    // predict scratch
+    double* dXs = nullptr; int64_t Xs_cap = 0;          // (M, D_in)
+    double* dFs = nullptr; int* dCs = nullptr; int64_t Fs_cap = 0, Cs_cap = 0;
+    double* dAt = nullptr; int64_t At_cap = 0;           // (Mp, Np) rows = test points
+    double* dMean = nullptr; double* dVar = nullptr; int64_t out_cap = 0;
+
+    // options
+    int opt_lookahead = 1;
+
+    // timing
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_panel[2] = {nullptr, nullptr}, ev_col[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_pool;
+    double timings[GB2_N_TIMINGS] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int64_t launches = 0;
+};
+
+#define GB2_CUDA(h, call)                                                                         \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ +   \
+                       ":" + std::to_string(__LINE__) + ")";                                     \
+            return -100 - (int)e__;                                                               \
+        }                                                                                         \
+    } while (0)
+
+#define GB2_ARG(h, cond, msg)                                                                     \
+    do {                                                                                          \
+        if (!(cond)) {                                                                            \
+            (h)->err = std::string("invalid argument: ") + (msg);                                \
+            return -1;                                                                            \
+        }                                                                                         \
+    } while (0)

@@ -1,0 +1,62 @@
+// Posterior mean / variance over a block of prediction points (Marginal._build_conditional):
+//   A = L^-1 K(X,X*),  mu = A^T v,  var = k** - colsum(A*A) (+ noise)
+// Stored transposed: At (Mp x Np) row-major, one row per prediction point, so that every operand of the solve is
+// K-contiguous for dgemm.cuh.  The solve  At <- At L^-T  is a recursive blocked TRSM: leaves multiply by the
+// inverted 128x128 diagonal blocks (computed during the factorisation), everything else is one large DMMA GEMM.
+#pragma once
+#include "cholesky.cuh"
+#include "kbuild.cuh"
+
+namespace gb2 {
+
+inline void trsm_rec(cudaStream_t s, const double* L, int64_t ld, const double* Dinv, double* At, int64_t ldt,
+                     int64_t Mp, int c0, int c1, int& launches) {
+    if (c1 - c0 == 1) {
+        double* X = At + (int64_t)c0 * TILE;
+        dgemm_nt_launch<64, 128, GM_SET>(s, X, ldt, Dinv + (int64_t)c0 * TILE * TILE, TILE, X, ldt, Mp, TILE, TILE, 0, 0, 0);
+        launches++;
+        return;
+    }
+    const int mid = c0 + (c1 - c0 + 1) / 2;
+    trsm_rec(s, L, ld, Dinv, At, ldt, Mp, c0, mid, launches);
+    dgemm_nt_launch<128, 64, GM_SUB>(s, At + (int64_t)c0 * TILE, ldt, L + (int64_t)mid * TILE * ld + (int64_t)c0 * TILE, ld,
+                                     At + (int64_t)mid * TILE, ldt, Mp, (int64_t)(c1 - mid) * TILE, (mid - c0) * TILE, 0, 0, 0);
+    launches++;
+    trsm_rec(s, L, ld, Dinv, At, ldt, Mp, mid, c1, launches);
+}
+
+// One warp per prediction point: mean = sum_i At[m,i] v[i], var = kss - sum_i At[m,i]^2 (+ noise diag).
+__global__ void __launch_bounds__(256)
+posterior_reduce_kernel(KParams kp, const double* __restrict__ Btab, const double* __restrict__ Fs,
+                        const int* __restrict__ Cs, int64_t stride_s, const double* __restrict__ At, int64_t ldt,
+                        const double* __restrict__ v, int64_t n, int64_t M, int pred_noise,
+                        double* __restrict__ mean, double* __restrict__ var) {
+    const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (m >= M) return;
+    const int lane = threadIdx.x & 31;
+    const double* row = At + m * ldt;
+    double mu = 0.0, ss = 0.0;
+    for (int64_t i = 2 * lane; i < n; i += 64) {  // n is even-aligned by construction of ldt; tail handled below
+        if (i + 1 < n) {
+            const double2 a = *reinterpret_cast<const double2*>(row + i);
+            const double2 w = *reinterpret_cast<const double2*>(v + i);
+            mu = fma(a.x, w.x, mu); ss = fma(a.x, a.x, ss);
+            mu = fma(a.y, w.y, mu); ss = fma(a.y, a.y, ss);
+        } else {
+            const double a = row[i];
+            mu = fma(a, v[i], mu); ss = fma(a, a, ss);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mu += __shfl_xor_sync(0xffffffffu, mu, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if (lane == 0) {
+        double kss, nz;
+        point_diag(kp, Btab, Fs, Cs, stride_s, m, kss, nz);
+        mean[m] = mu;
+        var[m] = (kss - ss) + (pred_noise ? nz : 0.0);
+    }
+}
+
+}  // namespace gb2

@@ -1,0 +1,137 @@
+"""GPEngine: one fitted-model handle on one B200, over the C ABI.
+
+Mirrors what ``pm.gp.Marginal`` does for ``PymcGP`` (gumbi/regression/pymc/GP.py:580, :845-847) but keeps the
+factor ``L`` and ``v = L^-1 y`` resident in HBM between calls (the reference rebuilds and re-factorises on
+every ``predict``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+TIMING_KEYS = ("prep_ms", "kbuild_ms", "cholesky_ms", "kstar_ms", "solve_ms", "reduce_ms", "launches_factorize", "launches_predict")
+
+
+def _c_f64(a, ndim=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if ndim is not None and a.ndim != ndim:
+        raise ValueError(f"expected a {ndim}-D array, got shape {a.shape}")
+    return a
+
+
+class GPEngine:
+    """Opaque handle owner.  ``precision`` is "fp64" (default) or "tf32"."""
+
+    def __init__(self, device: int = 0, precision: str = "fp64"):
+        self._lib = _lib.load()
+        if precision not in ("fp64", "tf32"):
+            raise ValueError('precision must be "fp64" or "tf32"')
+        self.precision = precision
+        self.device = int(device)
+        h = C.c_void_p()
+        rc = self._lib.gb2_create(C.byref(h), self.device, _lib.FP64 if precision == "fp64" else _lib.TF32)
+        if rc != 0:
+            msg = self._lib.gb2_last_error(None).decode()
+            raise _lib.BackendUnavailable(f"gb2_create failed ({rc}): {msg}")
+        self._h = h
+        self._keep = None
+        self.N = 0
+        self.D_in = 0
+
+    # -- lifetime ------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gb2_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc == 0:
+            return
+        msg = self._lib.gb2_last_error(self._h).decode()
+        if rc > 0:
+            # same exception type the reference surfaces from scipy/pytensor's Cholesky
+            raise np.linalg.LinAlgError(f"{what}: {msg}")
+        if rc == -1:
+            raise ValueError(f"{what}: {msg}")
+        raise RuntimeError(f"{what} failed ({rc}): {msg}")
+
+    # -- data / hyper-parameters ----------------------------------------------------------------------
+    def set_train(self, X, y):
+        X = _c_f64(np.atleast_2d(X), 2)
+        y = _c_f64(y).reshape(-1)
+        if X.shape[0] != y.shape[0]:
+            raise ValueError(f"X has {X.shape[0]} rows but y has {y.shape[0]} entries")
+        if not (np.all(np.isfinite(X)) and np.all(np.isfinite(y))):
+            raise ValueError("X and y must be finite (get_shaped_data drops NaN rows, base.py:469-471)")
+        self._check(self._lib.gb2_set_train(self._h, _lib.as_dp(X), X.shape[0], X.shape[1], _lib.as_dp(y)), "set_train")
+        self.N, self.D_in = X.shape
+
+    def set_train_device(self, dX_ptr: int, N: int, D_in: int, dy_ptr: int):
+        """Device-resident inputs (e.g. ``torch.Tensor.data_ptr()`` of float64 C-contiguous CUDA tensors)."""
+        self._check(self._lib.gb2_set_train_dev(self._h, C.c_void_p(dX_ptr), N, D_in, C.c_void_p(dy_ptr)), "set_train_dev")
+        self.N, self.D_in = int(N), int(D_in)
+
+    def set_kernel(self, spec: dict):
+        k, keep = _lib.make_kernel_struct(spec)
+        self._check(self._lib.gb2_set_kernel(self._h, C.byref(k)), "set_kernel")
+        self._keep = (k, keep)
+
+    def set_option(self, name: str, value: int):
+        self._check(self._lib.gb2_set_option(self._h, name.encode(), int(value)), "set_option")
+
+    # -- compute --------------------------------------------------------------------------------------
+    def factorize(self):
+        self._check(self._lib.gb2_factorize(self._h), "factorize")
+
+    def mll(self) -> float:
+        out = C.c_double()
+        self._check(self._lib.gb2_mll(self._h, C.byref(out)), "mll")
+        return out.value
+
+    def predict(self, Xs, pred_noise: bool = True):
+        Xs = _c_f64(np.atleast_2d(Xs), 2)
+        if Xs.shape[1] != self.D_in:
+            raise ValueError(f"points_array has {Xs.shape[1]} columns, model has {self.D_in} dims")
+        if not np.all(np.isfinite(Xs)):
+            raise ValueError("points_array must be finite")
+        M = Xs.shape[0]
+        mean = np.empty(M, dtype=np.float64)
+        var = np.empty(M, dtype=np.float64)
+        self._check(self._lib.gb2_predict(self._h, _lib.as_dp(Xs), M, int(bool(pred_noise)), _lib.as_dp(mean), _lib.as_dp(var)), "predict")
+        return mean, var
+
+    def predict_device(self, dXs_ptr: int, M: int, pred_noise: bool, dmean_ptr: int, dvar_ptr: int):
+        self._check(
+            self._lib.gb2_predict_dev(self._h, C.c_void_p(dXs_ptr), int(M), int(bool(pred_noise)), C.c_void_p(dmean_ptr), C.c_void_p(dvar_ptr)),
+            "predict_dev",
+        )
+
+    # -- test hooks -----------------------------------------------------------------------------------
+    def get_K(self):
+        K = np.empty((self.N, self.N), dtype=np.float64)
+        self._check(self._lib.gb2_get_K(self._h, _lib.as_dp(K)), "get_K")
+        return K
+
+    def get_L(self):
+        L = np.empty((self.N, self.N), dtype=np.float64)
+        self._check(self._lib.gb2_get_L(self._h, _lib.as_dp(L)), "get_L")
+        return L
+
+    def get_v(self):
+        v = np.empty(self.N, dtype=np.float64)
+        self._check(self._lib.gb2_get_v(self._h, _lib.as_dp(v)), "get_v")
+        return v
+
+    def timings(self) -> dict:
+        out = np.zeros(_lib.N_TIMINGS, dtype=np.float64)
+        self._check(self._lib.gb2_get_timings(self._h, _lib.as_dp(out)), "get_timings")
+        return dict(zip(TIMING_KEYS, out.tolist()))

@@ -1,0 +1,130 @@
+/* gumbi_b200 -- C ABI of the B200-native exact-GP inference core.
+ *
+ * The reference (JohnGoertz/Gumbi @ 27bdbee) has no FFI: its hot path leaves the repo through
+ * Python calls into PyMC (gumbi/regression/pymc/GP.py).  Each entry point below names the reference
+ * call it replaces; the Python-side binding a maintainer would add is in INTEGRATION.md
+ * (gumbi_b200/_lib.py is that binding, via ctypes).
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok; > 0 = LAPACK-style "leading minor of order k is not
+ *     positive definite" (first failing pivot, 1-based); < 0 = argument / CUDA / NCCL error, text
+ *     via gb2_last_error().
+ *   - plain pointers + sizes only; no exceptions, no Python or torch types cross this boundary.
+ *   - host-pointer entry points copy in/out synchronously; *_dev entry points take device pointers
+ *     on the handle's device and are ordered on the handle's stream (they return after the stream
+ *     has drained unless documented otherwise).
+ *   - the caller owns every buffer it passes; the handle owns all device memory it allocates.
+ *   - one handle = one GPU = one pair of CUDA streams; handles share no mutable global state.
+ *   - matrices are C-contiguous (row-major) float64, indices int32, exactly as numpy hands them
+ *     over from Regressor.get_shaped_data (gumbi/regression/base.py:435-471).
+ */
+#ifndef GUMBI_B200_H
+#define GUMBI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GB2_ABI_VERSION 1
+
+/* continuous_kernel= of PymcGP.fit (gumbi/regression/pymc/GP.py:266, :664-684) */
+enum gb2_kind {
+    GB2_EXPQUAD = 0,     /* pm.gp.cov.ExpQuad      exp(-r^2/2)                               */
+    GB2_MATERN52 = 1,    /* pm.gp.cov.Matern52     (1+sqrt5 r+5/3 r^2) exp(-sqrt5 r)          */
+    GB2_MATERN32 = 2,    /* pm.gp.cov.Matern32     (1+sqrt3 r) exp(-sqrt3 r)                  */
+    GB2_MATERN12 = 3,    /* pm.gp.cov.Matern12     exp(-r)                                    */
+    GB2_EXPONENTIAL = 4  /* pm.gp.cov.Exponential  exp(-r/2)                                  */
+};
+
+enum gb2_precision {
+    GB2_FP64 = 0,        /* everything IEEE fp64 (DMMA tensor path for the contractions)      */
+    GB2_TF32 = 1         /* tf32 tensor-core Cholesky trailing update (tcgen05), fp64 elsewhere */
+};
+
+#define GB2_MAX_TERMS 4
+#define GB2_MAX_D 16
+#define GB2_MAX_LIN 8
+#define GB2_MAX_COREG 3
+#define GB2_MAX_P 16
+
+/* One additive term  (eta^2 k_cont(ls) [+ tau Linear(c)]) * prod_f Coregion_f
+ * = what PymcGP._construct_kernels builds per GP (GP.py:711-727, :739-750).            */
+typedef struct gb2_term {
+    int32_t kind;                         /* enum gb2_kind                                      */
+    int32_t d;                            /* # active continuous columns (<= GB2_MAX_D)         */
+    int32_t cont_idx[GB2_MAX_D];          /* active_dims of the stationary kernel (GP.py:410)   */
+    double ls[GB2_MAX_D];                 /* lengthscale per active column (ARD=False: repeat)  */
+    double eta;                           /* cov = eta**2 * k  (GP.py:409-410)                  */
+    int32_t n_lin;                        /* # linear columns (0 = no Linear kernel)            */
+    int32_t lin_idx[GB2_MAX_LIN];         /* active_dims of pm.gp.cov.Linear (GP.py:453)        */
+    double c[GB2_MAX_LIN];                /* Linear offset c                                    */
+    double tau;                           /* tau * Linear                                       */
+    int32_t n_coreg;                      /* # Coregion factors multiplying this term           */
+    int32_t coreg_col[GB2_MAX_COREG];     /* column of X holding the level index (GP.py:462)    */
+    int32_t coreg_P[GB2_MAX_COREG];       /* # levels                                           */
+    const double* coreg_B[GB2_MAX_COREG]; /* host ptr, P*P row-major, B = W W^T + diag(kappa)   */
+} gb2_term;
+
+typedef struct gb2_kernel {
+    int32_t n_terms;                      /* 1, or 1 + #categorical dims when additive=True     */
+    gb2_term terms[GB2_MAX_TERMS];
+    double sigma;                         /* pm.gp.cov.WhiteNoise(sigma)  (GP.py:560-561)       */
+    int32_t noise_col;                    /* -1, or column for the Output_noise Coregion (:569) */
+    int32_t noise_P;
+    const double* noise_B;                /* host ptr, P*P (only the diagonal is used)          */
+    double jitter;                        /* pm.gp.util.stabilize JITTER_DEFAULT = 1e-6         */
+} gb2_kernel;
+
+typedef struct gb2_handle gb2_handle;
+
+int gb2_abi_version(void);
+
+/* Lifetime.  device = CUDA ordinal.  Replaces nothing in the reference (it keeps no state: F8). */
+int gb2_create(gb2_handle** out, int device, int precision);
+int gb2_destroy(gb2_handle* h);
+const char* gb2_last_error(const gb2_handle* h); /* h may be NULL: last create() error */
+
+/* Training data X:(N,D_in), y:(N,) as produced by Regressor.get_shaped_data (base.py:435-471),
+ * which PymcGP.build_model hands to gp.marginal_likelihood("ml", X=X, y=y, ...) (GP.py:521,580). */
+int gb2_set_train(gb2_handle* h, const double* X, int64_t N, int32_t D_in, const double* y);
+int gb2_set_train_dev(gb2_handle* h, const double* dX, int64_t N, int32_t D_in, const double* dy);
+
+/* Hyper-parameters = the point=self.MAP argument of Marginal.predict (GP.py:845-847) /
+ * one L-BFGS-B iterate of pm.find_MAP (GP.py:811).                                              */
+int gb2_set_kernel(gb2_handle* h, const gb2_kernel* k);
+
+/* K(X,X)+Knoise+jitter build -> Cholesky -> v = L^-1 y.  Replaces the first half of
+ * Marginal._build_conditional and MvNormal.logp's factorisation (GP.py:580, :845).             */
+int gb2_factorize(gb2_handle* h);
+
+/* log p(y | X, theta) = -N/2 log 2pi - sum log L_ii - 1/2 |v|^2 ; needs gb2_factorize.
+ * Replaces the "ml" term evaluated by pm.find_MAP (GP.py:580,811).                             */
+int gb2_mll(gb2_handle* h, double* out);
+
+/* Posterior mean/variance at Xs:(M,D_in) -- replaces PymcGP.predict (GP.py:837-849):
+ * Marginal.predict(Xs, point=MAP, diag=True, pred_noise=with_noise).  Needs gb2_factorize.     */
+int gb2_predict(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_noise, double* mean, double* var);
+int gb2_predict_dev(gb2_handle* h, const double* dXs, int64_t M, int32_t pred_noise, double* dmean, double* dvar);
+
+/* Test hooks: copy the dense objects back (row-major, n x n with n = N).  The strict upper
+ * triangle is returned as zero for L and mirrored for K.                                        */
+int gb2_get_K(gb2_handle* h, double* K_out);   /* rebuilds K+Knoise+jitter into scratch; O(N^2)  */
+int gb2_get_L(gb2_handle* h, double* L_out);
+int gb2_get_v(gb2_handle* h, double* v_out);   /* v = L^-1 y, length N                           */
+
+/* Device-side milliseconds (CUDA events on the handle's stream) of the phases of the most recent
+ * gb2_factorize / gb2_predict*: out[0]=feature prep, [1]=K build, [2]=Cholesky(+v),
+ * [3]=K* build, [4]=triangular solve, [5]=mean/var reduction, [6]=#kernel launches of the last
+ * factorize, [7]=#kernel launches of the last predict.                                          */
+#define GB2_N_TIMINGS 8
+int gb2_get_timings(gb2_handle* h, double* out);
+
+/* Tunables (for benchmarking/ablation): name in {"lookahead","graph"}; returns <0 if unknown.   */
+int gb2_set_option(gb2_handle* h, const char* name, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GUMBI_B200_H */
