@@ -52,7 +52,7 @@ class Kernel(C.Structure):
 EXPORTS = [
     "gb2_abi_version", "gb2_create", "gb2_destroy", "gb2_last_error", "gb2_set_train", "gb2_set_train_dev",
     "gb2_set_kernel", "gb2_factorize", "gb2_mll", "gb2_predict", "gb2_predict_dev", "gb2_get_K", "gb2_get_L",
-    "gb2_get_v", "gb2_get_timings", "gb2_set_option",
+    "gb2_get_v", "gb2_get_timings", "gb2_set_option", "gb2_mark", "gb2_elapsed_ms",
 ]
 
 _lib = None
@@ -96,6 +96,8 @@ def load():
     lib.gb2_get_v.argtypes = [H, dp]
     lib.gb2_get_timings.argtypes = [H, dp]
     lib.gb2_set_option.argtypes = [H, C.c_char_p, C.c_int]
+    lib.gb2_mark.argtypes = [H, C.c_int]
+    lib.gb2_elapsed_ms.argtypes = [H, C.c_int, C.c_int, dp]
     for name in EXPORTS:
         if name not in ("gb2_last_error",):
             getattr(lib, name).restype = C.c_int

@@ -1,0 +1,356 @@
+"""``B200GP``: the Gumbi ``Regressor`` backend whose dense path runs on the CUDA core.
+
+Host-side mirror of ``gumbi.regression.pymc.GP.PymcGP`` (gumbi/regression/pymc/GP.py:21-979) for the hot path only:
+``fit`` (:255-387), ``build_model`` (:468-583), ``_construct_kernels`` (:652-757), ``find_MAP`` (:799-813) and
+``predict`` (:837-849) keep their names, arguments, ``MAP`` keys and error behaviour, but no PyMC model is built: the
+kernel composition is lowered to the plain ``spec`` dict of ``gumbi_b200._lib.make_kernel_struct`` and everything
+O(N^2) and up happens behind the C ABI on the GPU.  There is no CPU fallback.
+
+Two ways to use it:
+
+* inside Gumbi (drop-in):  ``B200GP = gumbi_b200.make_backend(gumbi.regression.base.Regressor)`` gives a third
+  ``Regressor`` subclass next to ``PymcGP``/``BotorchGP``; ``specify_model``, ``get_shaped_data``, ``prepare_grid``,
+  ``predict_points``, ``predict_grid``, ``cross_validate`` ... are inherited unchanged.
+* stand-alone on shaped arrays (what the tests on the GPU box do, where Gumbi is not installed):
+  ``ArrayGP(X, y, continuous_dims=..., ...)`` -- a minimal stand-in for the state ``specify_model`` leaves behind.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .engine import GPEngine
+
+CONTINUOUS_KERNELS = ["ExpQuad", "Matern12", "Matern32", "Matern52", "Exponential"]
+JITTER_DEFAULT = 1e-6  # pymc.gp.util.JITTER_DEFAULT
+
+
+def assert_in(name, value, allowed):
+    """Same message shape as gumbi.utils.misc.assert_in (used at pymc/GP.py:674)."""
+    if value not in allowed:
+        raise ValueError(f"{name} must be one of {allowed}, got {value!r}")
+
+
+class B200Backend:
+    """Mixin with the three backend methods + ``fit``.  Expects the attributes ``Regressor.specify_model`` sets."""
+
+    # -- construction -----------------------------------------------------------------------------------------------
+    def _init_backend(self, device=0, precision="fp64"):
+        self.device = device
+        self.precision = precision
+        self.engine = None
+        self.MAP = None
+        self.trace = None
+        self.gp_dict = None
+        self.model = None
+        self.continuous_kernel = "ExpQuad"
+        self.heteroskedastic_inputs = False
+        self.heteroskedastic_outputs = True
+        self.sparse = False
+        self.latent = False
+        self.n_u = 100
+        self.ARD = True
+        self._factor_key = None
+        self.model_specs = {
+            "seed": self.seed,
+            "continuous_kernel": self.continuous_kernel,
+            "heteroskedastic_inputs": self.heteroskedastic_inputs,
+            "heteroskedastic_outputs": self.heteroskedastic_outputs,
+            "sparse": self.sparse,
+            "n_u": self.n_u,
+        }
+
+    # -- fit (GP.py:255-387) ------------------------------------------------------------------------------------------
+    def fit(self, outputs=None, linear_dims=None, continuous_dims=None, continuous_levels=None, continuous_coords=None,
+            categorical_dims=None, categorical_levels=None, additive=False, seed=None, continuous_kernel="ExpQuad",
+            period=None, heteroskedastic_inputs=False, heteroskedastic_outputs=True, sparse=False, n_u=100, ARD=True,
+            ls_bounds=None, mass=0.98, spec_kwargs=None, build_kwargs=None, MAP_kwargs=None):
+        self.specify_model(outputs=outputs, linear_dims=linear_dims, continuous_dims=continuous_dims,
+                           continuous_levels=continuous_levels, continuous_coords=continuous_coords,
+                           categorical_dims=categorical_dims, categorical_levels=categorical_levels, additive=additive,
+                           **(spec_kwargs or {}))
+        self.build_model(seed=seed, continuous_kernel=continuous_kernel, period=period,
+                         heteroskedastic_inputs=heteroskedastic_inputs, heteroskedastic_outputs=heteroskedastic_outputs,
+                         sparse=sparse, n_u=n_u, ARD=ARD, ls_bounds=ls_bounds, mass=mass, **(build_kwargs or {}))
+        self.find_MAP(**(MAP_kwargs or {}))
+        return self
+
+    # -- build_model (GP.py:468-583) ----------------------------------------------------------------------------------
+    def build_model(self, seed=None, continuous_kernel="ExpQuad", period=None, heteroskedastic_inputs=False,
+                    heteroskedastic_outputs=True, sparse=False, n_u=100, ARD=True, ls_bounds=None, mass=0.98):
+        if heteroskedastic_inputs:
+            raise NotImplementedError("Heteroskedasticity over inputs is not yet implemented.")
+        if sparse:
+            raise NotImplementedError("The B200 backend implements the exact (dense) GP only; sparse=True is out of scope.")
+        if period is not None or str(continuous_kernel).endswith("Periodic"):
+            raise NotImplementedError("Periodic kernels are not implemented in the B200 backend.")
+        assert_in("Continuous kernel", continuous_kernel, CONTINUOUS_KERNELS)
+
+        X, y = self.get_shaped_data("mean")
+        D_in = len(self.dims)
+        assert X.shape[1] == D_in
+
+        seed = self.seed if seed is None else seed
+        self.seed = seed
+        self.continuous_kernel = continuous_kernel
+        self.heteroskedastic_inputs = heteroskedastic_inputs
+        self.heteroskedastic_outputs = heteroskedastic_outputs
+        self.sparse = sparse
+        self.n_u = n_u
+        self.latent = False
+        self.ARD = ARD
+        self.ls_bounds = ls_bounds
+        self.mass = mass
+        self.model_specs = {
+            "seed": seed,
+            "continuous_kernel": continuous_kernel,
+            "heteroskedastic_inputs": heteroskedastic_inputs,
+            "heteroskedastic_outputs": heteroskedastic_outputs,
+            "sparse": sparse,
+            "n_u": n_u,
+        }
+        self._X = np.ascontiguousarray(X, dtype=np.float64)
+        self._y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
+        self._layout = self._model_layout()
+        if self.engine is None:
+            self.engine = GPEngine(self.device, self.precision)
+        self.engine.set_train(self._X, self._y)
+        self._factor_key = None
+        self.model = self._layout  # truthy placeholder: the reference asserts ``self.model is not None`` in find_MAP
+        return self
+
+    # -- structure of the covariance (GP.py:652-757) ------------------------------------------------------------------
+    def _get_dim_counts(self):
+        return {"l": len(self.linear_dims), "s": len(self.continuous_dims), "c": len(self.categorical_dims),
+                "p": len(self.outputs)}
+
+    def _get_dim_indexes(self):
+        return {
+            "l": [self.dims.index(dim) for dim in self.linear_dims],
+            "s": [self.dims.index(dim) for dim in self.continuous_dims],
+            "c": [self.dims.index(dim) for dim in self.categorical_dims],
+            "p": self.dims.index(self.out_col) if self.out_col in self.dims else None,
+        }
+
+    def _model_layout(self):
+        """Which random variables exist and how they combine -- the structure ``_construct_kernels`` builds.
+
+        Returns a list of terms; each term is ``{"suffix", "coreg": [(name, col, P), ...]}`` where ``name`` keys the
+        ``W_<name>``/``kappa`` entries of MAP.  The output Coregion (``W_<out_col>``) is shared by all terms (:724-727,:749).
+        """
+        ns, idxs = self._get_dim_counts(), self._get_dim_indexes()
+        multi = self.out_col in self.categorical_dims
+        out_cg = (self.out_col, idxs["p"], len(self.categorical_levels[self.out_col])) if multi else None
+        terms = []
+        total = {"suffix": "total", "coreg": []}
+        if ns["c"] > 0 and not self.additive:
+            for dim, idx in zip(self.categorical_dims, idxs["c"]):
+                if dim == self.out_col:
+                    continue
+                total["coreg"].append((dim, idx, len(self.categorical_levels[dim])))
+        if multi:
+            total["coreg"].append(out_cg)
+        terms.append(total)
+        if self.additive:
+            for dim, idx in zip(self.categorical_dims, idxs["c"]):
+                if dim == self.out_col:
+                    continue
+                t = {"suffix": dim, "coreg": [(dim, idx, len(self.categorical_levels[dim]))]}
+                if multi:
+                    t["coreg"].append(out_cg)
+                terms.append(t)
+        noise_cg = None
+        if self.heteroskedastic_outputs and multi:
+            noise_cg = ("Output_noise", idxs["p"], out_cg[2])
+        return {"terms": terms, "noise_coreg": noise_cg, "idx_s": idxs["s"], "idx_l": idxs["l"], "n_s": ns["s"],
+                "n_l": ns["l"]}
+
+    def param_shapes(self):
+        """Names and shapes of the free hyper-parameters, in the order PyMC would register them."""
+        lay = self._layout
+        shapes = {}
+        seen = set()
+        for t in lay["terms"]:
+            sfx = t["suffix"]
+            shapes[f"ls_{sfx}"] = (lay["n_s"] if self.ARD else 1,)
+            shapes[f"η_{sfx}"] = ()
+            if lay["n_l"] > 0:
+                shapes[f"c_{sfx}"] = (lay["n_l"],)
+                shapes[f"τ_{sfx}"] = ()
+            for name, _, P in t["coreg"]:
+                if name not in seen:
+                    seen.add(name)
+                    shapes[f"W_{name}"] = (P, 2)
+                    shapes[f"κ_{name}"] = (P,)
+        shapes["σ"] = ()
+        if lay["noise_coreg"]:
+            name, _, P = lay["noise_coreg"]
+            shapes[f"W_{name}"] = (P, 2)
+            shapes[f"κ_{name}"] = (P,)
+        return shapes
+
+    def spec_from_point(self, point):
+        """MAP-style dict of hyper-parameter values -> kernel ``spec`` for the CUDA core."""
+        lay = self._layout
+        terms = []
+        for t in lay["terms"]:
+            sfx = t["suffix"]
+            ls = np.atleast_1d(np.asarray(point[f"ls_{sfx}"], dtype=np.float64))
+            term = {"kind": self.continuous_kernel, "cont_idx": list(lay["idx_s"]), "ls": ls.tolist(),
+                    "eta": float(point[f"η_{sfx}"]), "lin_idx": [], "c": [], "tau": 0.0, "coreg": []}
+            if lay["n_l"] > 0:
+                term["lin_idx"] = list(lay["idx_l"])
+                term["c"] = np.atleast_1d(np.asarray(point[f"c_{sfx}"], dtype=np.float64)).tolist()
+                term["tau"] = float(point[f"τ_{sfx}"])
+            for name, col, _ in t["coreg"]:
+                term["coreg"].append({"col": col, "W": np.asarray(point[f"W_{name}"]).tolist(),
+                                      "kappa": np.asarray(point[f"κ_{name}"]).tolist()})
+            terms.append(term)
+        spec = {"terms": terms, "sigma": float(point["σ"]), "noise_coreg": None, "jitter": JITTER_DEFAULT}
+        if lay["noise_coreg"]:
+            name, col, _ = lay["noise_coreg"]
+            spec["noise_coreg"] = {"col": col, "W": np.asarray(point[f"W_{name}"]).tolist(),
+                                   "kappa": np.asarray(point[f"κ_{name}"]).tolist()}
+        return spec
+
+    # -- find_MAP (GP.py:799-813) -------------------------------------------------------------------------------------
+    def find_MAP(self, *args, **kwargs):
+        """Maximum a posteriori hyper-parameters (``pm.find_MAP``: L-BFGS-B on -(logp + log-priors), jacobian=False).
+
+        ``start=`` may carry initial values; ``point=`` pins the hyper-parameters outright (no optimisation), which is
+        how a maintainer feeds an existing PyMC ``MAP`` dict to this backend.
+        """
+        assert self.model is not None
+        point = kwargs.pop("point", None)
+        if point is not None:
+            self.MAP = self._complete_point(point)
+        else:
+            from .map import find_map  # local import: scipy only needed for fitting
+
+            self.MAP = find_map(self, *args, **kwargs)
+        self._factor_key = None
+        return self.MAP
+
+    def _complete_point(self, point):
+        shapes = self.param_shapes()
+        out = {}
+        for name, shape in shapes.items():
+            if name not in point:
+                raise KeyError(f"hyper-parameter {name!r} missing from point (expected {sorted(shapes)})")
+            val = np.asarray(point[name], dtype=np.float64)
+            if name.startswith("ls_") and val.size == 1:
+                val = val.reshape(1) if shape == (1,) else np.repeat(val.reshape(1), shape[0])
+            if val.shape != tuple(shape):
+                raise ValueError(f"hyper-parameter {name!r} has shape {val.shape}, expected {tuple(shape)}")
+            out[name] = val
+            if name.split("_")[0] in ("ls", "η", "τ", "κ", "σ"):
+                if np.any(val <= 0):
+                    raise ValueError(f"hyper-parameter {name!r} must be positive")
+                out[name + "_log__"] = np.log(val)  # pm.find_MAP also returns the transformed values
+        return out
+
+    # -- predict (GP.py:837-849) --------------------------------------------------------------------------------------
+    def _ensure_factorized(self):
+        if self.MAP is None:
+            raise RuntimeError("predict called before find_MAP/fit")
+        key = id(self.MAP)
+        if self._factor_key != key:
+            self.engine.set_kernel(self.spec_from_point(self.MAP))
+            self.engine.factorize()
+            self._factor_key = key
+
+    def predict(self, points_array, with_noise=True, additive_level="total", **kwargs):
+        if additive_level != "total":
+            raise NotImplementedError("Prediction for additive sublevels is not yet supported.")
+        if kwargs:
+            raise TypeError(f"unsupported predict arguments for the B200 backend: {sorted(kwargs)}")
+        self._ensure_factorized()
+        points_array = np.atleast_2d(np.asarray(points_array, dtype=np.float64))
+        return self.engine.predict(points_array, pred_noise=bool(with_noise))
+
+    def predict_cold(self, points_array, with_noise=True):
+        """What ONE reference ``predict`` call costs: rebuild K, re-factorise, solve.  For benchmarking."""
+        self._factor_key = None
+        return self.predict(points_array, with_noise=with_noise)
+
+    def marginal_log_likelihood(self, point=None):
+        """log p(y | X, theta) of ``gp.marginal_likelihood("ml", ...)`` (GP.py:580) at ``point`` (default: MAP)."""
+        if point is not None:
+            self.engine.set_kernel(self.spec_from_point(self._complete_point(point)))
+            self.engine.factorize()
+            self._factor_key = None
+        else:
+            self._ensure_factorized()
+        return self.engine.mll()
+
+
+class ArrayRegressor:
+    """Minimal stand-in for the state a ``gumbi.regression.base.Regressor`` holds after ``specify_model``.
+
+    It carries already-shaped arrays (what ``get_shaped_data`` returns, base.py:435-471) so that the backend can be
+    exercised where Gumbi itself is not installed (the GPU box).  Columns of ``X`` follow ``self.dims`` =
+    continuous_dims + categorical_dims, with the output column last (base.py:155-158).
+    """
+
+    def __init__(self, X, y, continuous_dims, linear_dims=None, categorical_dims=None, categorical_levels=None,
+                 out_col="Variable", outputs=None, additive=False, seed=2021):
+        self._X_shaped = np.atleast_2d(np.asarray(X, dtype=np.float64))
+        self._y_shaped = np.asarray(y, dtype=np.float64).reshape(-1)
+        self.continuous_dims = list(continuous_dims)
+        self.linear_dims = list(linear_dims or [])
+        self.categorical_dims = list(categorical_dims or [])
+        self.categorical_levels = dict(categorical_levels or {})
+        self.out_col = out_col
+        self.outputs = list(outputs or ["y"])
+        self.additive = additive
+        self.seed = seed
+        self.filter_dims = {}
+        self.model_specs = {}
+        if self._X_shaped.shape[1] != len(self.dims):
+            raise ValueError(f"X has {self._X_shaped.shape[1]} columns but dims = {self.dims}")
+        for dim in self.linear_dims:
+            if dim not in self.continuous_dims:
+                raise ValueError("linear_dims must be a subset of continuous_dims")
+
+    @property
+    def dims(self):
+        return self.continuous_dims + self.categorical_dims
+
+    def specify_model(self, **kwargs):
+        given = {k: v for k, v in kwargs.items() if v not in (None, False)}
+        if given:
+            raise TypeError(f"ArrayRegressor is specified at construction; got {sorted(given)}")
+
+    def get_shaped_data(self, metric="mean", dropna=True):
+        nans = np.isnan(self._y_shaped)
+        return self._X_shaped[~nans], self._y_shaped[~nans]
+
+
+class ArrayGP(B200Backend, ArrayRegressor):
+    def __init__(self, X, y, continuous_dims, device=0, precision="fp64", **kwargs):
+        ArrayRegressor.__init__(self, X, y, continuous_dims, **kwargs)
+        self._init_backend(device=device, precision=precision)
+
+
+def make_backend(regressor_base):
+    """Create the drop-in ``B200GP`` subclass of Gumbi's ``Regressor`` (``gumbi.regression.base.Regressor``)."""
+
+    class B200GP(B200Backend, regressor_base):
+        def __init__(self, dataset, outputs=None, seed=2021, device=0, precision="fp64"):
+            regressor_base.__init__(self, dataset, outputs, seed)
+            self._init_backend(device=device, precision=precision)
+
+    B200GP.__doc__ = "Gumbi Regressor backend running the exact-GP dense path on a B200 (see gumbi_b200.backend)."
+    return B200GP
+
+
+def __getattr__(name):
+    if name == "B200GP":  # resolved lazily so that importing gumbi_b200 never requires gumbi
+        try:
+            from gumbi.regression.base import Regressor
+        except Exception as e:  # pragma: no cover - depends on the environment
+            raise ImportError("gumbi is not importable; use gumbi_b200.ArrayGP or make_backend(Regressor)") from e
+        cls = make_backend(Regressor)
+        globals()["B200GP"] = cls
+        return cls
+    raise AttributeError(name)
+

@@ -180,6 +180,7 @@ int gb2_destroy(gb2_handle* h) {
     cudaFree(h->dAt); cudaFree(h->dMean); cudaFree(h->dVar);
     for (auto ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto ev : h->ev_pool) cudaEventDestroy(ev);
+    for (auto ev : h->ev_mark) if (ev) cudaEventDestroy(ev);
     if (h->s_main) cudaStreamDestroy(h->s_main);
     if (h->s_panel) cudaStreamDestroy(h->s_panel);
     delete h;
@@ -390,6 +391,26 @@ int gb2_get_v(gb2_handle* h, double* v_out) {
 int gb2_get_timings(gb2_handle* h, double* out) {
     if (!h || !out) return -1;
     for (int i = 0; i < GB2_N_TIMINGS; i++) out[i] = h->timings[i];
+    return 0;
+}
+
+int gb2_mark(gb2_handle* h, int slot) {
+    if (!h) return -1;
+    GB2_ARG(h, slot >= 0 && slot < 4, "mark slot must be in [0, 4)");
+    GB2_CUDA(h, cudaSetDevice(h->device));
+    if (!h->ev_mark[slot]) GB2_CUDA(h, cudaEventCreate(&h->ev_mark[slot]));
+    GB2_CUDA(h, cudaEventRecord(h->ev_mark[slot], h->s_main));
+    return 0;
+}
+
+int gb2_elapsed_ms(gb2_handle* h, int a, int b, double* ms) {
+    if (!h) return -1;
+    GB2_ARG(h, ms && a >= 0 && a < 4 && b >= 0 && b < 4 && h->ev_mark[a] && h->ev_mark[b], "bad marks");
+    GB2_CUDA(h, cudaSetDevice(h->device));
+    GB2_CUDA(h, cudaEventSynchronize(h->ev_mark[b]));
+    float f = 0.f;
+    GB2_CUDA(h, cudaEventElapsedTime(&f, h->ev_mark[a], h->ev_mark[b]));
+    *ms = (double)f;
     return 0;
 }
 

@@ -94,6 +94,7 @@ struct gb2_handle {
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_panel[2] = {nullptr, nullptr}, ev_col[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> ev_pool;
+    cudaEvent_t ev_mark[4] = {nullptr, nullptr, nullptr, nullptr};
     double timings[GB2_N_TIMINGS] = {0, 0, 0, 0, 0, 0, 0, 0};
     int64_t launches = 0;
 };

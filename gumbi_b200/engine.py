@@ -115,6 +115,15 @@ class GPEngine:
             "predict_dev",
         )
 
+    def mark(self, slot: int):
+        """Record a timing mark on the handle's stream (device-side timing for benchmarks)."""
+        self._check(self._lib.gb2_mark(self._h, int(slot)), "mark")
+
+    def elapsed_ms(self, a: int, b: int) -> float:
+        out = C.c_double()
+        self._check(self._lib.gb2_elapsed_ms(self._h, int(a), int(b), C.byref(out)), "elapsed_ms")
+        return out.value
+
     # -- test hooks -----------------------------------------------------------------------------------
     def get_K(self):
         K = np.empty((self.N, self.N), dtype=np.float64)

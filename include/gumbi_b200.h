@@ -121,6 +121,11 @@ int gb2_get_v(gb2_handle* h, double* v_out);   /* v = L^-1 y, length N          
 #define GB2_N_TIMINGS 8
 int gb2_get_timings(gb2_handle* h, double* out);
 
+/* Stream-ordered timing marks for benchmarks: gb2_mark(h, slot) records a CUDA event (slot 0..3) on the handle's
+ * main stream; gb2_elapsed_ms synchronises on mark b and returns the device time between marks a and b.          */
+int gb2_mark(gb2_handle* h, int slot);
+int gb2_elapsed_ms(gb2_handle* h, int a, int b, double* ms);
+
 /* Tunables (for benchmarking/ablation): name in {"lookahead","graph"}; returns <0 if unknown.   */
 int gb2_set_option(gb2_handle* h, const char* name, int value);
 

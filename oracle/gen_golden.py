@@ -1,0 +1,219 @@
+"""Generate tests/golden/*.npz  --  TEST INFRASTRUCTURE ONLY; run in the build container (needs /root/reference).
+
+For each case the reference's OWN wrapper layers (DataSet / Standardizer / Regressor.specify_model /
+get_shaped_data / prepare_grid / _prepare_points_for_prediction, imported unmodified from /root/reference with the
+plotting + PyMC imports stubbed) produce the standardized arrays that cross the backend boundary
+(gumbi/regression/base.py:574), the numpy oracle (oracle/gp_oracle.py) produces the posterior at a fixed,
+seed-derived hyper-parameter point, and the reference's predict_points post-processing (base.py:578-601) turns that
+into un-standardized uparray fields.  Everything is stored so that the GPU box (no reference, no gumbi) can replay it.
+
+    python oracle/gen_golden.py            # rewrites tests/golden/*.npz
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import types
+from unittest.mock import MagicMock
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def import_reference():
+    """Stub the absent third-party imports, then import gumbi from the read-only reference tree."""
+    if "gumbi" in sys.modules:
+        return sys.modules["gumbi"]
+
+    def stub(name):
+        m = types.ModuleType(name)
+        m.__path__ = []
+        m.__getattr__ = lambda attr: MagicMock()
+        sys.modules[name] = m
+        return m
+
+    for n in ["matplotlib", "matplotlib.pyplot", "seaborn", "uncertainties", "uncertainties.unumpy", "pymc", "pytensor",
+              "pytensor.tensor", "gpytorch", "gpytorch.priors", "gpytorch.priors.prior", "gpytorch.priors.utils",
+              "botorch"]:
+        try:
+            __import__(n)
+        except Exception:
+            stub(n)
+    if isinstance(getattr(sys.modules.get("gpytorch.priors.prior"), "Prior", None), MagicMock):
+        sys.modules["gpytorch.priors.prior"].Prior = type("Prior", (), {})
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, REF)
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import gumbi
+    return gumbi
+
+
+def fixed_point(shapes, seed):
+    """Deterministic hyper-parameters of plausible magnitude (not a MAP: the oracle is evaluated AT this point)."""
+    rng = np.random.default_rng(seed)
+    pt = {}
+    for name, shape in shapes.items():
+        base = name.split("_")[0]
+        if base == "ls":
+            pt[name] = rng.uniform(0.7, 2.5, size=shape)
+        elif base == "η":
+            pt[name] = np.asarray(rng.uniform(0.8, 1.6))
+        elif base == "c":
+            pt[name] = rng.normal(0, 0.5, size=shape)
+        elif base == "τ":
+            pt[name] = np.asarray(rng.uniform(0.05, 0.5))
+        elif base == "W":
+            pt[name] = rng.standard_normal(size=shape) * (0.3 if "noise" in name else 1.0)
+        elif base == "κ":
+            pt[name] = rng.uniform(0.5, 1.5, size=shape)
+        elif base == "σ":
+            pt[name] = np.asarray(rng.uniform(0.08, 0.3))
+        else:
+            raise KeyError(name)
+    return pt
+
+
+def main():
+    sys.path.insert(0, ROOT)
+    gmb = import_reference()
+    import pandas as pd
+    from gumbi.regression.base import Regressor
+
+    from gumbi_b200.backend import B200Backend
+    from oracle import gp_oracle as orc
+
+    class OracleEngine:
+        """Stands where GPEngine stands, answers with the numpy oracle (generation only -- never shipped)."""
+
+        def set_train(self, X, y):
+            self.X, self.y = X, y
+
+        def set_kernel(self, spec):
+            self.spec = spec
+
+        def factorize(self):
+            self.L, self.v = orc.factorize(self.spec, self.X, self.y)
+
+        def predict(self, Xs, pred_noise=True):
+            return orc.conditional(self.spec, self.X, self.L, self.v, Xs, pred_noise)
+
+        def mll(self):
+            return orc.mll(self.spec, self.X, self.y)
+
+    class GoldenGP(B200Backend, Regressor):
+        def __init__(self, dataset, outputs=None, seed=2021):
+            Regressor.__init__(self, dataset, outputs, seed)
+            self._init_backend()
+            self.engine = OracleEngine()
+
+    os.makedirs(OUT, exist_ok=True)
+
+    def dump(name, gp, point, points_array, extra):
+        spec = gp.spec_from_point(gp.MAP)
+        mu, var = gp.predict(points_array, with_noise=True)
+        mu_nf, var_nf = gp.predict(points_array, with_noise=False)
+        meta = {
+            "continuous_dims": gp.continuous_dims, "linear_dims": gp.linear_dims, "categorical_dims": gp.categorical_dims,
+            "categorical_levels": {k: list(map(str, v)) for k, v in gp.categorical_levels.items()},
+            "categorical_coords": {k: {str(a): int(b) for a, b in v.items()} for k, v in gp.categorical_coords.items()},
+            "out_col": gp.out_col, "outputs": gp.outputs, "additive": bool(gp.additive),
+            "continuous_kernel": gp.continuous_kernel, "ARD": bool(gp.ARD), "spec": spec,
+            "point": {k: np.asarray(v).tolist() for k, v in point.items()},
+            "generator": "oracle/gen_golden.py", "reference_commit": "27bdbee",
+        }
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), X=gp._X, y=gp._y, points=points_array, mean=mu, var=var,
+                            mean_noisefree=mu_nf, var_noisefree=var_nf, mll=np.asarray(gp.marginal_log_likelihood()),
+                            meta=np.asarray(json.dumps(meta, ensure_ascii=False)), **extra)
+        print(f"{name}: X{gp._X.shape} points{points_array.shape} mll={gp.marginal_log_likelihood():.6f}")
+
+    # ---- 1. Simple_Regression notebook (docs/source/notebooks/examples/Simple_Regression.pct.py:34-63) -------------
+    df = pd.read_pickle(os.path.join(REF, "gumbi", "data", "Example_DataSet.pkl")).query('Metric=="mean"')
+    outputs = ["a", "b", "c", "d", "e", "f"]
+    log_vars = ["Y", "b", "c", "d", "f"]
+    logit_vars = ["X", "e"]
+    ds = gmb.DataSet(df, outputs=outputs, log_vars=log_vars, logit_vars=logit_vars)
+    ds.tidy = ds.tidy[ds.tidy.Color.isin(["cyan", "magenta"]) & (ds.tidy.Pair == "burrata+barbaresco")]
+    for kern in ("ExpQuad", "Matern52"):
+        gp = GoldenGP(ds, outputs=["d"])
+        gp.specify_model(continuous_dims=["X", "Y", "lg10_Z"], linear_dims=["X", "Y", "lg10_Z"])
+        gp.build_model(continuous_kernel=kern)
+        point = fixed_point(gp.param_shapes(), 11)
+        gp.find_MAP(point=point)
+        gp.prepare_grid(at=gp.parray(lg10_Z=8, X=0.5))
+        pts_grid, _, _ = gp._prepare_points_for_prediction(gp.grid_points, output=gp._parse_prediction_output(None))
+        pts_one, _, _ = gp._prepare_points_for_prediction(gp.parray(lg10_Z=8, X=0.5, Y=88), output=gp._parse_prediction_output(None))
+        points_array = np.vstack([pts_one, pts_grid])
+        # reference post-processing of the same predictions (base.py:578-601): natural-space mean and z-space fields
+        up = gp.predict_points(gp.grid_points)
+        extra = {"post_mu_z": np.asarray(up.z["μ"] if "μ" in up.z.dtype.names else up["μ"]),
+                 "post_mu_natural": np.asarray(up["μ"]), "post_sigma2": np.asarray(up["σ2"])}
+        dump(f"simple_regression_{kern}", gp, point, points_array, extra)
+
+    # ---- 2. Multioutput_Regression notebook (Multioutput_Regression.pct.py:40-100) ---------------------------------
+    df = pd.read_pickle(os.path.join(REF, "gumbi", "data", "Example_DataSet.pkl"))
+    df = df[(df.Name == "binary-pollen") & (df.Color == "cyan") & (df.Metric == "mean")]
+    ds = gmb.DataSet(df, outputs=outputs, log_vars=log_vars, logit_vars=logit_vars)
+    fit_params = ["a", "b", "c", "d", "e"]
+    gp = GoldenGP(ds, outputs=fit_params)
+    gp.specify_model(continuous_dims="lg10_Z", linear_dims="lg10_Z")
+    gp.build_model()
+    point = fixed_point(gp.param_shapes(), 12)
+    gp.find_MAP(point=point)
+    gp.prepare_grid(limits=gp.parray(lg10_Z=[1, 9]), resolution=17)
+    out = gp._parse_prediction_output(None)
+    points_array, _, _ = gp._prepare_points_for_prediction(gp.grid_points, output=out)
+    dump("multioutput_regression", gp, point, points_array, {})
+
+    # ---- 3. reference test fixture (tests/test_regression.py:13-45, :94-112, :158-166) ------------------------------
+    example_stdzr = {
+        "a": {"μ": -0.762, "σ2": 1.258 ** 2}, "b": {"μ": -0.0368, "σ2": 0.351 ** 2}, "c": {"μ": -5.30, "σ2": 0.582 ** 2},
+        "d": {"μ": -0.307, "σ2": 0.158 ** 2}, "e": {"μ": -1.056, "σ2": 0.398 ** 2}, "f": {"μ": 3.34, "σ2": 0.1501 ** 2},
+        "X": {"μ": -0.282, "σ2": 1 ** 2}, "Y": {"μ": 4.48, "σ2": 0.75 ** 2}, "lg10_Z": {"μ": 5, "σ2": 2 ** 2},
+    }
+    es = pd.read_pickle(os.path.join(REF, "tests", "test_data", "test_dataset.pkl"))
+    stdzr = gmb.Standardizer(**example_stdzr, log_vars=["d", "f", "b", "c", "Y"], logit_vars=["e", "X"])
+    ds = gmb.DataSet.from_tidy(es, names_column="Parameter", stdzr=stdzr)
+    # Joint and additive categorical structure with two outputs (the shape of tests/test_regression.py:158-166).  The
+    # reference test uses the NUMERIC column lg10_Z as the categorical dim; its coords are then the level values
+    # themselves, get z-scored by get_shaped_data (base.py:464) and truncated by Coregion's int32 cast into indices
+    # {1,0,0,-1}: the test only asserts "runs".  A string-valued categorical dim (Color) gives the 0..P-1 coords the
+    # Coregion kernel is meant to see, so that is what the golden cases pin.
+    dfc = pd.read_pickle(os.path.join(REF, "gumbi", "data", "Example_DataSet.pkl"))
+    dfc = dfc[(dfc.Pair == "burrata+merlot") & (dfc.Metric == "mean")]
+    dsc = gmb.DataSet(dfc, outputs=outputs, log_vars=log_vars, logit_vars=logit_vars)
+    for additive in (False, True):
+        gp = GoldenGP(dsc, outputs=["d", "c"])
+        gp.specify_model(outputs=["d", "c"], continuous_dims=["X", "Y", "lg10_Z"], linear_dims=["Y"] if additive else None,
+                         categorical_dims="Color", additive=additive)
+        gp.build_model(continuous_kernel="Matern32" if additive else "ExpQuad")
+        point = fixed_point(gp.param_shapes(), 13)
+        gp.find_MAP(point=point)
+        ygrid = np.geomspace(12.0, 160.0, 20)
+        blocks = []
+        for lvl, coord in gp.categorical_coords["Color"].items():
+            pts = gp.parray(X=np.full(20, 0.5), Y=ygrid, lg10_Z=np.full(20, 8.0), Color=np.full(20, float(coord)), stdzd=False)
+            pa, _, _ = gp._prepare_points_for_prediction(pts, output=gp._parse_prediction_output(None))
+            blocks.append(pa)
+        points_array = np.vstack(blocks)
+        dump("categorical_additive" if additive else "categorical_joint", gp, point, points_array, {})
+
+    # single-level filter case: tests/test_regression.py:108-112 (continuous_levels filters lg10_Z to one level)
+    gp = GoldenGP(ds, outputs="d")
+    gp.specify_model(continuous_dims=["X", "Y", "lg10_Z"], continuous_levels={"lg10_Z": [8]})
+    gp.build_model(ARD=False)
+    point = fixed_point(gp.param_shapes(), 14)
+    gp.find_MAP(point=point)
+    gp.prepare_grid(resolution=15)
+    points_array, _, _ = gp._prepare_points_for_prediction(gp.grid_points, output=gp._parse_prediction_output(None))
+    dump("test_dataset_filtered", gp, point, points_array, {})
+
+
+if __name__ == "__main__":
+    main()
