@@ -12,79 +12,232 @@
 
 namespace gb2 {
 
-constexpr int PD_THREADS = 512;
-constexpr int PD_LD = TILE + 1;  // padded shared row
-constexpr size_t PD_SMEM = (size_t)TILE * PD_LD * sizeof(double) + TILE * sizeof(double);
-
-// Factor the diagonal block starting at global index g0 (in place, lower), then invert it into Dinv (dense 128x128,
-// strict upper triangle zero).  Columns with global index >= n_real (the y row and the identity padding) get pivot 1.
+// ---------------------------------------------------------------------------------------------------------------
+// Diagonal-panel kernel: factor one 128x128 diagonal block and invert the factor, entirely in shared memory.
+//
+// The block is held as 10 lower 32x32 sub-blocks (row stride 34 doubles: rows are 16-byte aligned, and a lane-per-row
+// LDS.128 sweep touches every bank exactly once per quarter-warp).  Work is organised as in a textbook right-looking
+// blocked Cholesky with inner block 32:
+//   potrf32   one warp, lane r owns row r in registers, column broadcast through a double-buffered shared column
+//   trsm32    one warp per sub-block below, lane r owns row r: x <- x L_pp^-T by forward substitution (axpy form)
+//   inv32     one warp, lane c owns column c of inv(L_pp)
+//   update    C_ij -= L_ip L_jp^T as 32x32x32 block products, split in 8-column units over all 16 warps
+// and then the inverse of the 128x128 factor is assembled from the four 32x32 inverses with block products
+//   X_ij = -X_ii ( sum_{k=j..i-1} L_ik X_kj ).
+// Columns with global index >= n_real (the y row of the augmented system and the identity padding) get pivot 1.
 // A non-positive pivot records info = global column + 1 (first one wins) and is replaced by 1 so that the rest of the
 // pipeline stays finite; the host turns info into LinAlgError.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int PD_THREADS = 512;
+constexpr int PB = 32;                 // inner block
+constexpr int PB_LD = 34;              // row stride of a sub-block, doubles
+constexpr int PB_SZ = PB * PB_LD;
+constexpr int PD_NBLK = 10;            // lower sub-blocks of a 4x4 block grid
+constexpr size_t PD_SMEM = (size_t)(2 * PD_NBLK + 3) * PB_SZ * sizeof(double) + (TILE + 2 * 2 * PB) * sizeof(double);
+
+__device__ __forceinline__ int pd_blk(int i, int j) { return i * (i + 1) / 2 + j; }
+
+// One unit of a block product: C[r][c0..c0+7] (op)= sum_k A[r][k] B[k][c0..c0+7], lane = r.
+//   MODE 0: C -= AB   1: C = AB   2: C += AB   3: C = -(AB)
+template <int MODE>
+__device__ __forceinline__ void pd_unit(double* C, const double* A, const double* B, int c0, int lane) {
+    double a[PB];
+    const double2* ar = reinterpret_cast<const double2*>(A + lane * PB_LD);
+#pragma unroll
+    for (int q = 0; q < PB / 2; q++) { const double2 v = ar[q]; a[2 * q] = v.x; a[2 * q + 1] = v.y; }
+    double acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) acc[q] = 0.0;
+#pragma unroll
+    for (int k = 0; k < PB; k++) {
+        const double2* br = reinterpret_cast<const double2*>(B + k * PB_LD + c0);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const double2 v = br[q];
+            acc[2 * q] = fma(a[k], v.x, acc[2 * q]);
+            acc[2 * q + 1] = fma(a[k], v.y, acc[2 * q + 1]);
+        }
+    }
+    __syncwarp();  // C may alias B (in-place stages): every lane has finished reading before any lane writes
+    double2* cr = reinterpret_cast<double2*>(C + lane * PB_LD + c0);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        double2 v;
+        if (MODE == 1) v = make_double2(acc[2 * q], acc[2 * q + 1]);
+        else if (MODE == 3) v = make_double2(-acc[2 * q], -acc[2 * q + 1]);
+        else {
+            v = cr[q];
+            if (MODE == 0) { v.x -= acc[2 * q]; v.y -= acc[2 * q + 1]; }
+            else { v.x += acc[2 * q]; v.y += acc[2 * q + 1]; }
+        }
+        cr[q] = v;
+    }
+}
+
 __global__ void __launch_bounds__(PD_THREADS, 1)
 potrf_diag_kernel(double* __restrict__ A, int64_t ld, int64_t g0, int64_t n_real, double* __restrict__ Dinv,
                   int* __restrict__ info) {
     extern __shared__ __align__(16) unsigned char pd_smem[];
-    double* S = reinterpret_cast<double*>(pd_smem);
-    double* col = S + TILE * PD_LD;
-    const int tid = threadIdx.x;
+    double* Lb = reinterpret_cast<double*>(pd_smem);     // 10 sub-blocks of the factor
+    double* Xb = Lb + PD_NBLK * PB_SZ;                    // 10 sub-blocks of its inverse
+    double* Tb = Xb + PD_NBLK * PB_SZ;                    // 3 transposed panel sub-blocks (k-major operand of the update)
+    double* rdiag = Tb + 3 * PB_SZ;                       // 1 / L[j][j]
+    double* colbuf = rdiag + TILE;                        // 2 x 2 x 32: double-buffered column broadcast (potrf32, inv32)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = PD_THREADS / 32;
     double* Ab = A + g0 * ld + g0;
-    for (int e = tid; e < TILE * TILE; e += PD_THREADS) {
-        int r = e >> 7, c = e & 127;
-        S[r * PD_LD + c] = (c <= r) ? Ab[(int64_t)r * ld + c] : 0.0;
+
+    // ---- load the lower sub-blocks (256-byte coalesced rows); strict upper parts of diagonal sub-blocks are zeroed
+    for (int e = tid; e < PD_NBLK * PB * PB; e += PD_THREADS) {
+        const int b = e >> 10, r = (e >> 5) & 31, c = e & 31;
+        int bi = 0;
+        while ((bi + 1) * (bi + 2) / 2 <= b) bi++;
+        const int bj = b - bi * (bi + 1) / 2;
+        double v = 0.0;
+        if (bi != bj || c <= r) v = Ab[(int64_t)(bi * PB + r) * ld + bj * PB + c];
+        Lb[b * PB_SZ + r * PB_LD + c] = v;
     }
     __syncthreads();
 
-    for (int j = 0; j < TILE; j++) {
-        double p = S[j * PD_LD + j];
-        if (g0 + j >= n_real) {
-            p = 1.0;
-        } else if (!(p > 0.0)) {
-            if (tid == 0) atomicCAS(info, 0, (int)(g0 + j + 1));
-            p = 1.0;
+    for (int p = 0; p < 4; p++) {
+        double* Lpp = Lb + pd_blk(p, p) * PB_SZ;
+        // ---- potrf32: warp 0, lane r owns row r
+        if (warp == 0) {
+            double a[PB];
+            const double2* ar = reinterpret_cast<const double2*>(Lpp + lane * PB_LD);
+#pragma unroll
+            for (int q = 0; q < PB / 2; q++) { const double2 v = ar[q]; a[2 * q] = v.x; a[2 * q + 1] = v.y; }
+#pragma unroll
+            for (int c = 0; c < PB; c++) {
+                double* cb = colbuf + (c & 1) * PB;
+                double d = __shfl_sync(0xffffffffu, a[c], c);
+                const int64_t gcol = g0 + p * PB + c;
+                if (gcol >= n_real) {
+                    d = 1.0;
+                } else if (!(d > 0.0)) {
+                    if (lane == 0) atomicCAS(info, 0, (int)(gcol + 1));
+                    d = 1.0;
+                }
+                const double rs = rsqrt(d);
+                a[c] = (lane == c) ? d * rs : a[c] * rs;
+                if (lane == c) rdiag[p * PB + c] = rs;
+                cb[lane] = a[c];
+                __syncwarp();
+#pragma unroll
+                for (int c2 = (c + 1) & ~1; c2 < PB; c2 += 2) {
+                    const double2 l = *reinterpret_cast<const double2*>(cb + c2);
+                    if (c2 > c) a[c2] = fma(-a[c], l.x, a[c2]);
+                    a[c2 + 1] = fma(-a[c], l.y, a[c2 + 1]);
+                }
+            }
+            double* wr = Lpp + lane * PB_LD;
+#pragma unroll
+            for (int c = 0; c < PB; c++) wr[c] = (c <= lane) ? a[c] : 0.0;
         }
-        const double ljj = sqrt(p);
-        const double inv = 1.0 / ljj;
-        __syncthreads();  // everyone has read the pivot before it is overwritten
-        if (tid == 0) S[j * PD_LD + j] = ljj;
-        for (int r = j + 1 + tid; r < TILE; r += PD_THREADS) S[r * PD_LD + j] *= inv;
         __syncthreads();
-        const int n = TILE - 1 - j;
-        for (int e = tid; e < n * n; e += PD_THREADS) {
-            const int rr = e / n, cc = e - rr * n;
-            if (cc <= rr) {
-                const int r = j + 1 + rr, c = j + 1 + cc;
-                S[r * PD_LD + c] = fma(-S[r * PD_LD + j], S[c * PD_LD + j], S[r * PD_LD + c]);
+
+        // ---- inv32 (warp 0: column `lane` of inv(L_pp)) || trsm32 (warps 1..3-p: rows of the sub-blocks below)
+        if (warp == 0) {
+            double b[PB];
+#pragma unroll
+            for (int k = 0; k < PB; k++) b[k] = (k == lane) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < PB; k++) {
+                b[k] *= rdiag[p * PB + k];
+#pragma unroll
+                for (int r = k + 1; r < PB; r++) b[r] = fma(-Lpp[r * PB_LD + k], b[k], b[r]);
+            }
+            double* X = Xb + pd_blk(p, p) * PB_SZ;
+#pragma unroll
+            for (int r = 0; r < PB; r++) X[r * PB_LD + lane] = b[r];   // X[r][c=lane]; zero above the diagonal
+        } else if (warp <= 3 - p) {
+            const int i = p + warp;
+            double* Lip = Lb + pd_blk(i, p) * PB_SZ;
+            double x[PB];
+            const double2* ar = reinterpret_cast<const double2*>(Lip + lane * PB_LD);
+#pragma unroll
+            for (int q = 0; q < PB / 2; q++) { const double2 v = ar[q]; x[2 * q] = v.x; x[2 * q + 1] = v.y; }
+#pragma unroll
+            for (int k = 0; k < PB; k++) {
+                x[k] *= rdiag[p * PB + k];
+#pragma unroll
+                for (int c = k + 1; c < PB; c++) x[c] = fma(-Lpp[c * PB_LD + k], x[k], x[c]);
+            }
+            double2* wr = reinterpret_cast<double2*>(Lip + lane * PB_LD);
+#pragma unroll
+            for (int q = 0; q < PB / 2; q++) wr[q] = make_double2(x[2 * q], x[2 * q + 1]);
+            double* T = Tb + (warp - 1) * PB_SZ;   // T[k][r] = L_ip[r][k]
+#pragma unroll
+            for (int k = 0; k < PB; k++) T[k * PB_LD + lane] = x[k];
+        }
+        __syncthreads();
+
+        // ---- trailing update inside the block: C_ij -= L_ip L_jp^T for p < j <= i, 4 column units per product
+        {
+            const int m = 3 - p;                      // sub-blocks below
+            const int n_units = m * (m + 1) / 2 * 4;
+            for (int u = warp; u < n_units; u += NW) {
+                const int op = u >> 2, chunk = u & 3;
+                int ii = 0;
+                while ((ii + 1) * (ii + 2) / 2 <= op) ii++;
+                const int jj = op - ii * (ii + 1) / 2;
+                const int i = p + 1 + ii, j = p + 1 + jj;
+                pd_unit<0>(Lb + pd_blk(i, j) * PB_SZ, Lb + pd_blk(i, p) * PB_SZ, Tb + (j - p - 1) * PB_SZ, chunk * 8, lane);
             }
         }
         __syncthreads();
     }
-    for (int e = tid; e < TILE * TILE; e += PD_THREADS) {
-        int r = e >> 7, c = e & 127;
-        if (c <= r) Ab[(int64_t)r * ld + c] = S[r * PD_LD + c];
+
+    // ---- factor back to global (lower triangle only)
+    for (int e = tid; e < PD_NBLK * PB * PB; e += PD_THREADS) {
+        const int b = e >> 10, r = (e >> 5) & 31, c = e & 31;
+        int bi = 0;
+        while ((bi + 1) * (bi + 2) / 2 <= b) bi++;
+        const int bj = b - bi * (bi + 1) / 2;
+        if (bi != bj || c <= r) Ab[(int64_t)(bi * PB + r) * ld + bj * PB + c] = Lb[b * PB_SZ + r * PB_LD + c];
+    }
+
+    // ---- assemble inv(L): T_ij = sum_k L_ik X_kj accumulated in Xb(i,j), then X_ij = -X_ii T_ij in place
+    auto X = [&](int i, int j) { return Xb + pd_blk(i, j) * PB_SZ; };
+    auto L = [&](int i, int j) { return Lb + pd_blk(i, j) * PB_SZ; };
+    // stage A: T_ij = L_ij X_jj for all i > j (6 products)
+    for (int u = warp; u < 24; u += NW) {
+        const int op = u >> 2, chunk = u & 3;
+        const int i = op < 1 ? 1 : (op < 3 ? 2 : 3);
+        const int j = op - (i == 1 ? 0 : (i == 2 ? 1 : 3));
+        pd_unit<1>(X(i, j), L(i, j), X(j, j), chunk * 8, lane);
     }
     __syncthreads();
-
-    // In-place inversion of the lower-triangular block, column by column from the right (LAPACK dtrti2 order):
-    //   X[j][j] = 1/L[j][j];   X[r][j] = -X[j][j] * sum_{k=j+1..r} X[r][k] L[k][j]
-    // 4 threads share a row r and split the dot product; shuffle-reduced.
-    for (int j = TILE - 1; j >= 0; j--) {
-        for (int r = j + tid; r < TILE; r += PD_THREADS) col[r] = S[r * PD_LD + j];
-        __syncthreads();
-        const double xjj = 1.0 / col[j];
-        const int r = j + 1 + (tid >> 2), part = tid & 3;
-        double s = 0.0;
-        if (r < TILE) {
-            for (int k = j + 1 + part; k <= r; k += 4) s = fma(S[r * PD_LD + k], col[k], s);
-        }
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (r < TILE && part == 0) S[r * PD_LD + j] = -s * xjj;
-        if (tid == 0) S[j * PD_LD + j] = xjj;
-        __syncthreads();
+    // stage B: X_{j+1,j} = -X_{j+1,j+1} T_{j+1,j}
+    for (int u = warp; u < 12; u += NW) {
+        const int j = u >> 2, chunk = u & 3;
+        pd_unit<3>(X(j + 1, j), X(j + 1, j + 1), X(j + 1, j), chunk * 8, lane);
     }
+    __syncthreads();
+    // stage C1: T_{j+2,j} += L_{j+2,j+1} X_{j+1,j}
+    for (int u = warp; u < 8; u += NW) {
+        const int j = u >> 2, chunk = u & 3;
+        pd_unit<2>(X(j + 2, j), L(j + 2, j + 1), X(j + 1, j), chunk * 8, lane);
+    }
+    __syncthreads();
+    // stage C2: X_{j+2,j} = -X_{j+2,j+2} T_{j+2,j}
+    for (int u = warp; u < 8; u += NW) {
+        const int j = u >> 2, chunk = u & 3;
+        pd_unit<3>(X(j + 2, j), X(j + 2, j + 2), X(j + 2, j), chunk * 8, lane);
+    }
+    __syncthreads();
+    // stage D: T_30 += L_31 X_10 + L_32 X_20 ; X_30 = -X_33 T_30   (a unit only touches its own 8 columns of X_30)
+    if (warp < 4) {
+        pd_unit<2>(X(3, 0), L(3, 1), X(1, 0), warp * 8, lane);
+        __syncwarp();
+        pd_unit<2>(X(3, 0), L(3, 2), X(2, 0), warp * 8, lane);
+        __syncwarp();
+        pd_unit<3>(X(3, 0), X(3, 3), X(3, 0), warp * 8, lane);
+    }
+    __syncthreads();
     for (int e = tid; e < TILE * TILE; e += PD_THREADS) {
-        int r = e >> 7, c = e & 127;
-        Dinv[e] = (c <= r) ? S[r * PD_LD + c] : 0.0;
+        const int r = e >> 7, c = e & 127;
+        Dinv[e] = (c <= r) ? Xb[pd_blk(r >> 5, c >> 5) * PB_SZ + (r & 31) * PB_LD + (c & 31)] : 0.0;
     }
 }
 
