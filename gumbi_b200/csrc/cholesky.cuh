@@ -15,13 +15,13 @@ namespace gb2 {
 // ---------------------------------------------------------------------------------------------------------------
 // Diagonal-panel kernel: factor one 128x128 diagonal block and invert the factor, entirely in shared memory.
 //
-// The block is held as 10 lower 32x32 sub-blocks (row stride 34 doubles: rows are 16-byte aligned, and a lane-per-row
-// LDS.128 sweep touches every bank exactly once per quarter-warp).  Work is organised as in a textbook right-looking
+// The block is held as 10 lower 32x32 sub-blocks (row stride 36 doubles: rows are 16-byte aligned and the 8x4 DMMA
+// fragment loads are bank-conflict free).  Work is organised as in a textbook right-looking
 // blocked Cholesky with inner block 32:
 //   potrf32   one warp, lane r owns row r in registers, column broadcast through a double-buffered shared column
 //   trsm32    one warp per sub-block below, lane r owns row r: x <- x L_pp^-T by forward substitution (axpy form)
 //   inv32     one warp, lane c owns column c of inv(L_pp)
-//   update    C_ij -= L_ip L_jp^T as 32x32x32 block products, split in 8-column units over all 16 warps
+//   update    C_ij -= L_ip L_jp^T as 32x32x32 block products on DMMA, split in 8-column units over all 16 warps
 // and then the inverse of the 128x128 factor is assembled from the four 32x32 inverses with block products
 //   X_ij = -X_ii ( sum_{k=j..i-1} L_ik X_kj ).
 // Columns with global index >= n_real (the y row of the augmented system and the identity padding) get pivot 1.
@@ -30,111 +30,163 @@ namespace gb2 {
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int PD_THREADS = 512;
 constexpr int PB = 32;                 // inner block
-constexpr int PB_LD = 34;              // row stride of a sub-block, doubles
+constexpr int PB_LD = 36;              // row stride of a sub-block, doubles (72 words = 8 mod 32: conflict-free DMMA fragments)
 constexpr int PB_SZ = PB * PB_LD;
 constexpr int PD_NBLK = 10;            // lower sub-blocks of a 4x4 block grid
-constexpr size_t PD_SMEM = (size_t)(2 * PD_NBLK + 3) * PB_SZ * sizeof(double) + (TILE + 2 * 2 * PB) * sizeof(double);
+// Lb (10 sub-blocks of the factor) + Xt (10 sub-blocks of the inverse, stored transposed) + Xd (4 diagonal inverses)
+constexpr size_t PD_SMEM = (size_t)(2 * PD_NBLK + 4) * PB_SZ * sizeof(double) + (TILE + 2 * PB) * sizeof(double);
 
 __device__ __forceinline__ int pd_blk(int i, int j) { return i * (i + 1) / 2 + j; }
 
-// One unit of a block product: C[r][c0..c0+7] (op)= sum_k A[r][k] B[k][c0..c0+7], lane = r.
-//   MODE 0: C -= AB   1: C = AB   2: C += AB   3: C = -(AB)
-template <int MODE>
-__device__ __forceinline__ void pd_unit(double* C, const double* A, const double* B, int c0, int lane) {
-    double a[PB];
-    const double2* ar = reinterpret_cast<const double2*>(A + lane * PB_LD);
+// Branch-free 1/sqrt(d): MUFU.RSQ64H seed (rsqrt.approx.ftz.f64, ~2^-22) + two Newton steps in fp64.  The library
+// rsqrt() carries a predicated slow-path CALL that pins it in program order; this version is straight-line code that
+// ptxas interleaves with the rank-1 update of the previous column.  d must be a normal positive number (pivots are).
+__device__ __forceinline__ double pd_rsqrt(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
 #pragma unroll
-    for (int q = 0; q < PB / 2; q++) { const double2 v = ar[q]; a[2 * q] = v.x; a[2 * q + 1] = v.y; }
-    double acc[8];
+    for (int it = 0; it < 2; it++) {
+        const double e = fma(-d * y, y, 1.0);
+        y = fma(0.5 * y, e, y);
+    }
+    return y;
+}
+
+// One unit of a block product on DMMA: a 32 x 8 slab  C[0..31][c0..c0+7] (op)= sum_k A[r][k] * Bt[c][k]
+// (both operands K-contiguous, row stride PB_LD), optionally followed by a second product accumulated in registers.
+//   OP 0: C -= P   1: C = P   2: C += P   3: C = -P          (P = the product(s))
+//   TR false: C is a normal sub-block  C[r*LD + c];  TR true: C is stored transposed  C[c*LD + r]
+//   G != nullptr: the slab is also written to global memory at G[r*ldg + c]  (row-major)
+template <int OP, bool TR>
+__device__ __forceinline__ void pd_unit(double* C, const double* A, const double* Bt, const double* A2, const double* Bt2,
+                                        int c0, int lane, double* G = nullptr, int ldg = 0) {
+    const int g = lane >> 2, t = lane & 3;
+    double acc[4][2];
 #pragma unroll
-    for (int q = 0; q < 8; q++) acc[q] = 0.0;
+    for (int mi = 0; mi < 4; mi++) acc[mi][0] = acc[mi][1] = 0.0;
+    const double* pa = A + g * PB_LD + t;
+    const double* pb = Bt + (c0 + g) * PB_LD + t;
 #pragma unroll
-    for (int k = 0; k < PB; k++) {
-        const double2* br = reinterpret_cast<const double2*>(B + k * PB_LD + c0);
+    for (int kk = 0; kk < PB / 4; kk++) {
+        const double bv = pb[kk * 4];
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const double2 v = br[q];
-            acc[2 * q] = fma(a[k], v.x, acc[2 * q]);
-            acc[2 * q + 1] = fma(a[k], v.y, acc[2 * q + 1]);
+        for (int mi = 0; mi < 4; mi++) dmma884(acc[mi][0], acc[mi][1], pa[mi * 8 * PB_LD + kk * 4], bv);
+    }
+    if (A2) {
+        pa = A2 + g * PB_LD + t;
+        pb = Bt2 + (c0 + g) * PB_LD + t;
+#pragma unroll
+        for (int kk = 0; kk < PB / 4; kk++) {
+            const double bv = pb[kk * 4];
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++) dmma884(acc[mi][0], acc[mi][1], pa[mi * 8 * PB_LD + kk * 4], bv);
         }
     }
-    __syncwarp();  // C may alias B (in-place stages): every lane has finished reading before any lane writes
-    double2* cr = reinterpret_cast<double2*>(C + lane * PB_LD + c0);
+    __syncwarp();  // C may alias Bt (in-place stages): every lane has finished reading before any lane writes
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        double2 v;
-        if (MODE == 1) v = make_double2(acc[2 * q], acc[2 * q + 1]);
-        else if (MODE == 3) v = make_double2(-acc[2 * q], -acc[2 * q + 1]);
+    for (int mi = 0; mi < 4; mi++) {
+        const int r = mi * 8 + g, c = c0 + 2 * t;
+        double v0, v1;
+        if (OP == 1) { v0 = acc[mi][0]; v1 = acc[mi][1]; }
+        else if (OP == 3) { v0 = -acc[mi][0]; v1 = -acc[mi][1]; }
         else {
-            v = cr[q];
-            if (MODE == 0) { v.x -= acc[2 * q]; v.y -= acc[2 * q + 1]; }
-            else { v.x += acc[2 * q]; v.y += acc[2 * q + 1]; }
+            if (TR) { v0 = C[c * PB_LD + r]; v1 = C[(c + 1) * PB_LD + r]; }
+            else { const double2 o = *reinterpret_cast<const double2*>(C + r * PB_LD + c); v0 = o.x; v1 = o.y; }
+            if (OP == 0) { v0 -= acc[mi][0]; v1 -= acc[mi][1]; }
+            else { v0 += acc[mi][0]; v1 += acc[mi][1]; }
         }
-        cr[q] = v;
+        if (TR) { C[c * PB_LD + r] = v0; C[(c + 1) * PB_LD + r] = v1; }
+        else *reinterpret_cast<double2*>(C + r * PB_LD + c) = make_double2(v0, v1);
+        if (G) *reinterpret_cast<double2*>(G + (int64_t)r * ldg + c) = make_double2(v0, v1);
     }
 }
 
 __global__ void __launch_bounds__(PD_THREADS, 1)
 potrf_diag_kernel(double* __restrict__ A, int64_t ld, int64_t g0, int64_t n_real, double* __restrict__ Dinv,
-                  int* __restrict__ info) {
+                  int* __restrict__ info, long long* __restrict__ clk = nullptr) {
     extern __shared__ __align__(16) unsigned char pd_smem[];
-    double* Lb = reinterpret_cast<double*>(pd_smem);     // 10 sub-blocks of the factor
-    double* Xb = Lb + PD_NBLK * PB_SZ;                    // 10 sub-blocks of its inverse
-    double* Tb = Xb + PD_NBLK * PB_SZ;                    // 3 transposed panel sub-blocks (k-major operand of the update)
-    double* rdiag = Tb + 3 * PB_SZ;                       // 1 / L[j][j]
-    double* colbuf = rdiag + TILE;                        // 2 x 2 x 32: double-buffered column broadcast (potrf32, inv32)
+    int clk_i = 0;
+#define PD_CLK() do { if (clk && threadIdx.x == 0) clk[clk_i++] = clock64(); } while (0)
+    PD_CLK();
+    double* Lb = reinterpret_cast<double*>(pd_smem);     // 10 sub-blocks of the factor, L_ij[r][k]
+    double* Xt = Lb + PD_NBLK * PB_SZ;                    // 10 sub-blocks of inv(L), transposed: Xt_ij[c][r] = X_ij[r][c]
+    double* Xd = Xt + PD_NBLK * PB_SZ;                    // the 4 diagonal sub-blocks of inv(L), not transposed
+    double* rdiag = Xd + 4 * PB_SZ;                       // 1 / L[j][j]
+    double* colbuf = rdiag + TILE;                        // 2 x 32: double-buffered column broadcast of potrf32
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = PD_THREADS / 32;
     double* Ab = A + g0 * ld + g0;
 
-    // ---- load the lower sub-blocks (256-byte coalesced rows); strict upper parts of diagonal sub-blocks are zeroed
-    for (int e = tid; e < PD_NBLK * PB * PB; e += PD_THREADS) {
-        const int b = e >> 10, r = (e >> 5) & 31, c = e & 31;
-        int bi = 0;
-        while ((bi + 1) * (bi + 2) / 2 <= b) bi++;
-        const int bj = b - bi * (bi + 1) / 2;
-        double v = 0.0;
-        if (bi != bj || c <= r) v = Ab[(int64_t)(bi * PB + r) * ld + bj * PB + c];
-        Lb[b * PB_SZ + r * PB_LD + c] = v;
+    // ---- load the lower sub-blocks: one warp per (sub-block, row) = 256 contiguous bytes, 20 independent loads in flight
+    // per thread; strict upper parts of the diagonal sub-blocks are zeroed
+    {
+        double v[PD_NBLK * PB / NW];
+#pragma unroll
+        for (int q = 0; q < PD_NBLK * PB / NW; q++) {
+            const int pr = warp + q * NW, b = pr >> 5, r = pr & 31;
+            const int bi = (b >= 6) ? 3 : (b >= 3) ? 2 : (b >= 1) ? 1 : 0;
+            const int bj = b - bi * (bi + 1) / 2;
+            v[q] = (bi != bj || lane <= r) ? Ab[(int64_t)(bi * PB + r) * ld + bj * PB + lane] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < PD_NBLK * PB / NW; q++) {
+            const int pr = warp + q * NW;
+            Lb[(pr >> 5) * PB_SZ + (pr & 31) * PB_LD + lane] = v[q];
+        }
     }
     __syncthreads();
+    PD_CLK();
 
     for (int p = 0; p < 4; p++) {
         double* Lpp = Lb + pd_blk(p, p) * PB_SZ;
-        // ---- potrf32: warp 0, lane r owns row r
+        // ---- potrf32: warp 0, lane r owns row r.  The next pivot's 1/sqrt is started before the column broadcast of
+        // the current column is consumed, so its latency hides behind the rank-1 update.
         if (warp == 0) {
             double a[PB];
             const double2* ar = reinterpret_cast<const double2*>(Lpp + lane * PB_LD);
 #pragma unroll
             for (int q = 0; q < PB / 2; q++) { const double2 v = ar[q]; a[2 * q] = v.x; a[2 * q + 1] = v.y; }
+            // pivots of the y row / identity padding are 1; a non-positive pivot is replaced by 1 and remembered
+            // (branch-free, so that ptxas can overlap the 1/sqrt chain with the rank-1 update of the previous column)
+            int first_bad = PB;
+            auto pivot = [&](double d, int c) {
+                const bool pad = g0 + p * PB + c >= n_real;
+                const bool bad = !pad && !(d > 0.0);
+                first_bad = (bad && c < first_bad) ? c : first_bad;
+                return (pad || bad) ? 1.0 : d;
+            };
+            double d = pivot(__shfl_sync(0xffffffffu, a[0], 0), 0);
+            double rs = pd_rsqrt(d);
 #pragma unroll
             for (int c = 0; c < PB; c++) {
                 double* cb = colbuf + (c & 1) * PB;
-                double d = __shfl_sync(0xffffffffu, a[c], c);
-                const int64_t gcol = g0 + p * PB + c;
-                if (gcol >= n_real) {
-                    d = 1.0;
-                } else if (!(d > 0.0)) {
-                    if (lane == 0) atomicCAS(info, 0, (int)(gcol + 1));
-                    d = 1.0;
-                }
-                const double rs = rsqrt(d);
                 a[c] = (lane == c) ? d * rs : a[c] * rs;
                 if (lane == c) rdiag[p * PB + c] = rs;
                 cb[lane] = a[c];
                 __syncwarp();
+                double rs_next = 0.0, d_next = 0.0;
+                if (c + 1 < PB) {
+                    // lane c+1 owns both numbers the next pivot needs
+                    const double tmp = fma(-a[c], a[c], a[c + 1]);
+                    d_next = pivot(__shfl_sync(0xffffffffu, tmp, c + 1), c + 1);
+                    rs_next = pd_rsqrt(d_next);
+                }
 #pragma unroll
                 for (int c2 = (c + 1) & ~1; c2 < PB; c2 += 2) {
                     const double2 l = *reinterpret_cast<const double2*>(cb + c2);
                     if (c2 > c) a[c2] = fma(-a[c], l.x, a[c2]);
                     a[c2 + 1] = fma(-a[c], l.y, a[c2 + 1]);
                 }
+                d = d_next;
+                rs = rs_next;
             }
+            if (first_bad < PB && lane == 0) atomicCAS(info, 0, (int)(g0 + p * PB + first_bad + 1));
             double* wr = Lpp + lane * PB_LD;
 #pragma unroll
             for (int c = 0; c < PB; c++) wr[c] = (c <= lane) ? a[c] : 0.0;
         }
         __syncthreads();
+        PD_CLK();
 
         // ---- inv32 (warp 0: column `lane` of inv(L_pp)) || trsm32 (warps 1..3-p: rows of the sub-blocks below)
         if (warp == 0) {
@@ -147,9 +199,17 @@ potrf_diag_kernel(double* __restrict__ A, int64_t ld, int64_t g0, int64_t n_real
 #pragma unroll
                 for (int r = k + 1; r < PB; r++) b[r] = fma(-Lpp[r * PB_LD + k], b[k], b[r]);
             }
-            double* X = Xb + pd_blk(p, p) * PB_SZ;
+            double* X = Xd + p * PB_SZ;
+            double* XT = Xt + pd_blk(p, p) * PB_SZ;
+            double* G = Dinv + (int64_t)(p * PB) * TILE + p * PB;
 #pragma unroll
-            for (int r = 0; r < PB; r++) X[r * PB_LD + lane] = b[r];   // X[r][c=lane]; zero above the diagonal
+            for (int r = 0; r < PB; r++) {       // X[r][c = lane]; exact zeros above the diagonal
+                X[r * PB_LD + lane] = b[r];
+                G[r * TILE + lane] = b[r];
+            }
+            double2* wt = reinterpret_cast<double2*>(XT + lane * PB_LD);
+#pragma unroll
+            for (int q = 0; q < PB / 2; q++) wt[q] = make_double2(b[2 * q], b[2 * q + 1]);
         } else if (warp <= 3 - p) {
             const int i = p + warp;
             double* Lip = Lb + pd_blk(i, p) * PB_SZ;
@@ -166,11 +226,9 @@ potrf_diag_kernel(double* __restrict__ A, int64_t ld, int64_t g0, int64_t n_real
             double2* wr = reinterpret_cast<double2*>(Lip + lane * PB_LD);
 #pragma unroll
             for (int q = 0; q < PB / 2; q++) wr[q] = make_double2(x[2 * q], x[2 * q + 1]);
-            double* T = Tb + (warp - 1) * PB_SZ;   // T[k][r] = L_ip[r][k]
-#pragma unroll
-            for (int k = 0; k < PB; k++) T[k * PB_LD + lane] = x[k];
         }
         __syncthreads();
+        PD_CLK();
 
         // ---- trailing update inside the block: C_ij -= L_ip L_jp^T for p < j <= i, 4 column units per product
         {
@@ -178,67 +236,66 @@ potrf_diag_kernel(double* __restrict__ A, int64_t ld, int64_t g0, int64_t n_real
             const int n_units = m * (m + 1) / 2 * 4;
             for (int u = warp; u < n_units; u += NW) {
                 const int op = u >> 2, chunk = u & 3;
-                int ii = 0;
-                while ((ii + 1) * (ii + 2) / 2 <= op) ii++;
+                const int ii = (op >= 3) ? 2 : (op >= 1) ? 1 : 0;
                 const int jj = op - ii * (ii + 1) / 2;
                 const int i = p + 1 + ii, j = p + 1 + jj;
-                pd_unit<0>(Lb + pd_blk(i, j) * PB_SZ, Lb + pd_blk(i, p) * PB_SZ, Tb + (j - p - 1) * PB_SZ, chunk * 8, lane);
+                pd_unit<0, false>(Lb + pd_blk(i, j) * PB_SZ, Lb + pd_blk(i, p) * PB_SZ, Lb + pd_blk(j, p) * PB_SZ, nullptr,
+                                  nullptr, chunk * 8, lane);
             }
         }
         __syncthreads();
+        PD_CLK();
     }
 
-    // ---- factor back to global (lower triangle only)
-    for (int e = tid; e < PD_NBLK * PB * PB; e += PD_THREADS) {
-        const int b = e >> 10, r = (e >> 5) & 31, c = e & 31;
-        int bi = 0;
-        while ((bi + 1) * (bi + 2) / 2 <= b) bi++;
+    // ---- factor back to global (lower triangle only); overlaps with stage A below (Lb is read-only from here on)
+#pragma unroll
+    for (int q = 0; q < PD_NBLK * PB / NW; q++) {
+        const int pr = warp + q * NW, b = pr >> 5, r = pr & 31;
+        const int bi = (b >= 6) ? 3 : (b >= 3) ? 2 : (b >= 1) ? 1 : 0;
         const int bj = b - bi * (bi + 1) / 2;
-        if (bi != bj || c <= r) Ab[(int64_t)(bi * PB + r) * ld + bj * PB + c] = Lb[b * PB_SZ + r * PB_LD + c];
+        if (bi != bj || lane <= r) Ab[(int64_t)(bi * PB + r) * ld + bj * PB + lane] = Lb[b * PB_SZ + r * PB_LD + lane];
     }
+    PD_CLK();
 
-    // ---- assemble inv(L): T_ij = sum_k L_ik X_kj accumulated in Xb(i,j), then X_ij = -X_ii T_ij in place
-    auto X = [&](int i, int j) { return Xb + pd_blk(i, j) * PB_SZ; };
+    // ---- assemble inv(L):  X_ij = -X_ii T_ij,  T_ij = sum_{k=j..i-1} L_ik X_kj.  T_ij lives (transposed) where X_ij
+    // will go; a unit only ever touches its own 8 columns of a sub-block, so the in-place steps are race-free.
+    auto XT = [&](int i, int j) { return Xt + pd_blk(i, j) * PB_SZ; };
     auto L = [&](int i, int j) { return Lb + pd_blk(i, j) * PB_SZ; };
-    // stage A: T_ij = L_ij X_jj for all i > j (6 products)
+    auto GD = [&](int i, int j) { return Dinv + (int64_t)(i * PB) * TILE + j * PB; };
+    // stage A: T_ij = L_ij X_jj for all i > j (6 products, 24 units)
     for (int u = warp; u < 24; u += NW) {
         const int op = u >> 2, chunk = u & 3;
         const int i = op < 1 ? 1 : (op < 3 ? 2 : 3);
         const int j = op - (i == 1 ? 0 : (i == 2 ? 1 : 3));
-        pd_unit<1>(X(i, j), L(i, j), X(j, j), chunk * 8, lane);
+        pd_unit<1, true>(XT(i, j), L(i, j), XT(j, j), nullptr, nullptr, chunk * 8, lane);
     }
     __syncthreads();
     // stage B: X_{j+1,j} = -X_{j+1,j+1} T_{j+1,j}
     for (int u = warp; u < 12; u += NW) {
         const int j = u >> 2, chunk = u & 3;
-        pd_unit<3>(X(j + 1, j), X(j + 1, j + 1), X(j + 1, j), chunk * 8, lane);
+        pd_unit<3, true>(XT(j + 1, j), Xd + (j + 1) * PB_SZ, XT(j + 1, j), nullptr, nullptr, chunk * 8, lane, GD(j + 1, j), TILE);
     }
     __syncthreads();
     // stage C1: T_{j+2,j} += L_{j+2,j+1} X_{j+1,j}
     for (int u = warp; u < 8; u += NW) {
         const int j = u >> 2, chunk = u & 3;
-        pd_unit<2>(X(j + 2, j), L(j + 2, j + 1), X(j + 1, j), chunk * 8, lane);
+        pd_unit<2, true>(XT(j + 2, j), L(j + 2, j + 1), XT(j + 1, j), nullptr, nullptr, chunk * 8, lane);
     }
     __syncthreads();
     // stage C2: X_{j+2,j} = -X_{j+2,j+2} T_{j+2,j}
     for (int u = warp; u < 8; u += NW) {
         const int j = u >> 2, chunk = u & 3;
-        pd_unit<3>(X(j + 2, j), X(j + 2, j + 2), X(j + 2, j), chunk * 8, lane);
+        pd_unit<3, true>(XT(j + 2, j), Xd + (j + 2) * PB_SZ, XT(j + 2, j), nullptr, nullptr, chunk * 8, lane, GD(j + 2, j), TILE);
     }
     __syncthreads();
-    // stage D: T_30 += L_31 X_10 + L_32 X_20 ; X_30 = -X_33 T_30   (a unit only touches its own 8 columns of X_30)
+    // stage D: T_30 += L_31 X_10 + L_32 X_20 ; X_30 = -X_33 T_30
     if (warp < 4) {
-        pd_unit<2>(X(3, 0), L(3, 1), X(1, 0), warp * 8, lane);
+        pd_unit<2, true>(XT(3, 0), L(3, 1), XT(1, 0), L(3, 2), XT(2, 0), warp * 8, lane);
         __syncwarp();
-        pd_unit<2>(X(3, 0), L(3, 2), X(2, 0), warp * 8, lane);
-        __syncwarp();
-        pd_unit<3>(X(3, 0), X(3, 3), X(3, 0), warp * 8, lane);
+        pd_unit<3, true>(XT(3, 0), Xd + 3 * PB_SZ, XT(3, 0), nullptr, nullptr, warp * 8, lane, GD(3, 0), TILE);
     }
-    __syncthreads();
-    for (int e = tid; e < TILE * TILE; e += PD_THREADS) {
-        const int r = e >> 7, c = e & 127;
-        Dinv[e] = (c <= r) ? Xb[pd_blk(r >> 5, c >> 5) * PB_SZ + (r & 31) * PB_LD + (c & 31)] : 0.0;
-    }
+    PD_CLK();
+#undef PD_CLK
 }
 
 // sum_{i<n} log A[i][i]  and  sum_{i<n} A[n][i]^2  (log-determinant half and |v|^2) -> scal[0], scal[1]

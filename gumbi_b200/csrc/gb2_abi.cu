@@ -289,6 +289,8 @@ static int build_K(gb2_handle* h, int& launches) {
         h->dA = nullptr; h->dDinv = nullptr; h->A_cap = 0;
         GB2_CUDA(h, cudaMalloc(&h->dA, (size_t)Np * Np * sizeof(double)));
         GB2_CUDA(h, cudaMalloc(&h->dDinv, (size_t)Np * TILE * sizeof(double)));
+        // the diagonal-panel kernel writes the lower block-triangle of each inverse only; the rest stays zero
+        GB2_CUDA(h, cudaMemsetAsync(h->dDinv, 0, (size_t)Np * TILE * sizeof(double), s));
         h->A_cap = Np;
     }
     GB2_CUDA(h, cudaMemsetAsync(h->dInfo, 0, 4 * sizeof(int), s));

@@ -122,6 +122,46 @@ __global__ void k_exp_err(const double* in, int n, double* maxrel) {
     atomicMax((unsigned long long*)maxrel, __double_as_longlong(rel));
 }
 
+// dependent-chain latencies with one warp (clock64 deltas / iters)
+__global__ void k_latency(long long* out, int iters, double a, double b) {
+    double x = threadIdx.x * 1e-9;
+    long long t0 = clock64();
+    for (int i = 0; i < iters; i++) x = fma(x, a, b);
+    long long t1 = clock64();
+    double c0 = x, c1 = -x;
+    for (int i = 0; i < iters; i++) dmma884(c0, c1, a, b);
+    long long t2 = clock64();
+    double y = x;
+    for (int i = 0; i < iters; i++) y = rsqrt(y + 1.5);
+    long long t3 = clock64();
+    double z = y;
+    for (int i = 0; i < iters; i++) z = __shfl_sync(0xffffffffu, z, (threadIdx.x + 1) & 31);
+    long long t4 = clock64();
+    float f = (float)z;
+    for (int i = 0; i < iters; i++) f = rsqrtf(f + 1.5f);
+    long long t5 = clock64();
+    double w = z;
+    for (int i = 0; i < iters; i++) w = (double)(float)w + 1.0;
+    long long t6 = clock64();
+    // independent DFMA issue rate from one warp: 8 accumulators
+    double acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = i + x;
+    long long t7 = clock64();
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] = fma(acc[i], a, b);
+    }
+    long long t8 = clock64();
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += acc[i];
+    if (threadIdx.x == 0) {
+        out[0] = t1 - t0; out[1] = t2 - t1; out[2] = t3 - t2; out[3] = t4 - t3; out[4] = t5 - t4; out[5] = t6 - t5; out[6] = t8 - t7;
+        out[7] = (long long)(c0 + c1 + s + f + w);
+    }
+}
+
 template <typename F>
 float time_ms(F f, int reps = 5) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -139,6 +179,14 @@ int main() {
     int sms = p.multiProcessorCount;
     printf("{\"device\":\"%s\",\"sms\":%d,\"clock_khz\":%d}\n", p.name, sms, p.clockRate);
     double* out; CK(cudaMalloc(&out, sizeof(double) * sms * 8 * 1024));
+    {
+        long long* lat; CK(cudaMalloc(&lat, 64)); long long hl[8];
+        k_latency<<<1, 32>>>(lat, 2048, 1.0000001, 1e-9); CK(cudaDeviceSynchronize());
+        k_latency<<<1, 32>>>(lat, 2048, 1.0000001, 1e-9); CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(hl, lat, 64, cudaMemcpyDeviceToHost));
+        printf("{\"bench\":\"latency_cycles\",\"dfma\":%.1f,\"dmma884\":%.1f,\"rsqrt_f64\":%.1f,\"shfl64\":%.1f,\"rsqrt_f32\":%.1f,\"cvt_roundtrip_add\":%.1f,\"dfma_issue_1warp\":%.2f}\n",
+               hl[0] / 2048.0, hl[1] / 2048.0, hl[2] / 2048.0, hl[3] / 2048.0, hl[4] / 2048.0, hl[5] / 2048.0, hl[6] / 2048.0 / 8);
+    }
     const int iters = 4096;
     for (int warps : {4, 8, 16, 32}) {
         int threads = warps * 32, blocks = sms * 2;

@@ -1,0 +1,15 @@
+"""Profiling driver (dev tool): a few factorize + predict calls at a given size, nothing else."""
+import sys
+sys.path.insert(0, ".")
+from gumbi_b200 import GPEngine
+from gumbi_b200.synthetic import synthetic_problem
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+kind = sys.argv[3] if len(sys.argv) > 3 else "ExpQuad"
+spec, X, y, Xs = synthetic_problem(n, 8, M_res=100, kind=kind)
+eng = GPEngine(0)
+eng.set_train(X, y); eng.set_kernel(spec)
+for _ in range(reps):
+    eng.factorize()
+    eng.predict(Xs, True)
+print(eng.timings())
