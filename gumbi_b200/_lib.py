@@ -13,6 +13,12 @@ import numpy as np
 
 MAX_TERMS, MAX_D, MAX_LIN, MAX_COREG, MAX_P = 4, 16, 8, 3, 16
 N_TIMINGS = 8
+# flat gradient layout of gb2_mll_grad (include/gumbi_b200.h)
+GRAD_LS, GRAD_ETA, GRAD_C, GRAD_TAU, GRAD_B = 0, MAX_D, MAX_D + 1, MAX_D + 1 + MAX_LIN, MAX_D + 2 + MAX_LIN
+GRAD_TERM = GRAD_B + MAX_COREG * MAX_P * MAX_P
+GRAD_SIGMA = MAX_TERMS * GRAD_TERM
+GRAD_NOISE_B = GRAD_SIGMA + 1
+GRAD_LEN = GRAD_NOISE_B + MAX_P * MAX_P
 KIND_IDS = {"ExpQuad": 0, "Matern52": 1, "Matern32": 2, "Matern12": 3, "Exponential": 4}
 FP64, TF32 = 0, 1
 
@@ -51,7 +57,7 @@ class Kernel(C.Structure):
 
 EXPORTS = [
     "gb2_abi_version", "gb2_create", "gb2_destroy", "gb2_last_error", "gb2_set_train", "gb2_set_train_dev",
-    "gb2_set_kernel", "gb2_factorize", "gb2_mll", "gb2_predict", "gb2_predict_dev", "gb2_get_K", "gb2_get_L",
+    "gb2_set_kernel", "gb2_factorize", "gb2_mll", "gb2_mll_grad", "gb2_predict", "gb2_predict_dev", "gb2_get_K", "gb2_get_L",
     "gb2_get_v", "gb2_get_timings", "gb2_set_option", "gb2_mark", "gb2_elapsed_ms",
 ]
 
@@ -89,6 +95,7 @@ def load():
     lib.gb2_set_kernel.argtypes = [H, C.POINTER(Kernel)]
     lib.gb2_factorize.argtypes = [H]
     lib.gb2_mll.argtypes = [H, dp]
+    lib.gb2_mll_grad.argtypes = [H, dp, dp]
     lib.gb2_predict.argtypes = [H, dp, C.c_int64, C.c_int32, dp, dp]
     lib.gb2_predict_dev.argtypes = [H, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
     lib.gb2_get_K.argtypes = [H, dp]

@@ -1,6 +1,7 @@
 // extern "C" boundary of the gumbi_b200 core (declared in include/gumbi_b200.h).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC gb2_abi.cu -o libgumbi_b200.so
 #include "predict.cuh"
+#include "mllgrad.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -167,6 +168,8 @@ int gb2_create(gb2_handle** out, int device, int precision) {
     if ((e = cholesky_configure()) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
     if ((e = cudaFuncSetAttribute(kbuild_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
     if ((e = cudaFuncSetAttribute(kbuild_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
+    if ((e = cudaFuncSetAttribute(mll_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 164 * 1024)) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
+    if ((e = dgemm_nt_configure<128, 64, GM_SET>()) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
     *out = h;
     return 0;
 }
@@ -178,6 +181,7 @@ int gb2_destroy(gb2_handle* h) {
     cudaFree(h->dX); cudaFree(h->dy); cudaFree(h->dBtab); cudaFree(h->dF); cudaFree(h->dC); cudaFree(h->dA);
     cudaFree(h->dDinv); cudaFree(h->dInfo); cudaFree(h->dScal); cudaFree(h->dXs); cudaFree(h->dFs); cudaFree(h->dCs);
     cudaFree(h->dAt); cudaFree(h->dMean); cudaFree(h->dVar);
+    cudaFree(h->dW); cudaFree(h->dS); cudaFree(h->dAlpha); cudaFree(h->dGrad);
     for (auto ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto ev : h->ev_pool) cudaEventDestroy(ev);
     for (auto ev : h->ev_mark) if (ev) cudaEventDestroy(ev);
@@ -271,6 +275,8 @@ int gb2_set_kernel(gb2_handle* h, const gb2_kernel* k) {
     GB2_CUDA(h, cudaMemcpyAsync(h->dBtab, btab.data(), btab.size() * sizeof(double), cudaMemcpyHostToDevice, h->s_main));
     GB2_CUDA(h, cudaStreamSynchronize(h->s_main));
     h->kp = kp; h->pp = pp;
+    for (int t = 0; t < k->n_terms; t++) h->eta_host[t] = k->terms[t].eta;
+    h->sigma_host = k->sigma;
     h->have_kernel = true; h->factorized = false;
     return 0;
 }
@@ -340,6 +346,58 @@ int gb2_mll(gb2_handle* h, double* out) {
     double sc[2];
     GB2_CUDA(h, cudaMemcpy(sc, h->dScal, 2 * sizeof(double), cudaMemcpyDeviceToHost));
     *out = -0.5 * (double)h->N * 1.8378770664093454836 - sc[0] - 0.5 * sc[1];
+    return 0;
+}
+
+int gb2_mll_grad(gb2_handle* h, double* mll_out, double* grad_out) {
+    if (!h) return -1;
+    GB2_ARG(h, mll_out && grad_out, "null pointer");
+    GB2_ARG(h, h->factorized, "gb2_mll_grad called before a successful gb2_factorize");
+    GB2_CUDA(h, cudaSetDevice(h->device));
+    const int64_t Np = h->Np, N = h->N;
+    const int nb = (int)(Np / TILE);
+    cudaStream_t s = h->s_main;
+    if (h->G_cap < Np) {
+        if (h->dW) GB2_CUDA(h, cudaFree(h->dW));
+        if (h->dS) GB2_CUDA(h, cudaFree(h->dS));
+        h->dW = h->dS = nullptr; h->G_cap = 0;
+        GB2_CUDA(h, cudaMalloc(&h->dW, (size_t)Np * Np * sizeof(double)));
+        GB2_CUDA(h, cudaMalloc(&h->dS, (size_t)Np * Np * sizeof(double)));
+        h->G_cap = Np;
+    }
+    int rc;
+    if ((rc = ensure(h, h->dAlpha, h->alpha_cap, Np))) return rc;
+    if (!h->dGrad) GB2_CUDA(h, cudaMalloc(&h->dGrad, GR_LEN * sizeof(double)));
+    int launches = 0;
+    // 1. W = L^-T (rows), alpha from the augmented column
+    set_identity_kernel<<<(unsigned)((Np * (Np / 2) + 255) / 256), 256, 0, s>>>(h->dW, Np, Np);
+    trsm_rec(s, h->dA, Np, h->dDinv, h->dW, Np, Np, 0, nb, launches);
+    extract_alpha_kernel<<<(unsigned)((Np + 255) / 256), 256, 0, s>>>(h->dW, Np, N, Np, h->dAlpha);
+    // 2. S = W W^T = K^-1 (lower tiles)
+    dgemm_nt_launch<128, 64, GM_SET>(s, h->dW, Np, h->dW, Np, h->dS, Np, Np, Np, (int)Np, 1, 0, 0);
+    // 3. one pass over G = alpha alpha^T - S
+    GB2_CUDA(h, cudaMemsetAsync(h->dGrad, 0, GR_LEN * sizeof(double), s));
+    dim3 grid((unsigned)(Np / KB_T), (unsigned)(Np / KB_T));
+    mll_grad_kernel<<<grid, KB_THREADS, mll_grad_smem_bytes(h->kp), s>>>(h->kp, h->dBtab, h->dF, h->dC, Np, N, h->dS, Np, h->dAlpha, h->dGrad);
+    GB2_CUDA(h, cudaGetLastError());
+    GB2_CUDA(h, cudaMemcpyAsync(grad_out, h->dGrad, GR_LEN * sizeof(double), cudaMemcpyDeviceToHost, s));
+    double sc[2];
+    GB2_CUDA(h, cudaMemcpyAsync(sc, h->dScal, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    GB2_CUDA(h, cudaStreamSynchronize(s));
+    *mll_out = -0.5 * (double)N * 1.8378770664093454836 - sc[0] - 0.5 * sc[1];
+    // host-side constant factors: the kernel accumulated sum_ij G_ij * (dK_ij/dtheta without these factors)
+    for (int t = 0; t < GB2_MAX_TERMS; t++) {
+        double* g = grad_out + t * GR_TERM;
+        if (t >= h->kp.n_terms) continue;
+        for (int k = 0; k < h->pp.d[t]; k++) g[GR_LS + k] *= 0.5 * h->pp.inv_ls[t][k];
+        g[GR_ETA] *= 0.5 * 2.0 * h->eta_host[t];
+        for (int l = 0; l < GB2_MAX_LIN; l++) g[GR_C + l] *= 0.5;
+        g[GR_TAU] *= 0.5;
+        for (int e = 0; e < GB2_MAX_COREG * GB2_MAX_P * GB2_MAX_P; e++) g[GR_B + e] *= 0.5;
+    }
+    grad_out[GR_SIGMA] *= 0.5 * 2.0 * h->sigma_host;
+    for (int e = 0; e < GB2_MAX_P * GB2_MAX_P; e++) grad_out[GR_NOISE_B + e] *= 0.5;
+    h->timings[6] = launches + 5;
     return 0;
 }
 

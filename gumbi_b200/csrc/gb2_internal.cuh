@@ -87,6 +87,13 @@ struct gb2_handle {
     double* dAt = nullptr; int64_t At_cap = 0;           // (Mp, Np) rows = test points
     double* dMean = nullptr; double* dVar = nullptr; int64_t out_cap = 0;
 
+    // MLL-gradient scratch: W = L^-T (Np x Np), S = K^-1 (Np x Np), alpha (Np), flat gradient
+    double* dW = nullptr; double* dS = nullptr; int64_t G_cap = 0;
+    double* dAlpha = nullptr; int64_t alpha_cap = 0;
+    double* dGrad = nullptr;
+    double eta_host[GB2_MAX_TERMS] = {0, 0, 0, 0};
+    double sigma_host = 0.0;
+
     // options
     int opt_lookahead = 1;
 

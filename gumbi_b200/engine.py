@@ -97,6 +97,42 @@ class GPEngine:
         self._check(self._lib.gb2_mll(self._h, C.byref(out)), "mll")
         return out.value
 
+    def mll_grad(self, spec: dict):
+        """(log p(y|X,theta), gradient) with the gradient shaped like ``spec``: per term ``ls``, ``eta``, ``c``, ``tau`` and
+        per Coregion factor ``W``/``kappa`` (chain rule through B = W W^T + diag(kappa) applied here), plus ``sigma`` and
+        the noise Coregion.  ``spec`` must be the one last passed to ``set_kernel``."""
+        L = _lib
+        val = C.c_double()
+        g = np.zeros(L.GRAD_LEN, dtype=np.float64)
+        self._check(self._lib.gb2_mll_grad(self._h, C.byref(val), L.as_dp(g)), "mll_grad")
+
+        def coreg_grad(cg, GB):
+            W = np.atleast_2d(np.asarray(cg["W"], dtype=np.float64))
+            return {"W": (GB + GB.T) @ W, "kappa": np.diag(GB).copy()}
+
+        out = {"terms": [], "sigma": float(g[L.GRAD_SIGMA]), "noise_coreg": None}
+        for t, term in enumerate(spec["terms"]):
+            gt = g[t * L.GRAD_TERM:(t + 1) * L.GRAD_TERM]
+            d = len(term["cont_idx"])
+            ls = np.atleast_1d(np.asarray(term["ls"], dtype=np.float64))
+            gls = gt[L.GRAD_LS:L.GRAD_LS + d].copy()
+            if ls.size == 1 and d > 1:  # shared lengthscale: sum over dimensions
+                gls = np.array([gls.sum()])
+            n_lin = len(term.get("lin_idx") or [])
+            tg = {"ls": gls, "eta": float(gt[L.GRAD_ETA]), "c": gt[L.GRAD_C:L.GRAD_C + n_lin].copy(),
+                  "tau": float(gt[L.GRAD_TAU]), "coreg": []}
+            for f, cg in enumerate(term.get("coreg") or []):
+                P = len(cg["kappa"])
+                GB = gt[L.GRAD_B + f * L.MAX_P ** 2:L.GRAD_B + f * L.MAX_P ** 2 + P * P].reshape(P, P)
+                tg["coreg"].append(coreg_grad(cg, GB))
+            out["terms"].append(tg)
+        ncg = spec.get("noise_coreg")
+        if ncg:
+            P = len(ncg["kappa"])
+            GB = g[L.GRAD_NOISE_B:L.GRAD_NOISE_B + P * P].reshape(P, P)
+            out["noise_coreg"] = coreg_grad(ncg, GB)
+        return val.value, out
+
     def predict(self, Xs, pred_noise: bool = True):
         Xs = _c_f64(np.atleast_2d(Xs), 2)
         if Xs.shape[1] != self.D_in:

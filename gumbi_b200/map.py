@@ -1,0 +1,290 @@
+"""``find_MAP`` for the B200 backend: host-side L-BFGS-B over device-evaluated objective and gradient.
+
+Restates what ``PymcGP.find_MAP`` -> ``pm.find_MAP()`` does (gumbi/regression/pymc/GP.py:799-813): SciPy L-BFGS-B on
+``-(log p(y|X,theta) + sum of log-priors)`` in the *transformed* space (positive variables are optimised through their
+logs, ``jacobian=False`` so no Jacobian term is added), started from the model's initial point (prior moments;
+``W`` from ``default_rng(seed).standard_normal`` as GP.py:459), ``maxeval=5000``.  The returned dict carries both the
+constrained values and the ``*_log__`` keys, as PyMC's does.
+
+Priors (cited per line): ls ~ InverseGamma(alpha, beta) from ``get_ls_prior`` (gumbi/utils/gp_utils.py:51-87) ->
+``pm.find_constrained_prior`` restated with SciPy below; eta ~ Gamma(2, 1) (GP.py:408); c ~ Normal(0, 10),
+tau ~ HalfNormal(10) (GP.py:451-452); W ~ Normal(0, 3), kappa ~ Gamma(1.5, 1) (GP.py:460-461); sigma ~ Exponential(1)
+(GP.py:560).
+
+Every O(N^2)-and-up quantity (K, Cholesky, K^-1, the N^2 gradient contraction) is computed on the GPU through
+``gb2_factorize`` / ``gb2_mll_grad``; this file only does the O(#parameters) bookkeeping.
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+from scipy import optimize, stats
+from scipy.special import gammaln
+
+POSITIVE = ("ls", "η", "τ", "κ", "σ")
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# length-scale prior (gp_utils.py:15-87)
+# ----------------------------------------------------------------------------------------------------------------------
+def _min_max_nonzero_distance(points):
+    """min and max non-zero pairwise Euclidean distance.  1-D columns (the ARD case) are done by sorting, which gives
+    exactly ``pdist``'s answer without the O(N^2) memory of gp_utils.py:34."""
+    points = np.asarray(points, dtype=np.float64)
+    if points.ndim == 1 or points.shape[1] == 1:
+        u = np.unique(points.reshape(-1))
+        if u.size < 2:
+            return None, None
+        return float(np.diff(u).min()), float(u[-1] - u[0])
+    from scipy.spatial.distance import pdist
+
+    n = points.shape[0]
+    if n <= 4096:
+        d = pdist(points)
+        d = d[d != 0]
+        return (float(d.min()), float(d.max())) if d.size else (None, None)
+    lo, hi = np.inf, 0.0
+    for s in range(0, n, 1024):  # blocked, O(N * 1024) memory
+        blk = points[s:s + 1024]
+        d2 = np.maximum((blk ** 2).sum(1)[:, None] + (points ** 2).sum(1)[None, :] - 2.0 * blk @ points.T, 0.0)
+        nz = d2[d2 > 1e-24]
+        if nz.size:
+            lo, hi = min(lo, float(np.sqrt(nz.min()))), max(hi, float(np.sqrt(nz.max())))
+    return (lo, hi) if hi > 0 else (None, None)
+
+
+def parse_ls_limits(X, ARD=True, lower=None, upper=None):
+    X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+    cols = [X[:, [j]] for j in range(X.shape[1])] if ARD else [X]
+
+    def spread(v):
+        v = [None] if v is None else list(np.atleast_1d(v))
+        if len(v) == 1:
+            v = v * len(cols)
+        if len(v) != len(cols):
+            raise ValueError("Number of bounds must match number of dimensions")
+        return v
+
+    lowers, uppers = spread(lower), spread(upper)
+    for i, pts in enumerate(cols):
+        dmin, dmax = _min_max_nonzero_distance(pts)
+        default_lower = dmin if dmin is not None else 0.01
+        lo = default_lower if lowers[i] is None else lowers[i]
+        lowers[i] = max(lo, default_lower, 0.01)
+        if uppers[i] is None:
+            uppers[i] = dmax if dmax is not None else 1
+    return lowers, uppers
+
+
+def find_constrained_invgamma(lower, upper, mass=0.98):
+    """``pm.find_constrained_prior(pm.InverseGamma, lower, upper, init_guess={alpha: lower, beta: upper}, mass)``.
+
+    PyMC poses: minimise (CDF(lower) - (1-mass)/2)^2 subject to CDF(upper) - CDF(lower) = mass, and hands it to SciPy's
+    SLSQP.  Both conditions can be met exactly, so the optimum is the root of a two-equation system; because beta is a
+    pure scale parameter it reduces to one monotone equation in alpha (the quantile ratio q_hi/q_lo of InvGamma(alpha, 1)
+    must equal upper/lower), solved here by bracketing.  Raises ValueError('Optimization of parameters failed') like
+    PyMC when no solution exists."""
+    if not (0 < lower < upper) or not (0 < mass < 1):
+        raise ValueError("Optimization of parameters failed.")
+    tail = (1.0 - mass) / 2.0
+    target = np.log(upper / lower)
+
+    def ratio(log_a):
+        a = np.exp(log_a)
+        return np.log(stats.invgamma.ppf(1.0 - tail, a) / stats.invgamma.ppf(tail, a)) - target
+
+    lo, hi = np.log(1e-2), np.log(1e7)
+    try:
+        f_lo, f_hi = ratio(lo), ratio(hi)
+        if not (np.isfinite(f_lo) and np.isfinite(f_hi)) or f_lo * f_hi > 0:
+            raise ValueError
+        log_a = optimize.brentq(ratio, lo, hi, xtol=1e-12, rtol=1e-12)
+    except ValueError:
+        raise ValueError("Optimization of parameters failed.") from None
+    alpha = float(np.exp(log_a))
+    beta = float(lower / stats.invgamma.ppf(tail, alpha))
+    return {"alpha": alpha, "beta": beta}
+
+
+def get_ls_prior(X, ARD=True, lower=None, upper=None, mass=0.98):
+    lowers, uppers = parse_ls_limits(X, ARD=ARD, lower=lower, upper=upper)
+    alphas, betas = [], []
+    for i, (lo, hi) in enumerate(zip(lowers, uppers)):
+        mass_ = mass
+        while True:
+            try:
+                p = find_constrained_invgamma(lo, hi, mass_)
+                break
+            except ValueError:
+                mass_ -= 0.01  # gp_utils.py:72-74
+                if mass_ <= 0.5:
+                    raise
+        if mass_ != mass:
+            warnings.warn(f"Mass of constrained lengthscale prior was reduced from {mass:.3f} to {mass_:.3f} to enable "
+                          f"convergence for dimension {i}.")
+        alphas.append(p["alpha"])
+        betas.append(p["beta"])
+    return {"alpha": np.array(alphas), "beta": np.array(betas)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# priors: (logp, dlogp/dx, initial value)
+# ----------------------------------------------------------------------------------------------------------------------
+def _invgamma(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    init = np.where(a > 1, b / np.maximum(a - 1, 1e-300), b / (a + 1))
+    return (lambda x: np.sum(a * np.log(b) - gammaln(a) - (a + 1) * np.log(x) - b / x),
+            lambda x: -(a + 1) / x + b / x ** 2, lambda shape: np.broadcast_to(init, shape).copy())
+
+
+def _gamma(a, b):
+    return (lambda x: np.sum(a * np.log(b) - gammaln(a) + (a - 1) * np.log(x) - b * x),
+            lambda x: (a - 1) / x - b, lambda shape: np.full(shape, a / b))
+
+
+def _normal(mu, sd):
+    return (lambda x: np.sum(-0.5 * ((x - mu) / sd) ** 2 - np.log(sd * np.sqrt(2 * np.pi))),
+            lambda x: -(x - mu) / sd ** 2, lambda shape: np.full(shape, float(mu)))
+
+
+def _halfnormal(sd):
+    return (lambda x: np.sum(-0.5 * (x / sd) ** 2 + np.log(np.sqrt(2 / np.pi) / sd)),
+            lambda x: -x / sd ** 2, lambda shape: np.full(shape, float(sd)))
+
+
+def _exponential(lam):
+    return (lambda x: np.sum(np.log(lam) - lam * x), lambda x: np.full(np.shape(x), -lam), lambda shape: np.full(shape, 1.0 / lam))
+
+
+def build_priors(gp):
+    """name -> (logp, dlogp, init) for every free hyper-parameter of ``gp`` (a built B200Backend)."""
+    lay = gp._layout
+    X = gp._X
+    Xs = X[:, lay["idx_s"]]
+    lower = upper = None
+    if getattr(gp, "ls_bounds", None) is not None:
+        raise NotImplementedError("ls_bounds is not supported by the B200 backend yet")
+    ls_params = get_ls_prior(Xs, ARD=gp.ARD, lower=lower, upper=upper, mass=gp.mass)
+    pri = {}
+    for name, shape in gp.param_shapes().items():
+        kind = name.split("_")[0]
+        if kind == "ls":
+            pri[name] = _invgamma(ls_params["alpha"], ls_params["beta"])
+        elif kind == "η":
+            pri[name] = _gamma(2.0, 1.0)
+        elif kind == "c":
+            pri[name] = _normal(0.0, 10.0)
+        elif kind == "τ":
+            pri[name] = _halfnormal(10.0)
+        elif kind == "W":
+            lp, dlp, _ = _normal(0.0, 3.0)
+            seed = gp.seed
+            pri[name] = (lp, dlp, lambda shape, seed=seed: np.random.default_rng(seed).standard_normal(size=shape))
+        elif kind == "κ":
+            pri[name] = _gamma(1.5, 1.0)
+        elif kind == "σ":
+            pri[name] = _exponential(1.0)
+        else:  # pragma: no cover
+            raise KeyError(name)
+    return pri
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# gradient of the spec-shaped device gradient -> named hyper-parameters
+# ----------------------------------------------------------------------------------------------------------------------
+def named_gradient(gp, gspec):
+    lay = gp._layout
+    out = {}
+
+    def add(name, val):
+        out[name] = out.get(name, 0.0) + np.asarray(val, dtype=np.float64)
+
+    for t, tg in zip(lay["terms"], gspec["terms"]):
+        sfx = t["suffix"]
+        add(f"ls_{sfx}", tg["ls"])
+        add(f"η_{sfx}", tg["eta"])
+        if lay["n_l"] > 0:
+            add(f"c_{sfx}", tg["c"])
+            add(f"τ_{sfx}", tg["tau"])
+        for (name, _, _), cg in zip(t["coreg"], tg["coreg"]):
+            add(f"W_{name}", cg["W"])       # the output Coregion is shared by all terms: contributions add up
+            add(f"κ_{name}", cg["kappa"])
+    add("σ", gspec["sigma"])
+    if lay["noise_coreg"]:
+        name = lay["noise_coreg"][0]
+        add(f"W_{name}", gspec["noise_coreg"]["W"])
+        add(f"κ_{name}", gspec["noise_coreg"]["kappa"])
+    return out
+
+
+def make_objective(gp, start=None):
+    """Packed objective of ``pm.find_MAP``: returns (fun, x0, unpack, names, positive) where ``fun(x)`` is
+    (-(log-likelihood + log-priors), its gradient) in the transformed space and ``unpack(x)`` the constrained point."""
+    shapes = gp.param_shapes()
+    pri = build_priors(gp)
+    names = list(shapes)
+    sizes = [int(np.prod(shapes[n])) if shapes[n] != () else 1 for n in names]
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(int)
+    positive = [n.split("_")[0] in POSITIVE for n in names]
+
+    x0 = np.zeros(offs[-1])
+    for i, n in enumerate(names):
+        shape = shapes[n] if shapes[n] != () else (1,)
+        val = pri[n][2](shape)
+        if start and n in start:
+            val = np.broadcast_to(np.asarray(start[n], dtype=np.float64), shape)
+        x0[offs[i]:offs[i + 1]] = (np.log(val) if positive[i] else val).reshape(-1)
+
+    def unpack(x):
+        point = {}
+        for i, n in enumerate(names):
+            v = x[offs[i]:offs[i + 1]]
+            v = np.exp(v) if positive[i] else v.copy()
+            point[n] = v.reshape(shapes[n]) if shapes[n] != () else float(v[0])
+        return point
+
+    def fun(x):
+        fun.n_eval += 1
+        point = unpack(x)
+        spec = gp.spec_from_point(point)
+        try:
+            gp.engine.set_kernel(spec)
+            gp.engine.factorize()
+            val, gspec = gp.engine.mll_grad(spec)
+        except (np.linalg.LinAlgError, FloatingPointError):
+            return 1e100, np.zeros_like(x)
+        g = named_gradient(gp, gspec)
+        grad = np.zeros_like(x)
+        for i, n in enumerate(names):
+            xv = np.asarray(point[n], dtype=np.float64).reshape(-1)
+            val += float(pri[n][0](np.asarray(point[n], dtype=np.float64)))
+            gi = np.asarray(g[n], dtype=np.float64).reshape(-1) + np.asarray(pri[n][1](xv), dtype=np.float64).reshape(-1)
+            grad[offs[i]:offs[i + 1]] = gi * xv if positive[i] else gi  # d/dlog(x) = x d/dx ; jacobian=False
+        if not np.isfinite(val):
+            return 1e100, np.zeros_like(x)
+        return -val, -grad
+
+    fun.n_eval = 0
+    return fun, x0, unpack, names, positive
+
+
+def find_map(gp, start=None, method="L-BFGS-B", maxeval=5000, return_raw=False, progressbar=False, **kwargs):
+    """Restatement of ``pm.find_MAP(start, method="L-BFGS-B", maxeval=5000)`` for a built ``B200Backend``."""
+    fun, x0, unpack, names, positive = make_objective(gp, start)
+    options = dict(kwargs.pop("options", {}) or {})
+    options.setdefault("maxfun", maxeval)
+    res = optimize.minimize(fun, x0, jac=True, method=method, options=options, **kwargs)
+    point = unpack(res.x)
+    MAP = {}
+    for i, n in enumerate(names):
+        val = np.asarray(point[n], dtype=np.float64)
+        MAP[n] = val
+        if positive[i]:
+            MAP[n + "_log__"] = np.log(val)
+    gp._factor_key = None
+    gp.map_result = res
+    gp.map_evals = fun.n_eval
+    if return_raw:
+        return MAP, res
+    return MAP

@@ -103,6 +103,21 @@ int gb2_factorize(gb2_handle* h);
  * Replaces the "ml" term evaluated by pm.find_MAP (GP.py:580,811).                             */
 int gb2_mll(gb2_handle* h, double* out);
 
+/* Value and gradient of log p(y | X, theta) w.r.t. every entry of gb2_kernel -- what pm.find_MAP's L-BFGS-B
+ * (GP.py:809-811) obtains from PyTensor's reverse mode through Cholesky; here the closed form
+ * 1/2 sum_ij (alpha alpha^T - K^-1)_ij dK_ij/dtheta evaluated on device.  Needs gb2_factorize.
+ * grad_out has GB2_GRAD_LEN doubles:
+ *   term t at offset t*GB2_GRAD_TERM:  [0, MAX_D) d/d ls[k] | [MAX_D] d/d eta | [MAX_D+1, +MAX_LIN) d/d c[l] |
+ *                                      [MAX_D+1+MAX_LIN] d/d tau | then MAX_COREG tables of MAX_P*MAX_P: d/d coreg_B[f][p*P+q]
+ *                                      (row-major with the factor's own P; B entries treated as independent)
+ *   [GB2_GRAD_SIGMA] d/d sigma | [GB2_GRAD_NOISE_B, +MAX_P*MAX_P) d/d noise_B[p*P+q] (diagonal only)
+ * The chain rule onto W, kappa (B = W W^T + diag kappa) and onto log-transformed variables is the caller's (tiny).   */
+#define GB2_GRAD_TERM (GB2_MAX_D + 2 + GB2_MAX_LIN + GB2_MAX_COREG * GB2_MAX_P * GB2_MAX_P)
+#define GB2_GRAD_SIGMA (GB2_MAX_TERMS * GB2_GRAD_TERM)
+#define GB2_GRAD_NOISE_B (GB2_GRAD_SIGMA + 1)
+#define GB2_GRAD_LEN (GB2_GRAD_NOISE_B + GB2_MAX_P * GB2_MAX_P)
+int gb2_mll_grad(gb2_handle* h, double* mll_out, double* grad_out);
+
 /* Posterior mean/variance at Xs:(M,D_in) -- replaces PymcGP.predict (GP.py:837-849):
  * Marginal.predict(Xs, point=MAP, diag=True, pred_noise=with_noise).  Needs gb2_factorize.     */
 int gb2_predict(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_noise, double* mean, double* var);

@@ -245,3 +245,75 @@ def test_full_size_config2_properties(engine):
     np.testing.assert_allclose(mu[sel], mu0, rtol=RTOL_GATE * 1e-2, atol=1e-9)
     np.testing.assert_allclose(var[sel], var0, rtol=RTOL_GATE * 1e-2, atol=1e-9)
     np.testing.assert_allclose(engine.mll(), -0.5 * 8192 * np.log(2 * np.pi) - np.log(np.diag(L0)).sum() - 0.5 * v0 @ v0, rtol=1e-10)
+
+
+GRAD_CASES = [
+    # n, d, P, kind, Q, linear
+    (150, 2, 1, "ExpQuad", 1, False),
+    (257, 3, 1, "Matern52", 1, True),
+    (200, 3, 2, "Matern32", 2, True),
+    (130, 2, 3, "Matern12", 1, False),
+    (300, 8, 1, "Exponential", 1, False),
+    (190, 16, 1, "ExpQuad", 1, False),
+]
+
+
+def _tree_close(a, b, rtol, atol):
+    if isinstance(a, dict):
+        for k in b:
+            _tree_close(a[k], b[k], rtol, atol)
+    elif isinstance(a, (list, tuple)):
+        assert len(a) == len(b)
+        for x, y in zip(a, b):
+            _tree_close(x, y, rtol, atol)
+    elif a is None:
+        assert b is None
+    else:
+        np.testing.assert_allclose(np.asarray(a, dtype=float), np.asarray(b, dtype=float), rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("n,d,P,kind,Q,linear", GRAD_CASES)
+def test_mll_gradient_against_oracle(engine, n, d, P, kind, Q, linear):
+    """gb2_mll_grad (device: L^-T, K^-1, one N^2 contraction pass) vs the dense numpy gradient of the oracle."""
+    spec, X, y, _ = orc.synthetic_problem(n, d, P=P, M_res=3, kind=kind, Q=Q)
+    if linear:
+        for t in spec["terms"]:
+            t["lin_idx"], t["c"], t["tau"] = [0, 1], [0.3, -0.2], 0.05
+    if P > 1:
+        spec["noise_coreg"]["W"] = (0.3 * np.random.default_rng(1).standard_normal((P, 2))).tolist()
+        spec["noise_coreg"]["kappa"] = np.random.default_rng(2).uniform(0.5, 2.0, P).tolist()
+        # shuffle the rows so that 64x64 tiles carry mixed output levels (exercises the atomics path of the kernel)
+        perm = np.random.default_rng(3).permutation(len(y))
+        X, y = np.ascontiguousarray(X[perm]), np.ascontiguousarray(y[perm])
+    engine.set_train(X, y)
+    engine.set_kernel(spec)
+    engine.factorize()
+    val, g = engine.mll_grad(spec)
+    val0, g0 = orc.mll_grad(spec, X, y)
+    np.testing.assert_allclose(val, val0, rtol=1e-10)
+    scale = max(1.0, abs(g0["sigma"]))
+    _tree_close(g, g0, rtol=1e-6, atol=1e-7 * scale)
+    # the factor must survive a gradient evaluation (predict afterwards still works)
+    mu, var = engine.predict(X[:5], True)
+    mu0, var0 = orc.predict(spec, X, y, X[:5], True)
+    np.testing.assert_allclose(mu, mu0, rtol=1e-7, atol=1e-9)
+
+
+def test_find_map_on_device_matches_host_double(lib_built):
+    """fit(): the same L-BFGS-B driver over the device objective and over the oracle objective lands on the same MAP."""
+    from gumbi_b200 import ArrayGP
+    from test_backend_host import gp_from_golden
+
+    g = load_golden("simple_regression_ExpQuad")
+    gp_dev = gp_from_golden(g, cls=ArrayGP)
+    gp_cpu = gp_from_golden(g)
+    opts = {"maxiter": 40}
+    MAP_dev = gp_dev.find_MAP(options=opts)
+    MAP_cpu = gp_cpu.find_MAP(options=opts)
+    for k in gp_dev.param_shapes():
+        np.testing.assert_allclose(MAP_dev[k], MAP_cpu[k], rtol=1e-4, atol=1e-6)
+    mu, var = gp_dev.predict(g["points"])
+    mu0, var0 = gp_cpu.predict(g["points"])
+    np.testing.assert_allclose(mu, mu0, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(var, var0, rtol=1e-4, atol=1e-6)
+    gp_dev.engine.close()

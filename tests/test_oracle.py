@@ -130,3 +130,36 @@ def test_oracle_reproduces_golden(case):
 
 def test_golden_cases_present():
     assert {"simple_regression_ExpQuad", "multioutput_regression", "categorical_additive"} <= set(GOLDEN_CASES)
+
+
+def test_oracle_mll_gradient_against_central_differences():
+    import copy
+
+    spec, X, y, _ = orc.synthetic_problem(30, 3, P=2, M_res=3, kind="Matern32", Q=2)
+    for t in spec["terms"]:
+        t["lin_idx"], t["c"], t["tau"] = [0, 1], [0.3, -0.2], 0.05
+    spec["noise_coreg"]["W"] = (0.3 * np.random.default_rng(1).standard_normal((2, 2))).tolist()
+    val, g = orc.mll_grad(spec, X, y)
+    assert val == pytest.approx(orc.mll(spec, X, y), rel=1e-12)
+
+    def fd(mut, eps=1e-6):
+        a, b = copy.deepcopy(spec), copy.deepcopy(spec)
+        mut(a, eps), mut(b, -eps)
+        return (orc.mll(a, X, y) - orc.mll(b, X, y)) / (2 * eps)
+
+    def bump(path):
+        def mut(s, e):
+            obj = s
+            for k in path[:-1]:
+                obj = obj[k]
+            obj[path[-1]] += e
+        return mut
+
+    checks = [(g["terms"][1]["ls"][2], ["terms", 1, "ls", 2]), (g["terms"][0]["eta"], ["terms", 0, "eta"]),
+              (g["terms"][0]["tau"], ["terms", 0, "tau"]), (g["terms"][1]["c"][0], ["terms", 1, "c", 0]),
+              (g["terms"][1]["coreg"][0]["W"][1, 0], ["terms", 1, "coreg", 0, "W", 1, 0]),
+              (g["terms"][0]["coreg"][0]["kappa"][1], ["terms", 0, "coreg", 0, "kappa", 1]),
+              (g["sigma"], ["sigma"]), (g["noise_coreg"]["W"][0, 1], ["noise_coreg", "W", 0, 1]),
+              (g["noise_coreg"]["kappa"][0], ["noise_coreg", "kappa", 0])]
+    for got, path in checks:
+        assert got == pytest.approx(fd(bump(path)), rel=2e-6, abs=1e-7), path
