@@ -17,8 +17,8 @@ under "warm".
 
 Workloads (BASELINE.json configs): c2 (default; N=8192 d=8 ExpQuad, M=10^4, fp64 -- the config the metric is quoted on),
 c1 (N=392 d=1, M=200), c3 (2-output ICM, n=16384 -> N=32768, d=4), c4 (Matern52 N=32768 d=8).
-N>1 GPUs: grid-sharded weak scaling -- every rank holds the factor (replicated factorisation, as a replica serving its
-own shard of the prediction grid) and predicts its own M points; no data-path collective.
+N>1 GPUs: ONE problem, strong scaling -- the factorisation is row-block-cyclic sharded over the ranks (per block step an NCCL
+broadcast of the diagonal block and an all-gather of the panel), every rank then holds the factor and serves 1/N of the grid.
 """
 from __future__ import annotations
 
@@ -234,27 +234,46 @@ def run_ours(args):
         return float(t.item())
 
     from gumbi_b200 import ArrayGP, GPEngine
+    from gumbi_b200 import dist as gdist
 
     spec, X, y, Xs, desc = make_workload(args.workload)
     N, D_in, M = len(y), X.shape[1], len(Xs)
     precision = args.precision
+    warmup = max(3, args.warmup)
 
     # ---- device-resident arm ("value") --------------------------------------------------------------------------
+    # N GPUs: ONE problem, strong scaling -- the factorisation is row-block sharded over the ranks (NCCL broadcast of the
+    # diagonal block + all-gather of the panel every block step), every rank then holds the factor and serves a contiguous
+    # 1/N slice of the grid; the slices are all-gathered on the handle's stream inside the timed region.
     eng = GPEngine(local_rank, precision)
+    if use_dist:
+        gdist.init_engine(eng)
+    lo, hi = gdist.grid_slice(M, rank, world)
+    slot = -(-M // world)   # padded slice length (equal counts for the all-gather)
     dX = torch.from_numpy(X).to(dev)
     dy = torch.from_numpy(y).to(dev)
-    dXs = torch.from_numpy(Xs).to(dev)
-    dmu = torch.empty(M, dtype=torch.float64, device=dev)
-    dvar = torch.empty(M, dtype=torch.float64, device=dev)
+    dXs = torch.from_numpy(np.ascontiguousarray(Xs[lo:hi])).to(dev)
+    dloc = torch.zeros(2 * slot, dtype=torch.float64, device=dev)          # [mean slice | var slice]
+    dall = torch.zeros(2 * slot * world, dtype=torch.float64, device=dev)
     torch.cuda.synchronize(dev)
     eng.set_train_device(dX.data_ptr(), N, D_in, dy.data_ptr())
 
     def step_dev():
         eng.set_kernel(spec)       # hyper-parameters arrive per call (point=MAP); tiny
-        eng.factorize()            # K-build + Cholesky + v
-        eng.predict_device(dXs.data_ptr(), M, True, dmu.data_ptr(), dvar.data_ptr())
+        eng.factorize()            # K-build + Cholesky + v  (collective when world > 1)
+        eng.predict_device(dXs.data_ptr(), hi - lo, True, dloc.data_ptr(), dloc.data_ptr() + 8 * slot)
+        if use_dist:
+            eng.allgather_device(dloc.data_ptr(), dall.data_ptr(), 2 * slot)
 
-    for _ in range(max(3, args.warmup)):
+    def gathered():
+        if not use_dist:
+            return dloc[:M].cpu().numpy(), dloc[slot:slot + M].cpu().numpy()
+        a = dall.cpu().numpy().reshape(world, 2, slot)
+        mu = np.concatenate([a[r, 0, : gdist.grid_slice(M, r, world)[1] - gdist.grid_slice(M, r, world)[0]] for r in range(world)])
+        var = np.concatenate([a[r, 1, : gdist.grid_slice(M, r, world)[1] - gdist.grid_slice(M, r, world)[0]] for r in range(world)])
+        return mu, var
+
+    for _ in range(warmup):
         step_dev()
     phase = {k: 0.0 for k in ("prep_ms", "kbuild_ms", "cholesky_ms", "kstar_ms", "solve_ms", "reduce_ms")}
     launches = 0
@@ -277,17 +296,19 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_total = max_over_ranks(ms_total)
     ms_step = ms_total / args.steps
-    value = world * M / (ms_step * 1e-3)
+    value = M / (ms_step * 1e-3)
     for k in phase:
-        phase[k] /= args.steps
+        phase[k] = max_over_ranks(phase[k] / args.steps)
 
     # warm predicts (factor resident)
     eng.mark(2)
     for _ in range(args.steps):
-        eng.predict_device(dXs.data_ptr(), M, True, dmu.data_ptr(), dvar.data_ptr())
+        eng.predict_device(dXs.data_ptr(), hi - lo, True, dloc.data_ptr(), dloc.data_ptr() + 8 * slot)
+        if use_dist:
+            eng.allgather_device(dloc.data_ptr(), dall.data_ptr(), 2 * slot)
     eng.mark(3)
     warm_ms = max_over_ranks(eng.elapsed_ms(2, 3) / args.steps)
-    mu_dev = dmu.cpu().numpy()
+    mu_dev, var_dev = gathered()
 
     # ---- end-to-end arm through the plugin class, host buffers ---------------------------------------------------
     n_, d_, P_, kind_, _, Q_, _ = WORKLOADS[args.workload]
@@ -304,14 +325,14 @@ def run_ours(args):
         point["κ_Output_noise"] = spec["noise_coreg"]["kappa"]
     e2e = None
     if Q_ == 1:
-        gp = ArrayGP(X, y, cont, device=local_rank, precision=precision, **cat)
         eng.close()  # free the first handle's factor before the plugin allocates its own
         del eng
+        gp = ArrayGP(X, y, cont, device=local_rank, precision=precision, distributed=use_dist, **cat)
 
         def step_e2e():
             gp.build_model(continuous_kernel=kind_)   # H2D X, y
             gp.find_MAP(point=point)
-            return gp.predict(Xs, with_noise=True)      # K-build + Cholesky + solve; H2D grid, D2H mean/var
+            return gp.predict(Xs, with_noise=True)      # K-build + Cholesky + solve; H2D grid (slice), D2H mean/var (+ gather)
 
         for _ in range(3):
             mu_h, var_h = step_e2e()
@@ -321,9 +342,10 @@ def run_ours(args):
             mu_h, var_h = step_e2e()
         torch.cuda.synchronize(dev)
         dt = max_over_ranks((time.perf_counter() - t0) / args.steps)
-        e2e = {"value": world * M / dt, "unit": "predictions/s", "ms_per_step": dt * 1e3,
-               "h2d_bytes_per_step": int(X.nbytes + y.nbytes + Xs.nbytes), "d2h_bytes_per_step": int(mu_h.nbytes + var_h.nbytes)}
-        assert np.allclose(mu_h, mu_dev, rtol=1e-9, atol=1e-12), "e2e and device arms disagree"
+        e2e = {"value": M / dt, "unit": "predictions/s", "ms_per_step": dt * 1e3,
+               "h2d_bytes_per_step": int(X.nbytes + y.nbytes + Xs[lo:hi].nbytes), "d2h_bytes_per_step": int(16 * (hi - lo)),
+               "timing": "host wall clock around the public call (it returns host arrays), max over ranks"}
+        assert np.allclose(mu_h, mu_dev, rtol=1e-6 if precision == "fp64" else 1e-2, atol=1e-9), "e2e and device arms disagree"
         gp.engine.close()
 
     if rank != 0:
@@ -334,29 +356,41 @@ def run_ours(args):
     # ---- rooflines ---------------------------------------------------------------------------------------------------
     peaks = measured_peaks()
     dgemm_peak = cublas_dgemm_peak(torch, dev)
-    Mp = (M + 127) // 128 * 128
-    solve_tflops = N * N * M / (phase["solve_ms"] * 1e-3) / 1e12
-    chol_tflops = N ** 3 / 3 / (phase["cholesky_ms"] * 1e-3) / 1e12
+    Ml = hi - lo
     kb_bytes = 8.0 * N * (N + 1) / 2 + 8.0 * N * D_in
-    kb_gbs = kb_bytes / (phase["kbuild_ms"] * 1e-3) / 1e9
+    kb_gbs = kb_bytes / world / (phase["kbuild_ms"] * 1e-3) / 1e9
+    chol_tflops = N ** 3 / 3 / (phase["cholesky_ms"] * 1e-3) / 1e12
+    solve_tflops = float(N) * N * Ml / (phase["solve_ms"] * 1e-3) / 1e12
     nblk = (N + 1 + 127) // 128
-    solve_launches = 2 * nblk - 1
-    roofline = {
-        "kernel": "dgemm_nt_kernel (DMMA m8n8k4 fp64) in the predict triangular solve L^-1 K(X,X*)",
-        "bound": "tensor", "achieved": solve_tflops, "peak": dgemm_peak, "unit": "TFLOP/s", "frac": solve_tflops / dgemm_peak,
-        "peak_source": "cuBLAS DGEMM 8192^3 burst measured live in this run (MEASURED_PEAKS.json has no fp64 entry; tcgen05 has no fp64 kind)",
-        "frac_of_measured_bf16_peak": solve_tflops / peaks["bf16_tflops"] if peaks["bf16_tflops"] else None,
-        "algorithmic_flop_per_step": float(N) * N * M, "launches_per_step": solve_launches,
-        "avg_launch_ms": phase["solve_ms"] / solve_launches, "traffic": None,
-    }
-    roofline_chol = {"kernel": "blocked Cholesky (potrf_diag + DMMA panel/trailing update)", "bound": "tensor", "achieved": chol_tflops,
-                     "peak": dgemm_peak, "unit": "TFLOP/s", "frac": chol_tflops / dgemm_peak, "algorithmic_flop_per_step": N ** 3 / 3}
+    if precision == "fp64":
+        solve_launches = 2 * nblk - 1
+        roofline = {
+            "kernel": "dgemm_nt_kernel (DMMA m8n8k4 fp64) in the predict triangular solve L^-1 K(X,X*)",
+            "bound": "tensor", "achieved": solve_tflops, "peak": dgemm_peak, "unit": "TFLOP/s", "frac": solve_tflops / dgemm_peak,
+            "peak_source": "cuBLAS DGEMM 8192^3 burst measured live in this run (MEASURED_PEAKS.json has no fp64 entry; tcgen05 has no fp64 kind)",
+            "algorithmic_flop_per_step": float(N) * N * Ml, "launches_per_step": solve_launches,
+            "avg_launch_ms": phase["solve_ms"] / solve_launches, "traffic": None,
+        }
+    else:
+        tf32_peak = peaks["bf16_tflops"] / 2.0
+        roofline = {
+            "kernel": "gemm_tf32x3_kernel (tcgen05.mma kind::tf32, 3 MMAs per product) in the predict triangular solve L^-1 K(X,X*)",
+            "bound": "tensor", "achieved": 3.0 * solve_tflops, "peak": tf32_peak, "unit": "TFLOP/s", "frac": 3.0 * solve_tflops / tf32_peak,
+            "peak_source": f"half of the bf16 GEMM peak of {peaks['source']} (tf32 dense rate = 1/2 bf16)",
+            "fp64_equivalent_tflops": solve_tflops, "algorithmic_flop_per_step": 3.0 * float(N) * N * Ml,
+            "note": "achieved counts the 3 tf32 MMAs issued per fp64-equivalent product; the fp64 leaf sub-solves (512 columns) are inside the timed phase",
+            "traffic": None,
+        }
+    roofline_chol = {"kernel": "blocked Cholesky (potrf_diag + DMMA panel" + (" + tcgen05 split-TF32 trailing SYRK)" if precision != "fp64" else "/trailing update)"),
+                     "bound": "tensor", "achieved": chol_tflops, "peak": dgemm_peak, "unit": "TFLOP/s (fp64-equivalent N^3/3)",
+                     "frac": chol_tflops / dgemm_peak, "algorithmic_flop_per_step": N ** 3 / 3,
+                     "peak_source": "cuBLAS DGEMM 8192^3 burst measured live in this run"}
     roofline_kb = {"kernel": "kbuild_kernel<train>", "bound": "hbm", "achieved": kb_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                   "frac": kb_gbs / peaks["hbm_gbs"], "peak_source": peaks["source"], "algorithmic_bytes_per_launch": kb_bytes, "traffic": None}
+                   "frac": kb_gbs / peaks["hbm_gbs"], "peak_source": peaks["source"], "algorithmic_bytes_per_launch": kb_bytes / world, "traffic": None}
 
     # ---- CPU baseline on the host cores (bounded: one full cold call) ---------------------------------------------
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         from oracle import gp_oracle as orc
 
         t0 = time.perf_counter()
@@ -364,18 +398,19 @@ def run_ours(args):
         t_cpu = time.perf_counter() - t0
         cpu = {"value": M / t_cpu, "unit": "predictions/s", "cores": os.cpu_count(), "kind": "port",
                "sample": f"1 full cold predict call (N={N}, M={M}) of the numpy/scipy restatement of the PyMC path, {t_cpu:.2f} s",
-               "max_rel_err_mean_vs_gpu": float(np.max(np.abs(mu_dev - mu_c)) / np.max(np.abs(mu_c)))}
+               "max_rel_err_mean_vs_gpu": float(np.max(np.abs(mu_dev - mu_c)) / np.max(np.abs(mu_c))),
+               "max_rel_err_var_vs_gpu": float(np.max(np.abs(var_dev - var_c) / np.abs(var_c)))}
 
     line = {
         "metric": "posterior predictions/sec on M-point grid (cold: K-build + Cholesky + solve per call)",
-        "value": value, "unit": "predictions/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64" if precision == "fp64" else "tf32+f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "N": N, "M_per_gpu": M, "d": d_, "outputs": P_, "kernel": kind_,
-                   "parallelism": "single GPU" if world == 1 else f"grid-sharded x{world}, factor replicated, no collective",
+        "value": value, "unit": "predictions/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+        "dtype": "f64" if precision == "fp64" else "tf32x3+f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "N": N, "M": M, "d": d_, "outputs": P_, "kernel": kind_,
+                   "parallelism": "single GPU" if world == 1 else f"row-block-cyclic sharded Cholesky over {world} GPUs (NCCL bcast + all-gather per block step), grid split {world} ways",
                    "l2_policy": f"inputs larger than L2: the factor is {8.0 * N * N / 1e6:.0f} MB and is rewritten every step"},
         "phases_ms": phase, "wall_ms_per_step": wall_ms / args.steps,
-        "warm": {"value": world * M / (warm_ms * 1e-3), "unit": "predictions/s", "ms_per_step": warm_ms},
+        "warm": {"value": M / (warm_ms * 1e-3), "unit": "predictions/s", "ms_per_step": warm_ms},
         "cholesky_tflops": chol_tflops,
         "roofline": roofline, "roofline_cholesky": roofline_chol, "roofline_kbuild": roofline_kb,
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,

@@ -59,6 +59,7 @@ EXPORTS = [
     "gb2_abi_version", "gb2_create", "gb2_destroy", "gb2_last_error", "gb2_set_train", "gb2_set_train_dev",
     "gb2_set_kernel", "gb2_factorize", "gb2_mll", "gb2_mll_grad", "gb2_predict", "gb2_predict_dev", "gb2_get_K", "gb2_get_L",
     "gb2_get_v", "gb2_get_timings", "gb2_set_option", "gb2_mark", "gb2_elapsed_ms",
+    "gb2_nccl_unique_id", "gb2_dist_init", "gb2_dist_finalize", "gb2_dist_allgather_dev",
 ]
 
 _lib = None
@@ -103,6 +104,10 @@ def load():
     lib.gb2_get_v.argtypes = [H, dp]
     lib.gb2_get_timings.argtypes = [H, dp]
     lib.gb2_set_option.argtypes = [H, C.c_char_p, C.c_int]
+    lib.gb2_nccl_unique_id.argtypes = [C.c_char_p]
+    lib.gb2_dist_init.argtypes = [H, C.c_int, C.c_int, C.c_char_p]
+    lib.gb2_dist_finalize.argtypes = [H]
+    lib.gb2_dist_allgather_dev.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int64]
     lib.gb2_mark.argtypes = [H, C.c_int]
     lib.gb2_elapsed_ms.argtypes = [H, C.c_int, C.c_int, dp]
     for name in EXPORTS:

@@ -34,9 +34,10 @@ class B200Backend:
     """Mixin with the three backend methods + ``fit``.  Expects the attributes ``Regressor.specify_model`` sets."""
 
     # -- construction -----------------------------------------------------------------------------------------------
-    def _init_backend(self, device=0, precision="fp64"):
+    def _init_backend(self, device=0, precision="fp64", distributed=False):
         self.device = device
         self.precision = precision
+        self.distributed = distributed   # True: join torch.distributed's default group (one process per GPU)
         self.engine = None
         self.MAP = None
         self.trace = None
@@ -113,6 +114,10 @@ class B200Backend:
         self._layout = self._model_layout()
         if self.engine is None:
             self.engine = GPEngine(self.device, self.precision)
+            if self.distributed:
+                from . import dist as gdist
+
+                gdist.init_engine(self.engine)   # collective: factorize() is row-block sharded across the ranks from here on
         self.engine.set_train(self._X, self._y)
         self._factor_key = None
         self.model = self._layout  # truthy placeholder: the reference asserts ``self.model is not None`` in find_MAP
@@ -265,6 +270,13 @@ class B200Backend:
             raise TypeError(f"unsupported predict arguments for the B200 backend: {sorted(kwargs)}")
         self._ensure_factorized()
         points_array = np.atleast_2d(np.asarray(points_array, dtype=np.float64))
+        if getattr(self.engine, "world", 1) > 1:
+            # every rank holds the factor: each serves a contiguous slice of the points, slices are gathered on all ranks
+            from . import dist as gdist
+
+            lo, hi = gdist.grid_slice(len(points_array), self.engine.rank, self.engine.world)
+            mu, var = self.engine.predict(points_array[lo:hi], pred_noise=bool(with_noise))
+            return gdist.gather_grid(mu, var, len(points_array))
         return self.engine.predict(points_array, pred_noise=bool(with_noise))
 
     def predict_cold(self, points_array, with_noise=True):
@@ -326,18 +338,18 @@ class ArrayRegressor:
 
 
 class ArrayGP(B200Backend, ArrayRegressor):
-    def __init__(self, X, y, continuous_dims, device=0, precision="fp64", **kwargs):
+    def __init__(self, X, y, continuous_dims, device=0, precision="fp64", distributed=False, **kwargs):
         ArrayRegressor.__init__(self, X, y, continuous_dims, **kwargs)
-        self._init_backend(device=device, precision=precision)
+        self._init_backend(device=device, precision=precision, distributed=distributed)
 
 
 def make_backend(regressor_base):
     """Create the drop-in ``B200GP`` subclass of Gumbi's ``Regressor`` (``gumbi.regression.base.Regressor``)."""
 
     class B200GP(B200Backend, regressor_base):
-        def __init__(self, dataset, outputs=None, seed=2021, device=0, precision="fp64"):
+        def __init__(self, dataset, outputs=None, seed=2021, device=0, precision="fp64", distributed=False):
             regressor_base.__init__(self, dataset, outputs, seed)
-            self._init_backend(device=device, precision=precision)
+            self._init_backend(device=device, precision=precision, distributed=distributed)
 
     B200GP.__doc__ = "Gumbi Regressor backend running the exact-GP dense path on a B200 (see gumbi_b200.backend)."
     return B200GP

@@ -9,6 +9,7 @@
 // Because row N of the augmented matrix holds y^T, the panel solves turn it into v^T = (L^-1 y)^T for free.
 #pragma once
 #include "dgemm.cuh"
+#include "tf32gemm.cuh"
 
 namespace gb2 {
 
@@ -103,7 +104,7 @@ __device__ __forceinline__ void pd_unit(double* C, const double* A, const double
 
 __global__ void __launch_bounds__(PD_THREADS, 1)
 potrf_diag_kernel(double* __restrict__ A, int64_t ld, int64_t g0, int64_t n_real, double* __restrict__ Dinv,
-                  int* __restrict__ info, long long* __restrict__ clk = nullptr) {
+                  int* __restrict__ info, double* __restrict__ Lpack = nullptr, long long* __restrict__ clk = nullptr) {
     extern __shared__ __align__(16) unsigned char pd_smem[];
     int clk_i = 0;
 #define PD_CLK() do { if (clk && threadIdx.x == 0) clk[clk_i++] = clock64(); } while (0)
@@ -253,7 +254,11 @@ potrf_diag_kernel(double* __restrict__ A, int64_t ld, int64_t g0, int64_t n_real
         const int pr = warp + q * NW, b = pr >> 5, r = pr & 31;
         const int bi = (b >= 6) ? 3 : (b >= 3) ? 2 : (b >= 1) ? 1 : 0;
         const int bj = b - bi * (bi + 1) / 2;
-        if (bi != bj || lane <= r) Ab[(int64_t)(bi * PB + r) * ld + bj * PB + lane] = Lb[b * PB_SZ + r * PB_LD + lane];
+        if (bi != bj || lane <= r) {
+            const double v = Lb[b * PB_SZ + r * PB_LD + lane];
+            Ab[(int64_t)(bi * PB + r) * ld + bj * PB + lane] = v;
+            if (Lpack) Lpack[(bi * PB + r) * TILE + bj * PB + lane] = v;   // contiguous copy for the multi-GPU broadcast
+        }
     }
     PD_CLK();
 
@@ -333,62 +338,189 @@ inline cudaError_t cholesky_configure() {
     return cudaSuccess;
 }
 
-// Enqueue the whole factorisation of h->dA (Np x Np).  Returns the number of kernel launches enqueued.
-inline int cholesky_enqueue(gb2_handle* h) {
-    const int64_t Np = h->Np, ld = h->Np;
-    const int nb = (int)(Np / TILE);
-    double* A = h->dA;
-    int launches = 0;
-    cudaStream_t sm = h->s_main, sp = h->opt_lookahead ? h->s_panel : h->s_main;
-    const bool two = h->opt_lookahead != 0;
-    // event pool: per step one "panel done" and one "next column updated"
-    while ((int)h->ev_pool.size() < 2 * nb + 2) {
+// 128x128 block copies between the factor storage (ld) and a packed buffer of contiguous 128x128 blocks.
+// blockIdx.x = block slot, blockIdx.y = 16-row slice.  dir 0: A -> packed, 1: packed -> A.
+// Slot s of rank `r` (owner-major order of an allgather) is global row block first[r] + s*G of column block k.
+__global__ void __launch_bounds__(256)
+panel_pack_kernel(double* __restrict__ A, int64_t ld, int64_t col0, double* __restrict__ packed, int dir, int G, int me, int nb, int k,
+                  int slots_per_rank, int only_rank) {
+    const int slot = blockIdx.x;
+    int r, li;
+    if (only_rank >= 0) { r = only_rank; li = slot; }              // pack: my own blocks, slots 0..cnt-1
+    else { r = slot / slots_per_rank; li = slot % slots_per_rank; if (r == me) return; }
+    const int first = k + 1 + (((r - (k + 1)) % G) + G) % G;
+    const int blk = first + li * G;
+    if (blk >= nb) return;
+    double* a = A + (int64_t)blk * TILE * ld + col0;
+    double* p = packed + ((int64_t)(only_rank >= 0 ? li : slot)) * TILE * TILE;
+    const int row0 = blockIdx.y * 8;
+    for (int e = threadIdx.x; e < 8 * (TILE / 2); e += 256) {
+        const int rr = row0 + e / (TILE / 2), c = (e % (TILE / 2)) * 2;
+        if (dir == 0) *reinterpret_cast<double2*>(p + rr * TILE + c) = *reinterpret_cast<const double2*>(a + (int64_t)rr * ld + c);
+        else *reinterpret_cast<double2*>(a + (int64_t)rr * ld + c) = *reinterpret_cast<const double2*>(p + rr * TILE + c);
+    }
+}
+
+// Minimal NCCL surface, bound at run time (dlopen) so that the library loads on machines without NCCL and never pulls a
+// second copy next to the one torch.distributed already loaded.
+struct NcclId { char bytes[128]; };   // ncclUniqueId
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+constexpr int NCCL_FLOAT64 = 8;  // ncclDataType_t ncclFloat64 / ncclDouble
+
+inline cudaEvent_t pool_event(gb2_handle* h, int idx) {
+    while ((int)h->ev_pool.size() <= idx) {
         cudaEvent_t e;
         cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
         h->ev_pool.push_back(e);
     }
-    if (two) {  // panel stream starts after everything already queued on main (the K build)
-        cudaEventRecord(h->ev_pool[2 * nb], sm);
-        cudaStreamWaitEvent(sp, h->ev_pool[2 * nb], 0);
+    return h->ev_pool[idx];
+}
+
+// Block steps k0 <= k < k1 of the right-looking factorisation, with every trailing update restricted to column blocks
+// < col_limit (col_limit = nb: the plain algorithm; col_limit = k1: factor a block-column panel only and leave the rest of the
+// trailing matrix to the caller -- the GB2_TF32 driver below applies that part with tcgen05).
+inline int factor_steps(gb2_handle* h, int k0, int k1, int col_limit) {
+    const int64_t Np = h->Np, ld = h->Np;
+    const int nb = (int)(Np / TILE);
+    const int G = h->world, me = h->rank;
+    const NcclApi* nc = h->nccl;
+    double* A = h->dA;
+    int launches = 0;
+    cudaStream_t sm = h->s_main, sp = (h->opt_lookahead || G > 1) ? h->s_panel : h->s_main;
+    const bool two = sp != sm;
+    if (two) {  // the panel stream starts after everything already queued on main (the K build / the previous trailing update)
+        cudaEvent_t e = pool_event(h, 2 * nb);
+        cudaEventRecord(e, sm);
+        cudaStreamWaitEvent(sp, e, 0);
     }
-    for (int k = 0; k < nb; k++) {
+    auto first_owned_after = [&](int k, int r) { return k + 1 + (((r - (k + 1)) % G) + G) % G; };   // smallest block > k owned by r
+    auto count_from = [&](int first) { return first < nb ? (nb - first + G - 1) / G : 0; };
+    for (int k = k0; k < k1; k++) {
         const int64_t g0 = (int64_t)k * TILE;
         const int64_t below = Np - g0 - TILE;
-        potrf_diag_kernel<<<1, PD_THREADS, PD_SMEM, sp>>>(A, ld, g0, h->N, h->dDinv + (int64_t)k * TILE * TILE, h->dInfo);
-        launches++;
+        const int owner = k % G;
+        double* Dk = h->dDinv + (int64_t)k * TILE * TILE;
+        double* Lk = G > 1 ? h->dLpack + (int64_t)k * TILE * TILE : nullptr;
+        if (owner == me) {
+            potrf_diag_kernel<<<1, PD_THREADS, PD_SMEM, sp>>>(A, ld, g0, h->N, Dk, h->dInfo, Lk);
+            launches++;
+        }
+        if (G > 1) {
+            nc->GroupStart();
+            nc->Broadcast(Dk, Dk, (size_t)TILE * TILE, NCCL_FLOAT64, owner, h->comm, sp);
+            nc->Broadcast(Lk, Lk, (size_t)TILE * TILE, NCCL_FLOAT64, owner, h->comm, sp);
+            nc->GroupEnd();
+            launches++;
+            if (owner != me)
+                cudaMemcpy2DAsync(A + g0 * ld + g0, ld * sizeof(double), Lk, TILE * sizeof(double), TILE * sizeof(double), TILE,
+                                  cudaMemcpyDeviceToDevice, sp);
+        }
         if (below > 0) {
-            double* panel = A + (g0 + TILE) * ld + g0;  // rows below the diagonal block, columns of block k
-            dgemm_nt_launch<64, 128, GM_SET>(sp, panel, ld, h->dDinv + (int64_t)k * TILE * TILE, TILE, panel, ld, below, TILE,
-                                             TILE, 0, 0, 0);
-            launches++;
-            if (two) {
-                cudaEventRecord(h->ev_pool[2 * k], sp);
-                cudaStreamWaitEvent(sm, h->ev_pool[2 * k], 0);
-            }
-            // next panel column first
-            double* C1 = A + (g0 + TILE) * ld + (g0 + TILE);
-            dgemm_nt_launch<128, 64, GM_SUB>(sm, panel, ld, panel, ld, C1, ld, below, TILE, TILE, 1, g0 + TILE, g0 + TILE);
-            launches++;
-            if (two) {
-                cudaEventRecord(h->ev_pool[2 * k + 1], sm);
-                cudaStreamWaitEvent(sp, h->ev_pool[2 * k + 1], 0);
-            }
-            if (below > TILE) {
-                // rest of the trailing matrix: rows from g0+2T, columns from g0+2T
-                const double* Arows = panel + (int64_t)TILE * ld;  // L[i,k], i >= k+2
-                const double* Brows = panel + (int64_t)TILE * ld;  // L[j,k], j >= k+2
-                double* C2 = A + (g0 + 2 * TILE) * ld + (g0 + 2 * TILE);
-                dgemm_nt_launch<128, 64, GM_SUB>(sm, Arows, ld, Brows, ld, C2, ld, below - TILE, below - TILE, TILE, 1,
-                                                 g0 + 2 * TILE, g0 + 2 * TILE);
+            const int f1 = first_owned_after(k, me), c1 = count_from(f1);         // owned blocks > k
+            double* colk = A + g0;                                                   // column block k, row 0
+            if (c1 > 0) {
+                dgemm_nt_launch<64, 128, GM_SET>(sp, colk, ld, Dk, TILE, colk, ld, (int64_t)c1 * TILE, TILE, TILE, 0, 0, 0, f1, G);
                 launches++;
+            }
+            if (G > 1) {
+                const int cmax = count_from(k + 1);                                  // most blocks any rank owns below k
+                if (c1 > 0) {
+                    panel_pack_kernel<<<dim3(c1, TILE / 8), 256, 0, sp>>>(A, ld, g0, h->dSend, 0, G, me, nb, k, cmax, me);
+                    launches++;
+                }
+                nc->AllGather(h->dSend, h->dRecv, (size_t)cmax * TILE * TILE, NCCL_FLOAT64, h->comm, sp);
+                panel_pack_kernel<<<dim3(cmax * G, TILE / 8), 256, 0, sp>>>(A, ld, g0, h->dRecv, 1, G, me, nb, k, cmax, -1);
+                launches += 2;
+            }
+            if (two) {
+                cudaEvent_t e = pool_event(h, 2 * k);
+                cudaEventRecord(e, sp);
+                cudaStreamWaitEvent(sm, e, 0);
+            }
+            // next panel column first: A[i, k+1] -= L[i,k] L[k+1,k]^T for owned i >= k+1
+            if (c1 > 0 && k + 1 < col_limit) {
+                dgemm_nt_launch<128, 64, GM_SUB>(sm, colk, ld, A + (g0 + TILE) * ld + g0, ld, A + g0 + TILE, ld, (int64_t)c1 * TILE, TILE,
+                                                 TILE, 1, 0, g0 + TILE, f1, G);
+                launches++;
+            }
+            if (two) {
+                cudaEvent_t e = pool_event(h, 2 * k + 1);
+                cudaEventRecord(e, sm);
+                cudaStreamWaitEvent(sp, e, 0);
+            }
+            if (k + 2 < col_limit) {
+                // rest of the trailing matrix: owned rows >= k+2, column blocks k+2 .. col_limit-1
+                const int f2 = first_owned_after(k + 1, me), c2 = count_from(f2);
+                if (c2 > 0) {
+                    dgemm_nt_launch<128, 64, GM_SUB>(sm, colk, ld, A + (g0 + 2 * TILE) * ld + g0, ld, A + g0 + 2 * TILE, ld,
+                                                     (int64_t)c2 * TILE, (int64_t)(col_limit - (k + 2)) * TILE, TILE, 1, 0,
+                                                     g0 + 2 * TILE, f2, G);
+                    launches++;
+                }
             }
         }
     }
     if (two) {  // join
-        cudaEventRecord(h->ev_pool[2 * nb + 1], sp);
-        cudaStreamWaitEvent(sm, h->ev_pool[2 * nb + 1], 0);
+        cudaEvent_t e = pool_event(h, 2 * nb + 1);
+        cudaEventRecord(e, sp);
+        cudaStreamWaitEvent(sm, e, 0);
     }
-    mll_terms_kernel<<<1, 1024, 0, sm>>>(A, ld, h->N, h->dScal);
+    return launches;
+}
+
+// Enqueue the whole factorisation of h->dA (Np x Np).  Returns the number of kernel launches enqueued.
+//
+// Multi-GPU (h->world > 1): 128-row blocks are owned block-cyclically (block i -> rank i % world).  Every rank
+// keeps the full-size buffer but builds/updates only the rows it owns; per block step
+//   owner:      potrf_diag(k)                                    -> L_kk, inv(L_kk)
+//   all:        ncclBroadcast(inv(L_kk), L_kk)                    (256 KB)
+//   all:        L[i,k] = A[i,k] inv(L_kk)^T  for owned i > k      (local rows of the panel)
+//   all:        pack -> ncclAllGather -> unpack                   (every rank now holds the whole panel column k)
+//   all:        trailing update of the owned rows (next column first = look-ahead), exactly as on one GPU.
+// When the loop ends every rank holds the complete factor (each panel was gathered everywhere), so predict() runs locally
+// on whatever slice of the prediction grid the rank is given.
+//
+// GB2_TF32 (single GPU): block columns are grouped in panels of h->opt_tf32_nb blocks (default 4 = 512 columns).  A panel is
+// factored in fp64 by factor_steps (DMMA), split into tf32 hi/lo pairs, and the whole trailing matrix is updated by ONE
+// tcgen05 split-TF32 SYRK of depth 512 (tf32gemm.cuh) -- 8x fewer passes over the trailing matrix than the 128-wide steps.
+inline int cholesky_enqueue(gb2_handle* h) {
+    const int64_t Np = h->Np, ld = h->Np;
+    const int nb = (int)(Np / TILE);
+    int launches = 0;
+    const int pw = h->opt_tf32_nb;
+    if (h->precision == GB2_TF32 && h->world == 1 && nb > pw) {
+        cudaStream_t sm = h->s_main;
+        for (int c0 = 0; c0 < nb; c0 += pw) {
+            const int c1 = c0 + pw < nb ? c0 + pw : nb;
+            launches += factor_steps(h, c0, c1, c1);
+            if (c1 >= nb) break;
+            const int64_t rows = Np - (int64_t)c1 * TILE, cols = (int64_t)(c1 - c0) * TILE;
+            const int64_t pld = (int64_t)pw * TILE;
+            tc::split_tf32_kernel<<<(unsigned)((rows * cols / 2 + 255) / 256), 256, 0, sm>>>(
+                h->dA + (int64_t)c1 * TILE * ld + (int64_t)c0 * TILE, ld, rows, cols, h->dPhi + (int64_t)c1 * TILE * pld,
+                h->dPlo + (int64_t)c1 * TILE * pld, pld);
+            launches++;
+            tc::GemmArgs g{};
+            g.C = h->dA; g.ldc = ld;
+            g.n_bi = nb - c1; g.n_bj = nb - c1;
+            g.rb_first = c1; g.rb_stride = 1; g.cblk0 = c1; g.lower = 1;
+            g.a_k0 = 0; g.b_row0 = c1 * TILE; g.b_k0 = 0;
+            tc::gemm_tf32x3_launch(sm, h->n_sm, h->mPhi, h->mPlo, h->mPhi, h->mPlo, g, (int)cols, launches);
+        }
+    } else {
+        launches += factor_steps(h, 0, nb, nb);
+    }
+    mll_terms_kernel<<<1, 1024, 0, h->s_main>>>(h->dA, ld, h->N, h->dScal);
     launches++;
     return launches;
 }

@@ -44,13 +44,21 @@ constexpr size_t dgemm_smem_bytes() { return (size_t)GM_STAGES * (BM + BN) * GM_
 // lower_only: skip tiles lying strictly above the diagonal of the global matrix, where tile (0,0) sits at
 // global (row_off, col_off).  In GM_SET mode C may alias A (in-place right-multiplication of a row panel):
 // each CTA owns complete rows and has consumed all of its A rows before the epilogue stores.
+//
+// Row-block sharding (multi-GPU factorisation): the rows a launch covers may be every `rb_stride`-th 128-row
+// block starting at block `rb_first` (block-cyclic ownership); row tile bi then sits at row
+//   ((rb_first + (bi / (128/BM)) * rb_stride) * 128 + (bi % (128/BM)) * BM   relative to the A / C base pointers.
+// rb_first = 0, rb_stride = 1 is the dense case.
 template <int BM, int BN, int MODE>
 __global__ void __launch_bounds__(GM_THREADS, 2)
 dgemm_nt_kernel(const double* A, int64_t lda, const double* __restrict__ B, int64_t ldb, double* C, int64_t ldc,
-                int kdepth, int lower_only, int64_t row_off, int64_t col_off) {
+                int kdepth, int lower_only, int64_t row_off, int64_t col_off, int rb_first, int rb_stride) {
     static_assert((BM / 32) * (BN / 32) == GM_THREADS / 32, "8 warps of 32x32");
+    static_assert(TILE % BM == 0, "row tiles must not straddle 128-row blocks");
     const int bi = blockIdx.x, bj = blockIdx.y;
-    if (lower_only && col_off + (int64_t)bj * BN > row_off + (int64_t)bi * BM + (BM - 1)) return;
+    constexpr int TPB = TILE / BM;
+    const int64_t grow = ((int64_t)rb_first + (int64_t)(bi / TPB) * rb_stride) * TILE + (int64_t)(bi % TPB) * BM;
+    if (lower_only && col_off + (int64_t)bj * BN > row_off + grow + (BM - 1)) return;
 
     extern __shared__ __align__(16) unsigned char gm_smem[];
     double* sA = reinterpret_cast<double*>(gm_smem);
@@ -60,7 +68,7 @@ dgemm_nt_kernel(const double* A, int64_t lda, const double* __restrict__ B, int6
     const int wm = warp % (BM / 32), wn = warp / (BM / 32);
     const int g = lane >> 2, t = lane & 3;
 
-    const double* Ag = A + (int64_t)bi * BM * lda;
+    const double* Ag = A + grow * lda;
     const double* Bg = B + (int64_t)bj * BN * ldb;
 
     auto load_stage = [&](int stage, int kt) {
@@ -114,7 +122,7 @@ dgemm_nt_kernel(const double* A, int64_t lda, const double* __restrict__ B, int6
     }
     cp_async_wait<0>();
 
-    double* Cg = C + ((int64_t)bi * BM + wm * 32 + g) * ldc + (int64_t)bj * BN + wn * 32 + 2 * t;
+    double* Cg = C + (grow + wm * 32 + g) * ldc + (int64_t)bj * BN + wn * 32 + 2 * t;
 #pragma unroll
     for (int mi = 0; mi < 4; mi++)
 #pragma unroll
@@ -141,11 +149,11 @@ inline cudaError_t dgemm_nt_configure() {
 template <int BM, int BN, int MODE>
 inline void dgemm_nt_launch(cudaStream_t s, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                             int64_t ldc, int64_t rows, int64_t cols, int kdepth, int lower_only, int64_t row_off,
-                            int64_t col_off) {
+                            int64_t col_off, int rb_first = 0, int rb_stride = 1) {
     if (rows <= 0 || cols <= 0 || kdepth <= 0) return;
     dim3 grid((unsigned)(rows / BM), (unsigned)(cols / BN));
     dgemm_nt_kernel<BM, BN, MODE><<<grid, GM_THREADS, dgemm_smem_bytes<BM, BN>(), s>>>(A, lda, B, ldb, C, ldc, kdepth,
-                                                                                      lower_only, row_off, col_off);
+                                                                                      lower_only, row_off, col_off, rb_first, rb_stride);
 }
 
 }  // namespace gb2

@@ -3,6 +3,8 @@
 #include "predict.cuh"
 #include "mllgrad.cuh"
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <new>
@@ -52,6 +54,15 @@ int validate_against_train(gb2_handle* h) {
     return 0;
 }
 
+int make_tmap_checked(gb2_handle* h, CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int64_t ld) {
+    const CUresult r = tc::make_tmap(map, ptr, (uint64_t)rows, (uint64_t)cols, (uint64_t)ld);
+    if (r != CUDA_SUCCESS) {
+        h->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")";
+        return -300 - (int)r;
+    }
+    return 0;
+}
+
 double ms_between(cudaEvent_t a, cudaEvent_t b) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, a, b);
@@ -71,6 +82,35 @@ int predict_common(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_nois
     const int ncols = (int)((N + TILE - 1) / TILE);  // column blocks that carry training points
     int rc;
     if ((rc = ensure(h, h->dAt, h->At_cap, chunk * Np))) return rc;
+    const bool tf32 = h->precision == GB2_TF32 && ncols > h->opt_tf32_nb;
+    if (tf32) {
+        // tf32 hi/lo copies: the factor (once per factorisation) and the solved panel (per chunk)
+        if (h->Lsplit_cap < Np * Np) {
+            if (h->dLhi) GB2_CUDA(h, cudaFree(h->dLhi));
+            if (h->dLlo) GB2_CUDA(h, cudaFree(h->dLlo));
+            h->dLhi = h->dLlo = nullptr; h->Lsplit_cap = 0;
+            GB2_CUDA(h, cudaMalloc(&h->dLhi, (size_t)Np * Np * sizeof(float)));
+            GB2_CUDA(h, cudaMalloc(&h->dLlo, (size_t)Np * Np * sizeof(float)));
+            h->Lsplit_cap = Np * Np;
+            h->L_split_valid = false;
+        }
+        if (!h->L_split_valid) {
+            if ((rc = make_tmap_checked(h, &h->mLhi, h->dLhi, Np, Np, Np))) return rc;
+            if ((rc = make_tmap_checked(h, &h->mLlo, h->dLlo, Np, Np, Np))) return rc;
+            tc::split_tf32_kernel<<<(unsigned)((Np * Np / 2 + 255) / 256), 256, 0, h->s_main>>>(h->dA, Np, Np, Np, h->dLhi, h->dLlo, Np);
+            h->L_split_valid = true;
+        }
+        if (h->Atsplit_cap < chunk * Np) {
+            if (h->dAthi) GB2_CUDA(h, cudaFree(h->dAthi));
+            if (h->dAtlo) GB2_CUDA(h, cudaFree(h->dAtlo));
+            h->dAthi = h->dAtlo = nullptr; h->Atsplit_cap = 0;
+            GB2_CUDA(h, cudaMalloc(&h->dAthi, (size_t)chunk * Np * sizeof(float)));
+            GB2_CUDA(h, cudaMalloc(&h->dAtlo, (size_t)chunk * Np * sizeof(float)));
+            h->Atsplit_cap = chunk * Np;
+        }
+        if ((rc = make_tmap_checked(h, &h->mAthi, h->dAthi, chunk, Np, Np))) return rc;
+        if ((rc = make_tmap_checked(h, &h->mAtlo, h->dAtlo, chunk, Np, Np))) return rc;
+    }
     if ((rc = ensure(h, h->dFs, h->Fs_cap, (int64_t)std::max(1, h->kp.n_feat) * chunk))) return rc;
     if ((rc = ensure(h, h->dCs, h->Cs_cap, (int64_t)std::max(1, h->kp.n_cat) * chunk))) return rc;
     const double* dXs_all = Xs;
@@ -95,10 +135,11 @@ int predict_common(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_nois
         GB2_CUDA(h, cudaEventRecord(h->ev[1], s));
         dim3 grid((unsigned)(Np / KB_T), (unsigned)(Mp / KB_T));
         kbuild_kernel<false><<<grid, KB_THREADS, kbuild_smem_bytes(h->kp), s>>>(h->kp, h->dBtab, h->dFs, h->dCs, Mp, Mc, h->dF, h->dC, Np, N,
-                                                                                 nullptr, h->dAt, Np);
+                                                                                 nullptr, h->dAt, Np, 1, 0);
         GB2_CUDA(h, cudaEventRecord(h->ev[2], s));
         launches += 2;
-        trsm_rec(s, h->dA, Np, h->dDinv, h->dAt, Np, Mp, 0, ncols, launches);
+        if (tf32) trsm_rec_tf32(h, s, Mp, 0, ncols, ncols, h->opt_tf32_nb, launches);
+        else trsm_rec(s, h->dA, Np, h->dDinv, h->dAt, Np, Mp, 0, ncols, launches);
         GB2_CUDA(h, cudaEventRecord(h->ev[3], s));
         posterior_reduce_kernel<<<(unsigned)((Mc + 7) / 8), 256, 0, s>>>(h->kp, h->dBtab, h->dFs, h->dCs, Mp, h->dAt, Np, h->dA + N * Np, N, Mc,
                                                                         pred_noise, dmean_all + m0, dvar_all + m0);
@@ -166,6 +207,8 @@ int gb2_create(gb2_handle** out, int device, int precision) {
     if ((e = cudaMalloc(&h->dInfo, 4 * sizeof(int))) != cudaSuccess) return fail(e, "cudaMalloc");
     if ((e = cudaMalloc(&h->dScal, 4 * sizeof(double))) != cudaSuccess) return fail(e, "cudaMalloc");
     if ((e = cholesky_configure()) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
+    if ((e = tc::gemm_tf32x3_configure()) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
+    h->n_sm = prop.multiProcessorCount;
     if ((e = cudaFuncSetAttribute(kbuild_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
     if ((e = cudaFuncSetAttribute(kbuild_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
     if ((e = cudaFuncSetAttribute(mll_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 164 * 1024)) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
@@ -178,10 +221,13 @@ int gb2_destroy(gb2_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    if (h->comm && h->nccl) { h->nccl->CommDestroy(h->comm); h->comm = nullptr; }
+    cudaFree(h->dLpack); cudaFree(h->dSend); cudaFree(h->dRecv);
     cudaFree(h->dX); cudaFree(h->dy); cudaFree(h->dBtab); cudaFree(h->dF); cudaFree(h->dC); cudaFree(h->dA);
     cudaFree(h->dDinv); cudaFree(h->dInfo); cudaFree(h->dScal); cudaFree(h->dXs); cudaFree(h->dFs); cudaFree(h->dCs);
     cudaFree(h->dAt); cudaFree(h->dMean); cudaFree(h->dVar);
     cudaFree(h->dW); cudaFree(h->dS); cudaFree(h->dAlpha); cudaFree(h->dGrad);
+    cudaFree(h->dPhi); cudaFree(h->dPlo); cudaFree(h->dLhi); cudaFree(h->dLlo); cudaFree(h->dAthi); cudaFree(h->dAtlo);
     for (auto ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto ev : h->ev_pool) cudaEventDestroy(ev);
     for (auto ev : h->ev_mark) if (ev) cudaEventDestroy(ev);
@@ -299,13 +345,41 @@ static int build_K(gb2_handle* h, int& launches) {
         GB2_CUDA(h, cudaMemsetAsync(h->dDinv, 0, (size_t)Np * TILE * sizeof(double), s));
         h->A_cap = Np;
     }
+    if (h->precision == GB2_TF32) {
+        const int64_t pld = (int64_t)h->opt_tf32_nb * TILE;
+        if (h->P_cap < Np * pld) {
+            if (h->dPhi) GB2_CUDA(h, cudaFree(h->dPhi));
+            if (h->dPlo) GB2_CUDA(h, cudaFree(h->dPlo));
+            h->dPhi = h->dPlo = nullptr; h->P_cap = 0;
+            GB2_CUDA(h, cudaMalloc(&h->dPhi, (size_t)Np * pld * sizeof(float)));
+            GB2_CUDA(h, cudaMalloc(&h->dPlo, (size_t)Np * pld * sizeof(float)));
+            h->P_cap = Np * pld;
+        }
+        int rc2;
+        if ((rc2 = make_tmap_checked(h, &h->mPhi, h->dPhi, Np, pld, pld))) return rc2;
+        if ((rc2 = make_tmap_checked(h, &h->mPlo, h->dPlo, Np, pld, pld))) return rc2;
+    }
+    if (h->world > 1 && h->xch_cap < Np) {
+        // broadcast payload for the diagonal blocks + staging of the per-step panel allgather (<= ceil(nb/world) blocks per rank)
+        if (h->dLpack) GB2_CUDA(h, cudaFree(h->dLpack));
+        if (h->dSend) GB2_CUDA(h, cudaFree(h->dSend));
+        if (h->dRecv) GB2_CUDA(h, cudaFree(h->dRecv));
+        h->dLpack = h->dSend = h->dRecv = nullptr; h->xch_cap = 0;
+        const int64_t nb = Np / TILE, per_rank = (nb + h->world - 1) / h->world;
+        GB2_CUDA(h, cudaMalloc(&h->dLpack, (size_t)Np * TILE * sizeof(double)));
+        GB2_CUDA(h, cudaMemsetAsync(h->dLpack, 0, (size_t)Np * TILE * sizeof(double), s));
+        GB2_CUDA(h, cudaMalloc(&h->dSend, (size_t)per_rank * TILE * TILE * sizeof(double)));
+        GB2_CUDA(h, cudaMalloc(&h->dRecv, (size_t)per_rank * h->world * TILE * TILE * sizeof(double)));
+        GB2_CUDA(h, cudaMemsetAsync(h->dSend, 0, (size_t)per_rank * TILE * TILE * sizeof(double), s));
+        h->xch_cap = Np;
+    }
     GB2_CUDA(h, cudaMemsetAsync(h->dInfo, 0, 4 * sizeof(int), s));
     GB2_CUDA(h, cudaEventRecord(h->ev[0], s));
     prep_features<<<(unsigned)((Np + 255) / 256), 256, 0, s>>>(h->dX, N, Np, h->pp, h->dF, h->dC, h->dInfo + 1);
     GB2_CUDA(h, cudaEventRecord(h->ev[1], s));
     dim3 grid((unsigned)(Np / KB_T), (unsigned)(Np / KB_T));
     kbuild_kernel<true><<<grid, KB_THREADS, kbuild_smem_bytes(h->kp), s>>>(h->kp, h->dBtab, h->dF, h->dC, Np, N, h->dF, h->dC, Np, N, h->dy,
-                                                                            h->dA, Np);
+                                                                            h->dA, Np, h->world, h->rank);
     GB2_CUDA(h, cudaEventRecord(h->ev[2], s));
     launches += 2;
     return 0;
@@ -317,6 +391,7 @@ int gb2_factorize(gb2_handle* h) {
     GB2_ARG(h, h->have_kernel, "gb2_factorize: no kernel (call gb2_set_kernel)");
     GB2_CUDA(h, cudaSetDevice(h->device));
     h->factorized = false;
+    h->L_split_valid = false;
     int launches = 0, rc;
     if ((rc = build_K(h, launches))) return rc;
     launches += cholesky_enqueue(h);
@@ -474,9 +549,102 @@ int gb2_elapsed_ms(gb2_handle* h, int a, int b, double* ms) {
     return 0;
 }
 
+// ---- multi-GPU: NCCL bound at run time ---------------------------------------------------------------------------
+static NcclApi g_nccl;
+static std::string g_nccl_err;
+
+static const NcclApi* load_nccl() {
+    if (g_nccl.lib) return &g_nccl;
+    // prefer a copy that is already mapped (torch.distributed's), then the usual sonames
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) { g_nccl_err = std::string("cannot load libnccl.so.2: ") + dlerror(); return nullptr; }
+    NcclApi a;
+    a.lib = lib;
+#define GB2_SYM(field, name)                                                                          \
+    *(void**)(&a.field) = dlsym(lib, name);                                                           \
+    if (!a.field) { g_nccl_err = std::string("libnccl has no symbol ") + name; return nullptr; }
+    GB2_SYM(GetUniqueId, "ncclGetUniqueId")
+    GB2_SYM(CommInitRank, "ncclCommInitRank")
+    GB2_SYM(CommDestroy, "ncclCommDestroy")
+    GB2_SYM(Broadcast, "ncclBroadcast")
+    GB2_SYM(AllGather, "ncclAllGather")
+    GB2_SYM(GroupStart, "ncclGroupStart")
+    GB2_SYM(GroupEnd, "ncclGroupEnd")
+    GB2_SYM(GetErrorString, "ncclGetErrorString")
+#undef GB2_SYM
+    g_nccl = a;
+    return &g_nccl;
+}
+
+int gb2_nccl_unique_id(char* out128) {
+    if (!out128) { g_create_err = "invalid argument: out128 is null"; return -1; }
+    const NcclApi* nc = load_nccl();
+    if (!nc) { g_create_err = g_nccl_err; return -5; }
+    NcclId id;
+    const int rc = nc->GetUniqueId(&id);
+    if (rc != 0) { g_create_err = std::string("ncclGetUniqueId: ") + nc->GetErrorString(rc); return -200 - rc; }
+    memcpy(out128, id.bytes, sizeof(id.bytes));
+    return 0;
+}
+
+int gb2_dist_init(gb2_handle* h, int rank, int world, const char* unique_id128) {
+    if (!h) return -1;
+    GB2_ARG(h, world >= 1 && rank >= 0 && rank < world, "gb2_dist_init: need 0 <= rank < world");
+    GB2_ARG(h, !h->comm, "gb2_dist_init: already initialised");
+    if (world == 1) { h->rank = 0; h->world = 1; return 0; }
+    GB2_ARG(h, unique_id128 != nullptr, "gb2_dist_init: unique id is null");
+    const NcclApi* nc = load_nccl();
+    if (!nc) { h->err = g_nccl_err; return -5; }
+    GB2_CUDA(h, cudaSetDevice(h->device));
+    NcclId id;
+    memcpy(id.bytes, unique_id128, sizeof(id.bytes));
+    void* comm = nullptr;
+    const int rc = nc->CommInitRank(&comm, world, id, rank);
+    if (rc != 0) { h->err = std::string("ncclCommInitRank: ") + nc->GetErrorString(rc); return -200 - rc; }
+    h->nccl = nc; h->comm = comm; h->rank = rank; h->world = world;
+    h->factorized = false;
+    return 0;
+}
+
+int gb2_dist_allgather_dev(gb2_handle* h, const double* dsend, double* drecv, int64_t count) {
+    if (!h) return -1;
+    GB2_ARG(h, dsend && drecv && count >= 0, "gb2_dist_allgather_dev: bad arguments");
+    GB2_CUDA(h, cudaSetDevice(h->device));
+    if (h->world == 1) {
+        if (dsend != drecv) GB2_CUDA(h, cudaMemcpyAsync(drecv, dsend, (size_t)count * sizeof(double), cudaMemcpyDeviceToDevice, h->s_main));
+    } else {
+        const int rc = h->nccl->AllGather(dsend, drecv, (size_t)count, NCCL_FLOAT64, h->comm, h->s_main);
+        if (rc != 0) { h->err = std::string("ncclAllGather: ") + h->nccl->GetErrorString(rc); return -200 - rc; }
+    }
+    GB2_CUDA(h, cudaStreamSynchronize(h->s_main));
+    return 0;
+}
+
+int gb2_dist_finalize(gb2_handle* h) {
+    if (!h) return -1;
+    if (h->comm) {
+        cudaSetDevice(h->device);
+        cudaDeviceSynchronize();
+        h->nccl->CommDestroy(h->comm);
+        h->comm = nullptr;
+    }
+    h->rank = 0; h->world = 1;
+    h->factorized = false;
+    return 0;
+}
+
 int gb2_set_option(gb2_handle* h, const char* name, int value) {
     if (!h || !name) return -1;
     if (!strcmp(name, "lookahead")) { h->opt_lookahead = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "tf32_nb")) {   // panel width of the GB2_TF32 factorisation / leaf width of its solve, in 128-column blocks
+        GB2_ARG(h, value >= 1 && value <= 16, "tf32_nb must be in [1, 16]");
+        h->opt_tf32_nb = value; h->P_cap = 0; h->factorized = false;
+        if (h->dPhi) { cudaFree(h->dPhi); h->dPhi = nullptr; }
+        if (h->dPlo) { cudaFree(h->dPlo); h->dPlo = nullptr; }
+        return 0;
+    }
     h->err = std::string("unknown option: ") + name;
     return -1;
 }

@@ -1,5 +1,6 @@
 // Internal declarations shared by the kernels of the gumbi_b200 core (one translation unit).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -48,6 +49,8 @@ struct PrepParams {
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+struct NcclApi;
+
 }  // namespace gb2
 
 struct gb2_handle {
@@ -94,7 +97,23 @@ struct gb2_handle {
     double eta_host[GB2_MAX_TERMS] = {0, 0, 0, 0};
     double sigma_host = 0.0;
 
+    // multi-GPU row-block sharding of the factorisation (gb2_dist_init); world == 1: single GPU
+    int rank = 0, world = 1;
+    const gb2::NcclApi* nccl = nullptr;
+    void* comm = nullptr;       // ncclComm_t
+    double* dLpack = nullptr;   // (Np/TILE, TILE, TILE) contiguous copies of the diagonal blocks of L (broadcast payload)
+    double* dSend = nullptr; double* dRecv = nullptr; int64_t xch_cap = 0;   // panel allgather staging
+
+    // GB2_TF32: tf32 hi/lo splits + their TMA descriptors (tf32gemm.cuh)
+    int n_sm = 148;
+    float* dPhi = nullptr; float* dPlo = nullptr; int64_t P_cap = 0;       // (Np, opt_tf32_nb*TILE) current factor panel
+    float* dLhi = nullptr; float* dLlo = nullptr; int64_t Lsplit_cap = 0;  // (Np, Np) the factor, for the predict solve
+    float* dAthi = nullptr; float* dAtlo = nullptr; int64_t Atsplit_cap = 0;  // (chunk, Np) solved prediction panel
+    CUtensorMap mPhi{}, mPlo{}, mLhi{}, mLlo{}, mAthi{}, mAtlo{};
+    bool L_split_valid = false;
+
     // options
+    int opt_tf32_nb = 4;
     int opt_lookahead = 1;
 
     // timing

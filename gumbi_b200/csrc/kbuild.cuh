@@ -72,9 +72,11 @@ __global__ void __launch_bounds__(KB_THREADS)
 kbuild_kernel(KParams kp, const double* __restrict__ Btab,
               const double* __restrict__ Fi, const int* __restrict__ Ci, int64_t stride_i, int64_t n_i,
               const double* __restrict__ Fj, const int* __restrict__ Cj, int64_t stride_j, int64_t n_j,
-              const double* __restrict__ y, double* __restrict__ out, int64_t ld) {
+              const double* __restrict__ y, double* __restrict__ out, int64_t ld, int own_stride, int own_rank) {
     const int bi = blockIdx.y, bj = blockIdx.x;
     if (TRAIN && bj > bi) return;
+    // multi-GPU row-block sharding: this rank builds only the 128-row blocks it owns (block-cyclic)
+    if (TRAIN && own_stride > 1 && ((bi * KB_T) / TILE) % own_stride != own_rank) return;
     extern __shared__ __align__(16) unsigned char kb_smem[];
     const int nf = kp.n_feat, nc = kp.n_cat;
     double* sFi = reinterpret_cast<double*>(kb_smem);

@@ -25,6 +25,35 @@ inline void trsm_rec(cudaStream_t s, const double* L, int64_t ld, const double* 
     trsm_rec(s, L, ld, Dinv, At, ldt, Mp, mid, c1, launches);
 }
 
+// GB2_TF32 variant: sub-solves of up to `leaf` column blocks stay in fp64 (DMMA); every larger off-diagonal product of the
+// recursion runs as a tcgen05 split-TF32 GEMM on the tf32 hi/lo copies of L (mLhi/mLlo) and of the already solved columns of
+// At (mAthi/mAtlo, refreshed after each leaf).  n_total = number of column blocks of the whole solve (no split needed for the
+// last columns, nothing to their right consumes them).
+inline void trsm_rec_tf32(gb2_handle* h, cudaStream_t s, int64_t Mp, int c0, int c1, int n_total, int leaf, int& launches) {
+    const int64_t Np = h->Np;
+    if (c1 - c0 <= leaf) {
+        trsm_rec(s, h->dA, Np, h->dDinv, h->dAt, Np, Mp, c0, c1, launches);
+        if (c1 < n_total) {
+            const int64_t cols = (int64_t)(c1 - c0) * TILE;
+            tc::split_tf32_kernel<<<(unsigned)((Mp * cols / 2 + 255) / 256), 256, 0, s>>>(h->dAt + (int64_t)c0 * TILE, Np, Mp, cols,
+                                                                                         h->dAthi + (int64_t)c0 * TILE,
+                                                                                         h->dAtlo + (int64_t)c0 * TILE, Np);
+            launches++;
+        }
+        return;
+    }
+    const int half = (c1 - c0 + 1) / 2;
+    const int mid = c0 + (half + leaf - 1) / leaf * leaf;
+    trsm_rec_tf32(h, s, Mp, c0, mid, n_total, leaf, launches);
+    tc::GemmArgs g{};
+    g.C = h->dAt; g.ldc = Np;
+    g.n_bi = (int)(Mp / TILE); g.n_bj = c1 - mid;
+    g.rb_first = 0; g.rb_stride = 1; g.cblk0 = mid; g.lower = 0;
+    g.a_k0 = c0 * TILE; g.b_row0 = mid * TILE; g.b_k0 = c0 * TILE;
+    tc::gemm_tf32x3_launch(s, h->n_sm, h->mAthi, h->mAtlo, h->mLhi, h->mLlo, g, (mid - c0) * TILE, launches);
+    trsm_rec_tf32(h, s, Mp, mid, c1, n_total, leaf, launches);
+}
+
 // One warp per prediction point: mean = sum_i At[m,i] v[i], var = kss - sum_i At[m,i]^2 (+ noise diag).
 __global__ void __launch_bounds__(256)
 posterior_reduce_kernel(KParams kp, const double* __restrict__ Btab, const double* __restrict__ Fs,

@@ -40,6 +40,7 @@ class GPEngine:
         self._keep = None
         self.N = 0
         self.D_in = 0
+        self.rank, self.world = 0, 1
 
     # -- lifetime ------------------------------------------------------------------------------------
     def close(self):
@@ -87,6 +88,29 @@ class GPEngine:
 
     def set_option(self, name: str, value: int):
         self._check(self._lib.gb2_set_option(self._h, name.encode(), int(value)), "set_option")
+
+    # -- multi-GPU ------------------------------------------------------------------------------------
+    def nccl_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = self._lib.gb2_nccl_unique_id(buf)
+        if rc != 0:
+            raise RuntimeError(f"gb2_nccl_unique_id failed ({rc}): {self._lib.gb2_last_error(None).decode()}")
+        return buf.raw
+
+    def dist_init(self, rank: int, world: int, unique_id: bytes):
+        """Collective over all ranks: afterwards ``factorize`` shards K by 128-row blocks across the ranks' GPUs."""
+        if world > 1 and len(unique_id) != 128:
+            raise ValueError("unique_id must be the 128 bytes of an ncclUniqueId")
+        self._check(self._lib.gb2_dist_init(self._h, int(rank), int(world), unique_id), "dist_init")
+        self.rank, self.world = int(rank), int(world)
+
+    def allgather_device(self, dsend_ptr: int, drecv_ptr: int, count: int):
+        """Rank-major gather of ``count`` float64 per rank on the handle's stream (device pointers)."""
+        self._check(self._lib.gb2_dist_allgather_dev(self._h, C.c_void_p(dsend_ptr), C.c_void_p(drecv_ptr), int(count)), "allgather")
+
+    def dist_finalize(self):
+        self._check(self._lib.gb2_dist_finalize(self._h), "dist_finalize")
+        self.rank, self.world = 0, 1
 
     # -- compute --------------------------------------------------------------------------------------
     def factorize(self):

@@ -141,6 +141,19 @@ int gb2_get_timings(gb2_handle* h, double* out);
 int gb2_mark(gb2_handle* h, int slot);
 int gb2_elapsed_ms(gb2_handle* h, int a, int b, double* ms);
 
+/* Multi-GPU factorisation (north_star: "shard K by row-blocks across the 8xB200 box ... NCCL-over-NVLink ... panel broadcast
+ * of the block Cholesky").  Nothing in the reference corresponds to this (it is single-process).  One process per GPU; each
+ * process creates its own handle, rank 0 obtains an id with gb2_nccl_unique_id and ships the 128 bytes to the other ranks by
+ * any means (the Python host side uses torch.distributed), then every rank calls gb2_dist_init.  Afterwards gb2_factorize is
+ * collective: 128-row blocks of K are owned block-cyclically, each rank builds and updates its own rows, the diagonal block
+ * is broadcast and the panel all-gathered every block step, and on return every rank holds the complete factor, so
+ * gb2_predict* stays a local call (ranks predict disjoint slices of the grid).  NCCL is bound with dlopen at the first call. */
+int gb2_nccl_unique_id(char* out128);
+int gb2_dist_init(gb2_handle* h, int rank, int world, const char* unique_id128);
+int gb2_dist_finalize(gb2_handle* h);
+/* Gather `count` doubles from every rank (rank-major) on the handle's stream: the per-rank slices of the posterior.  */
+int gb2_dist_allgather_dev(gb2_handle* h, const double* dsend, double* drecv, int64_t count);
+
 /* Tunables (for benchmarking/ablation): name in {"lookahead","graph"}; returns <0 if unknown.   */
 int gb2_set_option(gb2_handle* h, const char* name, int value);
 

@@ -1,0 +1,79 @@
+"""Multi-GPU check (run under torchrun, one rank per GPU): row-block-sharded Cholesky over NCCL vs the single-GPU factor,
+sliced prediction + gather vs the oracle, and factorisation timings.  Used by tests/test_dist_gpu.py and by hand:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gumbi_b200 import GPEngine  # noqa: E402
+from gumbi_b200 import dist as gdist  # noqa: E402
+from gumbi_b200.synthetic import synthetic_problem  # noqa: E402
+
+
+def main():
+    rank, local_rank, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sizes = [int(a) for a in sys.argv[1:]] or [1000, 3000, 8192]
+    with_oracle = os.environ.get("GB2_DIST_ORACLE", "1") == "1"
+    eng = GPEngine(local_rank)
+    r, w = gdist.init_engine(eng)
+    assert (r, w) == (rank, world)
+    ref = GPEngine(local_rank)  # same GPU, not sharded
+    ok = True
+    out = []
+    for n in sizes:
+        P = 2 if n == 3000 else 1
+        spec, X, y, Xs = synthetic_problem(n // P, 4, P=P, M_res=20, kind="Matern52" if n == 3000 else "ExpQuad")
+        eng.set_train(X, y); eng.set_kernel(spec)
+        ref.set_train(X, y); ref.set_kernel(spec)
+        for _ in range(2):
+            dist.barrier(); torch.cuda.synchronize()
+            t0 = time.perf_counter(); eng.factorize(); torch.cuda.synchronize(); t_shard = time.perf_counter() - t0
+        tm = eng.timings()
+        for _ in range(2):
+            t0 = time.perf_counter(); ref.factorize(); t_one = time.perf_counter() - t0
+        tm1 = ref.timings()
+        rec = {"N": len(y), "world": world, "rank": rank, "chol_ms_sharded": tm["cholesky_ms"], "chol_ms_single": tm1["cholesky_ms"],
+               "wall_ms_sharded": t_shard * 1e3, "wall_ms_single": t_one * 1e3}
+        if len(y) <= 8192:
+            L, L1 = eng.get_L(), ref.get_L()
+            rec["L_bit_identical"] = bool(np.array_equal(L, L1))
+            rec["L_max_abs_diff"] = float(np.max(np.abs(L - L1)))
+            rec["v_max_abs_diff"] = float(np.max(np.abs(eng.get_v() - ref.get_v())))
+            rec["mll_diff"] = abs(eng.mll() - ref.mll())
+            ok &= rec["L_max_abs_diff"] < 1e-9 and rec["v_max_abs_diff"] < 1e-9
+        lo, hi = gdist.grid_slice(len(Xs), rank, world)
+        mu_l, var_l = eng.predict(Xs[lo:hi], True)
+        mu, var = gdist.gather_grid(mu_l, var_l, len(Xs))
+        mu1, var1 = ref.predict(Xs, True)
+        rec["pred_max_abs_diff"] = float(max(np.max(np.abs(mu - mu1)), np.max(np.abs(var - var1))))
+        ok &= rec["pred_max_abs_diff"] < 1e-8
+        if with_oracle and rank == 0 and len(y) <= 4096:
+            from oracle import gp_oracle as orc
+
+            mu0, var0 = orc.predict(spec, X, y, Xs, True)
+            rec["oracle_max_rel"] = float(max(np.max(np.abs(mu - mu0)) / np.abs(mu0).max(), np.max(np.abs(var - var0) / np.abs(var0))))
+            ok &= rec["oracle_max_rel"] < 1e-6
+        out.append(rec)
+        if rank == 0:
+            print(json.dumps(rec), flush=True)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("DIST_CHECK", "OK" if int(flag.item()) == 1 else "FAILED", flush=True)
+    eng.close(); ref.close()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
