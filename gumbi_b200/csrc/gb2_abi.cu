@@ -134,8 +134,12 @@ int predict_common(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_nois
         prep_features<<<(unsigned)((Mp + 255) / 256), 256, 0, s>>>(dXs_all + m0 * h->D_in, Mc, Mp, h->pp, h->dFs, h->dCs, h->dInfo + 1);
         GB2_CUDA(h, cudaEventRecord(h->ev[1], s));
         dim3 grid((unsigned)(Np / KB_T), (unsigned)(Mp / KB_T));
-        kbuild_kernel<false><<<grid, KB_THREADS, kbuild_smem_bytes(h->kp), s>>>(h->kp, h->dBtab, h->dFs, h->dCs, Mp, Mc, h->dF, h->dC, Np, N,
-                                                                                 nullptr, h->dAt, Np, 1, 0);
+        if (h->opt_kbuild_v1)
+            kbuild_kernel<false><<<grid, KB_THREADS, kbuild_smem_bytes(h->kp), s>>>(h->kp, h->dBtab, h->dFs, h->dCs, Mp, Mc, h->dF, h->dC, Np, N,
+                                                                                     nullptr, h->dAt, Np, 1, 0);
+        else
+            kbuild_dmma_kernel<false><<<grid, KB_THREADS, kbuild_dmma_smem_bytes(h->kp), s>>>(h->kp, h->dBtab, h->dFs, h->dCs, Mp, Mc, h->dF, h->dC,
+                                                                                               Np, N, nullptr, h->dAt, Np, 1, 0);
         GB2_CUDA(h, cudaEventRecord(h->ev[2], s));
         launches += 2;
         if (tf32) trsm_rec_tf32(h, s, Mp, 0, ncols, ncols, h->opt_tf32_nb, launches);
@@ -211,6 +215,13 @@ int gb2_create(gb2_handle** out, int device, int precision) {
     h->n_sm = prop.multiProcessorCount;
     if ((e = cudaFuncSetAttribute(kbuild_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
     if ((e = cudaFuncSetAttribute(kbuild_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
+    if ((e = cudaFuncSetAttribute(kbuild_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
+    if ((e = cudaFuncSetAttribute(kbuild_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
+    {
+        double tab[64];
+        for (int j = 0; j < 64; j++) tab[j] = std::exp2((double)j / 64.0);
+        if ((e = cudaMemcpyToSymbol(g_exp2_tab, tab, sizeof(tab))) != cudaSuccess) return fail(e, "cudaMemcpyToSymbol");
+    }
     if ((e = cudaFuncSetAttribute(mll_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 164 * 1024)) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
     if ((e = dgemm_nt_configure<128, 64, GM_SET>()) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
     *out = h;
@@ -309,7 +320,7 @@ int gb2_set_kernel(gb2_handle* h, const gb2_kernel* k) {
     for (double b : btab) GB2_ARG(h, std::isfinite(b), "Coregion table holds a non-finite value");
     kp.n_feat = n_feat; kp.n_cat = n_cat;
     pp.n_cat = n_cat;
-    GB2_ARG(h, kbuild_smem_bytes(kp) <= 160 * 1024, "too many features per point for the K-build tile");
+    GB2_ARG(h, kbuild_smem_bytes(kp) <= 160 * 1024 && kbuild_dmma_smem_bytes(kp) <= 160 * 1024, "too many features per point for the K-build tile");
     GB2_CUDA(h, cudaSetDevice(h->device));
     if (btab.empty()) btab.push_back(1.0);
     if ((int)btab.size() > h->btab_len) {
@@ -378,8 +389,12 @@ static int build_K(gb2_handle* h, int& launches) {
     prep_features<<<(unsigned)((Np + 255) / 256), 256, 0, s>>>(h->dX, N, Np, h->pp, h->dF, h->dC, h->dInfo + 1);
     GB2_CUDA(h, cudaEventRecord(h->ev[1], s));
     dim3 grid((unsigned)(Np / KB_T), (unsigned)(Np / KB_T));
-    kbuild_kernel<true><<<grid, KB_THREADS, kbuild_smem_bytes(h->kp), s>>>(h->kp, h->dBtab, h->dF, h->dC, Np, N, h->dF, h->dC, Np, N, h->dy,
-                                                                            h->dA, Np, h->world, h->rank);
+    if (h->opt_kbuild_v1)
+        kbuild_kernel<true><<<grid, KB_THREADS, kbuild_smem_bytes(h->kp), s>>>(h->kp, h->dBtab, h->dF, h->dC, Np, N, h->dF, h->dC, Np, N, h->dy,
+                                                                                h->dA, Np, h->world, h->rank);
+    else
+        kbuild_dmma_kernel<true><<<grid, KB_THREADS, kbuild_dmma_smem_bytes(h->kp), s>>>(h->kp, h->dBtab, h->dF, h->dC, Np, N, h->dF, h->dC, Np, N,
+                                                                                          h->dy, h->dA, Np, h->world, h->rank);
     GB2_CUDA(h, cudaEventRecord(h->ev[2], s));
     launches += 2;
     return 0;
@@ -638,6 +653,7 @@ int gb2_dist_finalize(gb2_handle* h) {
 int gb2_set_option(gb2_handle* h, const char* name, int value) {
     if (!h || !name) return -1;
     if (!strcmp(name, "lookahead")) { h->opt_lookahead = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "kbuild_v1")) { h->opt_kbuild_v1 = value ? 1 : 0; h->factorized = false; return 0; }   // ablation: scalar-FMA + libm exp K-build
     if (!strcmp(name, "tf32_nb")) {   // panel width of the GB2_TF32 factorisation / leaf width of its solve, in 128-column blocks
         GB2_ARG(h, value >= 1 && value <= 16, "tf32_nb must be in [1, 16]");
         h->opt_tf32_nb = value; h->P_cap = 0; h->factorized = false;

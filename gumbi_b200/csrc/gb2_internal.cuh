@@ -114,6 +114,7 @@ struct gb2_handle {
 
     // options
     int opt_tf32_nb = 4;
+    int opt_kbuild_v1 = 0;
     int opt_lookahead = 1;
 
     // timing

@@ -212,6 +212,218 @@ kbuild_kernel(KParams kp, const double* __restrict__ Btab,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// K-build v2: the Gram part of the squared distance runs on the fp64 tensor pipe (DMMA m8n8k4) and the exponential is a
+// table-driven fp64 exp (64-entry 2^(j/64) table in shared memory + degree-5 polynomial, 10 fp64 instructions instead of
+// the ~25 of the library exp), so that the fp64 vector pipe -- which bounded v1 at 0.20 of the HBM roofline (ncu: fp64
+// pipe 27 % active, issue 37 %, DRAM 13 %) -- has roughly a third of the work per entry.
+//
+// Per term the tile edges are staged as augmented feature rows (K-dim ka = round_up(d + 2, 4)):
+//     row side   [ u_0 .. u_{d-1},  -|u|^2/2,  1,        0.. ]        u = x / ls
+//     col side   [ u_0 .. u_{d-1},  1,        -|u|^2/2,  0.. ]
+// so that one DMMA chain delivers  u_i.u_j - |u_i|^2/2 - |u_j|^2/2 = -r^2/2  (the expanded form PyMC uses, GP.py:410 ->
+// Stationary.square_dist) directly as the exponent of ExpQuad.
+// Tile 64 x 64, 8 warps; warp w owns rows (w>>1)*16..+16 and columns (w&1)*32..+32 = 2 x 4 DMMA blocks; a thread holds
+// (row g, columns 2t, 2t+1) of each block and stores it as one 16-byte row-contiguous piece.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int KB2_TS = 68;   // shared row stride (doubles): 68 = 4 mod 16 makes the 8x4 / 4x8 DMMA fragment loads conflict-free
+
+__device__ double g_exp2_tab[64];   // 2^(j/64), filled by the host at gb2_create
+
+// exp(x) for x <= ~0 (clamped at -708, where exp is 3e-308).  |relative error| ~ 2e-16.
+__device__ __forceinline__ double exp_tab(double x, const double* __restrict__ tab) {
+    x = fmax(x, -708.0);
+    const double t = fma(x, 92.33248261689366, 6755399441055744.0);   // 64/ln2, 1.5*2^52: low word of t = round(64 x / ln 2)
+    const int n = __double2loint(t);
+    const double kf = t - 6755399441055744.0;
+    double r = fma(kf, -0.01083042469326756, x);                       // ln2/64 split hi (32-bit mantissa) + lo
+    r = fma(kf, -2.9815858269852933e-12, r);
+    const double r2 = r * r;
+    double q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    q = fma(q, r, 1.0 / 6.0);
+    q = fma(q, r, 0.5);
+    const double p = fma(q, r2, r);                                     // e^r - 1, |r| <= ln2/128
+    const double T = tab[n & 63];
+    const double res = fma(T, p, T);
+    return __hiloint2double(__double2hiint(res) + ((n >> 6) << 20), __double2loint(res));
+}
+
+// value of the stationary kernel from x = -r^2/2
+__device__ __forceinline__ double stationary_x(int kind, double x, const double* __restrict__ tab) {
+    if (kind == GB2_EXPQUAD) return exp_tab(fmin(x, 0.0), tab);
+    const double r = sqrt(fmax(-2.0 * x, 0.0) + 1e-12);
+    switch (kind) {
+        case GB2_MATERN52: {
+            const double s5 = 2.23606797749978969641;
+            return (1.0 + s5 * r + (5.0 / 3.0) * (r * r)) * exp_tab(-s5 * r, tab);
+        }
+        case GB2_MATERN32: {
+            const double s3 = 1.73205080756887729353;
+            return (1.0 + s3 * r) * exp_tab(-s3 * r, tab);
+        }
+        case GB2_MATERN12: return exp_tab(-r, tab);
+        default: return exp_tab(-0.5 * r, tab);  // GB2_EXPONENTIAL
+    }
+}
+
+__device__ __forceinline__ void kb_dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__host__ __device__ inline int kb2_ka(int d) { return (d + 2 + 3) / 4 * 4; }
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(KB_THREADS)
+kbuild_dmma_kernel(KParams kp, const double* __restrict__ Btab,
+                   const double* __restrict__ Fi, const int* __restrict__ Ci, int64_t stride_i, int64_t n_i,
+                   const double* __restrict__ Fj, const int* __restrict__ Cj, int64_t stride_j, int64_t n_j,
+                   const double* __restrict__ y, double* __restrict__ out, int64_t ld, int own_stride, int own_rank) {
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (TRAIN && bj > bi) return;
+    if (TRAIN && own_stride > 1 && ((bi * KB_T) / TILE) % own_stride != own_rank) return;
+    extern __shared__ __align__(16) unsigned char kb_smem[];
+    // total augmented / linear rows over the terms
+    int ka_tot = 0, nl_tot = 0;
+    for (int t = 0; t < kp.n_terms; t++) { ka_tot += kb2_ka(kp.t[t].d); nl_tot += kp.t[t].n_lin; }
+    const int nc = kp.n_cat;
+    double* sA = reinterpret_cast<double*>(kb_smem);          // [ka_tot][TS] row side
+    double* sB = sA + ka_tot * KB2_TS;                         // [ka_tot][TS] column side
+    double* sLi = sB + ka_tot * KB2_TS;                        // [nl_tot][TS]
+    double* sLj = sLi + nl_tot * KB2_TS;                       // [nl_tot][TS]
+    double* sTab = sLj + nl_tot * KB2_TS;                      // [64]
+    int* sCi = reinterpret_cast<int*>(sTab + 64);              // [nc][64]
+    int* sCj = sCi + (nc > 0 ? nc : 1) * KB_T;
+    const int64_t i0 = (int64_t)bi * KB_T, j0 = (int64_t)bj * KB_T;
+    if (threadIdx.x < 64) sTab[threadIdx.x] = g_exp2_tab[threadIdx.x];
+    {
+        int aoff = 0, loff = 0;
+        for (int t = 0; t < kp.n_terms; t++) {
+            const TermDev& T = kp.t[t];
+            const int d = T.d, ka = kb2_ka(d);
+            for (int e = threadIdx.x; e < ka * KB_T; e += KB_THREADS) {
+                const int k = e / KB_T, p = e % KB_T;
+                double a, b;
+                if (k < d) {
+                    a = Fi[(int64_t)(T.feat_off + k) * stride_i + i0 + p];
+                    b = Fj[(int64_t)(T.feat_off + k) * stride_j + j0 + p];
+                } else if (k == d) {
+                    a = -0.5 * Fi[(int64_t)(T.feat_off + d) * stride_i + i0 + p];
+                    b = 1.0;
+                } else if (k == d + 1) {
+                    a = 1.0;
+                    b = -0.5 * Fj[(int64_t)(T.feat_off + d) * stride_j + j0 + p];
+                } else {
+                    a = b = 0.0;
+                }
+                sA[(aoff + k) * KB2_TS + p] = a;
+                sB[(aoff + k) * KB2_TS + p] = b;
+            }
+            for (int e = threadIdx.x; e < T.n_lin * KB_T; e += KB_THREADS) {
+                const int l = e / KB_T, p = e % KB_T;
+                sLi[(loff + l) * KB2_TS + p] = Fi[(int64_t)(T.feat_off + d + 1 + l) * stride_i + i0 + p];
+                sLj[(loff + l) * KB2_TS + p] = Fj[(int64_t)(T.feat_off + d + 1 + l) * stride_j + j0 + p];
+            }
+            aoff += ka; loff += T.n_lin;
+        }
+    }
+    for (int e = threadIdx.x; e < nc * KB_T; e += KB_THREADS) {
+        const int r = e / KB_T, p = e % KB_T;
+        sCi[e] = Ci[(int64_t)r * stride_i + i0 + p];
+        sCj[e] = Cj[(int64_t)r * stride_j + j0 + p];
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int r0 = (warp >> 1) * 16, c0 = (warp & 1) * 32;
+    double val[2][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) val[mi][ni][0] = val[mi][ni][1] = 0.0;
+
+    int aoff = 0, loff = 0;
+    for (int t = 0; t < kp.n_terms; t++) {
+        const TermDev& T = kp.t[t];
+        const int ka = kb2_ka(T.d);
+        double acc[2][4][2];
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        for (int kk = 0; kk < ka; kk += 4) {
+            const double* pa = sA + (aoff + kk + t4) * KB2_TS + r0 + g;
+            const double* pb = sB + (aoff + kk + t4) * KB2_TS + c0 + g;
+            const double a0 = pa[0], a1 = pa[8];
+            const double b0 = pb[0], b1 = pb[8], b2 = pb[16], b3 = pb[24];
+            kb_dmma(acc[0][0][0], acc[0][0][1], a0, b0); kb_dmma(acc[0][1][0], acc[0][1][1], a0, b1);
+            kb_dmma(acc[0][2][0], acc[0][2][1], a0, b2); kb_dmma(acc[0][3][0], acc[0][3][1], a0, b3);
+            kb_dmma(acc[1][0][0], acc[1][0][1], a1, b0); kb_dmma(acc[1][1][0], acc[1][1][1], a1, b1);
+            kb_dmma(acc[1][2][0], acc[1][2][1], a1, b2); kb_dmma(acc[1][3][0], acc[1][3][1], a1, b3);
+        }
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int pr = r0 + mi * 8 + g, pc = c0 + ni * 8 + 2 * t4 + e;
+                    double v = T.eta2 * stationary_x(T.kind, acc[mi][ni][e], sTab);
+                    if (T.n_lin > 0) {
+                        double lin = 0.0;
+                        for (int l = 0; l < T.n_lin; l++) lin = fma(sLi[(loff + l) * KB2_TS + pr], sLj[(loff + l) * KB2_TS + pc], lin);
+                        v = fma(T.tau, lin, v);
+                    }
+                    for (int f = 0; f < T.n_coreg; f++)
+                        v *= __ldg(Btab + T.cg_Boff[f] + sCi[T.cg_cat[f] * KB_T + pr] * T.cg_P[f] + sCj[T.cg_cat[f] * KB_T + pc]);
+                    val[mi][ni][e] += v;
+                }
+        aoff += ka; loff += T.n_lin;
+    }
+
+#pragma unroll
+    for (int mi = 0; mi < 2; mi++) {
+        const int pr = r0 + mi * 8 + g;
+        const int64_t gi = i0 + pr;
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+            double o[2];
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int64_t gj = j0 + c0 + ni * 8 + 2 * t4 + e;
+                double v = val[mi][ni][e];
+                if (TRAIN) {
+                    if (gi < n_i && gj < n_j) {
+                        if (gi == gj) {
+                            double nz = kp.sigma2;
+                            if (kp.noise_cat >= 0) {
+                                const int c = sCi[kp.noise_cat * KB_T + pr];
+                                nz *= __ldg(Btab + kp.noise_Boff + c * kp.noise_P + c);
+                            }
+                            v += nz + kp.jitter;
+                        }
+                    } else if (gi == n_i && gj < n_j) {
+                        v = y[gj];
+                    } else {
+                        v = (gi == gj) ? 1.0 : 0.0;
+                    }
+                } else {
+                    if (gi >= n_i || gj >= n_j) v = 0.0;
+                }
+                o[e] = v;
+            }
+            *reinterpret_cast<double2*>(out + gi * ld + j0 + c0 + ni * 8 + 2 * t4) = make_double2(o[0], o[1]);
+        }
+    }
+}
+
+inline size_t kbuild_dmma_smem_bytes(const KParams& kp) {
+    int ka_tot = 0, nl_tot = 0;
+    for (int t = 0; t < kp.n_terms; t++) { ka_tot += kb2_ka(kp.t[t].d); nl_tot += kp.t[t].n_lin; }
+    return (size_t)(2 * ka_tot + 2 * nl_tot) * KB2_TS * sizeof(double) + 64 * sizeof(double) +
+           (size_t)2 * (kp.n_cat > 0 ? kp.n_cat : 1) * KB_T * sizeof(int);
+}
+
 inline size_t kbuild_smem_bytes(const KParams& kp) {
     return (size_t)2 * kp.n_feat * KB_T * sizeof(double) + (size_t)2 * (kp.n_cat > 0 ? kp.n_cat : 1) * KB_T * sizeof(int);
 }
