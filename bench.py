@@ -246,6 +246,8 @@ def run_ours(args):
     # diagonal block + all-gather of the panel every block step), every rank then holds the factor and serves a contiguous
     # 1/N slice of the grid; the slices are all-gathered on the handle's stream inside the timed region.
     eng = GPEngine(local_rank, precision)
+    for kv in args.opt:
+        eng.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     if use_dist:
         gdist.init_engine(eng)
     lo, hi = gdist.grid_slice(M, rank, world)
@@ -429,6 +431,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="fp64", choices=["fp64", "tf32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--opt", action="append", default=[], help="engine tunable name=value (e.g. tf32_nb=8, kbuild_v1=1); ablations only")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -28,7 +28,9 @@ constexpr int TILE_BYTES = TM * TK * 4;          // 16 KB per operand tile
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // A_hi, A_lo, B_hi, B_lo
 constexpr int THREADS = 192;
 constexpr int TMEM_COLS = 256;                   // two 128-column fp32 accumulators
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int EPI_LD = 33;                       // padded row of the per-warp 32 x 32 fp32 transpose buffer (conflict-free both ways)
+constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;   // one buffer per epilogue warp
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + EPI_BYTES;
 constexpr int TC_MAX_K = 1024;                   // fp32 accumulation depth per launch
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -138,6 +140,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
     uint64_t* tfull = bars + 2 * STAGES;    // [2]       accumulator complete
     uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]    accumulator drained by the epilogue
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    float* epi = reinterpret_cast<float*>(base + STAGES * STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = ((g.n_bi + RASTER_GROUP - 1) / RASTER_GROUP) * RASTER_GROUP * g.n_bj;   // raster slots (some are skipped)
@@ -220,20 +223,25 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
             it++;
             mbar_wait(tfull + buf, tphase);
             tc_fence_after();
-            const int row = q * 32 + lane;
-            double* crow = g.C + ((int64_t)(g.rb_first + bi * g.rb_stride) * TM + row) * g.ldc + (int64_t)(g.cblk0 + bj) * TN;
+            // TMEM hands every thread one ROW (32 consecutive columns); the fp64 read-modify-write of C wants one row spread
+            // over the warp (lane = column, 256 contiguous bytes per request).  Transpose through a padded 32 x 32 buffer.
+            float* S = epi + (warp - 2) * 32 * EPI_LD;
+            double* cbase = g.C + ((int64_t)(g.rb_first + bi * g.rb_stride) * TM + q * 32) * g.ldc + (int64_t)(g.cblk0 + bj) * TN + lane;
 #pragma unroll 1
             for (int c0 = 0; c0 < TN; c0 += 32) {
+                // 32 independent 256-byte row requests per warp in flight (32 KB per SM) before anything is consumed
+                double* cp = cbase + c0;
+                double o[32];
+#pragma unroll
+                for (int u = 0; u < 32; u++) o[u] = cp[(int64_t)u * g.ldc];
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TN + c0), v);
 #pragma unroll
-                for (int c = 0; c < 32; c += 2) {
-                    double2* p = reinterpret_cast<double2*>(crow + c0 + c);
-                    double2 o = *p;
-                    o.x -= (double)v[c];
-                    o.y -= (double)v[c + 1];
-                    *p = o;
-                }
+                for (int c = 0; c < 32; c++) S[lane * EPI_LD + c] = v[c];
+                __syncwarp();
+#pragma unroll
+                for (int u = 0; u < 32; u++) cp[(int64_t)u * g.ldc] = o[u] - (double)S[u * EPI_LD + lane];
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();

@@ -6,8 +6,9 @@ from gumbi_b200.synthetic import synthetic_problem
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 kind = sys.argv[3] if len(sys.argv) > 3 else "ExpQuad"
+prec = sys.argv[4] if len(sys.argv) > 4 else "fp64"
 spec, X, y, Xs = synthetic_problem(n, 8, M_res=100, kind=kind)
-eng = GPEngine(0)
+eng = GPEngine(0, prec)
 eng.set_train(X, y); eng.set_kernel(spec)
 for _ in range(reps):
     eng.factorize()
