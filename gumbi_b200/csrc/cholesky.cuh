@@ -104,7 +104,8 @@ __device__ __forceinline__ void pd_unit(double* C, const double* A, const double
 
 __global__ void __launch_bounds__(PD_THREADS, 1)
 potrf_diag_kernel(double* __restrict__ A, int64_t ld, int64_t g0, int64_t n_real, double* __restrict__ Dinv,
-                  int* __restrict__ info, double* __restrict__ Lpack = nullptr, long long* __restrict__ clk = nullptr) {
+                  int* __restrict__ info, double* __restrict__ Lpack = nullptr, PushArgs sig = PushArgs{},
+                  long long* __restrict__ clk = nullptr) {
     extern __shared__ __align__(16) unsigned char pd_smem[];
     int clk_i = 0;
 #define PD_CLK() do { if (clk && threadIdx.x == 0) clk[clk_i++] = clock64(); } while (0)
@@ -301,6 +302,44 @@ potrf_diag_kernel(double* __restrict__ A, int64_t ld, int64_t g0, int64_t n_real
     }
     PD_CLK();
 #undef PD_CLK
+    if (sig.n_peers > 0) {
+        // multi-GPU, peer-memory exchange: L_kk / inv(L_kk) are complete in this GPU's memory; tell every peer (they pull)
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0)
+            for (int pr = 0; pr < sig.n_peers; pr++) atomicAdd_system(sig.peerFlag[pr], 1u);
+    }
+}
+
+// Spin (bounded) until a counter in local memory, bumped by peer GPUs over NVLink, reaches `expected`.
+__device__ __forceinline__ void wait_counter(const unsigned* flag, unsigned expected) {
+    const volatile unsigned* f = flag;
+    const long long t0 = clock64();
+    while (*f < expected) {
+        if (clock64() - t0 > (1LL << 33)) __trap();   // ~4 s: a protocol bug must end as an error, not as a hung GPU
+    }
+    __threadfence_system();
+}
+__global__ void wait_counter_kernel(const unsigned* flag, unsigned expected) {
+    if (threadIdx.x == 0) wait_counter(flag, expected);
+}
+
+// Non-owners of block step k: wait for the owner's announcement, then pull inv(L_kk) and L_kk (2 x 128 KB) from the owner's
+// memory through the peer mapping into the local copies, and L_kk into the local factor.  grid = 32 CTAs x 256 threads.
+__global__ void __launch_bounds__(256)
+pull_diag_kernel(const unsigned* flag, unsigned expected, const double* __restrict__ ownerDinv, const double* __restrict__ ownerLpack,
+                 double* __restrict__ Dinv, double* __restrict__ Lpack, double* __restrict__ Adiag, int64_t ld) {
+    if (threadIdx.x == 0) wait_counter(flag, expected);
+    __syncthreads();
+    const int per = TILE * TILE / 2 / gridDim.x;   // double2 elements per CTA
+    for (int e = blockIdx.x * per + threadIdx.x; e < (blockIdx.x + 1) * per; e += 256) {
+        const double2 d = reinterpret_cast<const double2*>(ownerDinv)[e];
+        const double2 l = reinterpret_cast<const double2*>(ownerLpack)[e];
+        reinterpret_cast<double2*>(Dinv)[e] = d;
+        reinterpret_cast<double2*>(Lpack)[e] = l;
+        const int r = (e * 2) / TILE, c = (e * 2) % TILE;
+        *reinterpret_cast<double2*>(Adiag + (int64_t)r * ld + c) = l;
+    }
 }
 
 // sum_{i<n} log A[i][i]  and  sum_{i<n} A[n][i]^2  (log-determinant half and |v|^2) -> scal[0], scal[1]
@@ -335,6 +374,7 @@ inline cudaError_t cholesky_configure() {
     if ((e = cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD_SMEM)) != cudaSuccess) return e;
     if ((e = dgemm_nt_configure<128, 64, GM_SUB>()) != cudaSuccess) return e;
     if ((e = dgemm_nt_configure<64, 128, GM_SET>()) != cudaSuccess) return e;
+    if ((e = dgemm_nt_configure<64, 128, GM_SET_PUSH>()) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -411,11 +451,24 @@ inline int factor_steps(gb2_handle* h, int k0, int k1, int col_limit) {
         const int owner = k % G;
         double* Dk = h->dDinv + (int64_t)k * TILE * TILE;
         double* Lk = G > 1 ? h->dLpack + (int64_t)k * TILE * TILE : nullptr;
+        const bool p2p = G > 1 && h->p2p_ready;
+        // counters of this block step in the current parity buffer: [0] = diagonal block announced, [1] = panel tiles landed
+        const size_t fl = ((size_t)h->p2p_parity * 2) * h->p2p_nbmax + k;
         if (owner == me) {
-            potrf_diag_kernel<<<1, PD_THREADS, PD_SMEM, sp>>>(A, ld, g0, h->N, Dk, h->dInfo, Lk);
+            PushArgs sig{};
+            if (p2p) {
+                for (int r = 0, q = 0; r < G; r++)
+                    if (r != me) sig.peerFlag[q++] = h->peerFlags[r] + fl;
+                sig.n_peers = G - 1;
+            }
+            potrf_diag_kernel<<<1, PD_THREADS, PD_SMEM, sp>>>(A, ld, g0, h->N, Dk, h->dInfo, Lk, sig);
+            launches++;
+        } else if (p2p) {
+            pull_diag_kernel<<<32, 256, 0, sp>>>(h->dFlags + fl, 1u, h->peerDinv[owner] + (int64_t)k * TILE * TILE,
+                                                 h->peerLpack[owner] + (int64_t)k * TILE * TILE, Dk, Lk, A + g0 * ld + g0, ld);
             launches++;
         }
-        if (G > 1) {
+        if (G > 1 && !p2p) {
             nc->GroupStart();
             nc->Broadcast(Dk, Dk, (size_t)TILE * TILE, NCCL_FLOAT64, owner, h->comm, sp);
             nc->Broadcast(Lk, Lk, (size_t)TILE * TILE, NCCL_FLOAT64, owner, h->comm, sp);
@@ -428,11 +481,27 @@ inline int factor_steps(gb2_handle* h, int k0, int k1, int col_limit) {
         if (below > 0) {
             const int f1 = first_owned_after(k, me), c1 = count_from(f1);         // owned blocks > k
             double* colk = A + g0;                                                   // column block k, row 0
-            if (c1 > 0) {
+            if (p2p) {
+                // panel solve fused with its exchange: tiles are stored locally and into every peer's factor over NVLink
+                if (c1 > 0) {
+                    PushArgs push{};
+                    for (int r = 0, q = 0; r < G; r++)
+                        if (r != me) { push.peerC[q] = h->peerA[r] + g0; push.peerFlag[q] = h->peerFlags[r] + fl + h->p2p_nbmax; q++; }
+                    push.n_peers = G - 1;
+                    dgemm_nt_launch<64, 128, GM_SET_PUSH>(sp, colk, ld, Dk, TILE, colk, ld, (int64_t)c1 * TILE, TILE, TILE, 0, 0, 0, f1, G, &push);
+                    launches++;
+                }
+                // every other rank pushes (its owned blocks below k) x (128/64 row tiles) CTAs' worth of tiles into this GPU
+                const unsigned expected = (unsigned)(2 * ((nb - (k + 1)) - c1));
+                if (expected > 0) {
+                    wait_counter_kernel<<<1, 32, 0, sp>>>(h->dFlags + fl + h->p2p_nbmax, expected);
+                    launches++;
+                }
+            } else if (c1 > 0) {
                 dgemm_nt_launch<64, 128, GM_SET>(sp, colk, ld, Dk, TILE, colk, ld, (int64_t)c1 * TILE, TILE, TILE, 0, 0, 0, f1, G);
                 launches++;
             }
-            if (G > 1) {
+            if (G > 1 && !p2p) {
                 const int cmax = count_from(k + 1);                                  // most blocks any rank owns below k
                 if (c1 > 0) {
                     panel_pack_kernel<<<dim3(c1, TILE / 8), 256, 0, sp>>>(A, ld, g0, h->dSend, 0, G, me, nb, k, cmax, me);
@@ -490,7 +559,7 @@ inline int factor_steps(gb2_handle* h, int k0, int k1, int col_limit) {
 // When the loop ends every rank holds the complete factor (each panel was gathered everywhere), so predict() runs locally
 // on whatever slice of the prediction grid the rank is given.
 //
-// GB2_TF32 (single GPU): block columns are grouped in panels of h->opt_tf32_nb blocks (default 4 = 512 columns).  A panel is
+// GB2_TF32: block columns are grouped in panels of h->opt_tf32_nb blocks (default 4 = 512 columns).  A panel is
 // factored in fp64 by factor_steps (DMMA), split into tf32 hi/lo pairs, and the whole trailing matrix is updated by ONE
 // tcgen05 split-TF32 SYRK of depth 512 (tf32gemm.cuh) -- 8x fewer passes over the trailing matrix than the 128-wide steps.
 inline int cholesky_enqueue(gb2_handle* h) {
@@ -498,22 +567,27 @@ inline int cholesky_enqueue(gb2_handle* h) {
     const int nb = (int)(Np / TILE);
     int launches = 0;
     const int pw = h->opt_tf32_nb;
-    if (h->precision == GB2_TF32 && h->world == 1 && nb > pw) {
+    if (h->precision == GB2_TF32 && nb > pw) {
         cudaStream_t sm = h->s_main;
+        const int G = h->world, me = h->rank;
         for (int c0 = 0; c0 < nb; c0 += pw) {
             const int c1 = c0 + pw < nb ? c0 + pw : nb;
             launches += factor_steps(h, c0, c1, c1);
             if (c1 >= nb) break;
+            // every rank holds the whole factored panel (it was all-gathered block step by block step): split all of it ...
             const int64_t rows = Np - (int64_t)c1 * TILE, cols = (int64_t)(c1 - c0) * TILE;
             const int64_t pld = (int64_t)pw * TILE;
             tc::split_tf32_kernel<<<(unsigned)((rows * cols / 2 + 255) / 256), 256, 0, sm>>>(
                 h->dA + (int64_t)c1 * TILE * ld + (int64_t)c0 * TILE, ld, rows, cols, h->dPhi + (int64_t)c1 * TILE * pld,
                 h->dPlo + (int64_t)c1 * TILE * pld, pld);
             launches++;
+            // ... and update the row blocks this rank owns (all of them on one GPU)
+            const int f = c1 + (((me - c1) % G) + G) % G;   // first owned block >= c1
+            const int cnt = f < nb ? (nb - f + G - 1) / G : 0;
             tc::GemmArgs g{};
             g.C = h->dA; g.ldc = ld;
-            g.n_bi = nb - c1; g.n_bj = nb - c1;
-            g.rb_first = c1; g.rb_stride = 1; g.cblk0 = c1; g.lower = 1;
+            g.n_bi = cnt; g.n_bj = nb - c1;
+            g.rb_first = f; g.rb_stride = G; g.cblk0 = c1; g.lower = 1;
             g.a_k0 = 0; g.b_row0 = c1 * TILE; g.b_k0 = 0;
             tc::gemm_tf32x3_launch(sm, h->n_sm, h->mPhi, h->mPlo, h->mPhi, h->mPlo, g, (int)cols, launches);
         }

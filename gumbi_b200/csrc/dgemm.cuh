@@ -35,7 +35,17 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-enum { GM_SUB = 0, GM_SET = 1 };
+enum { GM_SUB = 0, GM_SET = 1, GM_SET_PUSH = 2 };
+
+// GM_SET_PUSH (multi-GPU panel solve fused with its exchange): every output tile is also stored, at the same offset, into the
+// factor buffers of the peer GPUs (NVLink peer mappings obtained with cudaIpcOpenMemHandle), and each CTA then bumps a
+// counter in every peer's memory so that the peer knows when the whole panel has landed (fence.sys + red.release.sys).
+constexpr int GB2_MAX_PEERS = 7;
+struct PushArgs {
+    double* peerC[GB2_MAX_PEERS];        // peer's C base (same layout/offset as the local C argument)
+    unsigned* peerFlag[GB2_MAX_PEERS];   // counter to bump in the peer's memory
+    int n_peers;
+};
 
 template <int BM, int BN>
 constexpr size_t dgemm_smem_bytes() { return (size_t)GM_STAGES * (BM + BN) * GM_LDS * sizeof(double); }
@@ -52,7 +62,7 @@ constexpr size_t dgemm_smem_bytes() { return (size_t)GM_STAGES * (BM + BN) * GM_
 template <int BM, int BN, int MODE>
 __global__ void __launch_bounds__(GM_THREADS, 2)
 dgemm_nt_kernel(const double* A, int64_t lda, const double* __restrict__ B, int64_t ldb, double* C, int64_t ldc,
-                int kdepth, int lower_only, int64_t row_off, int64_t col_off, int rb_first, int rb_stride) {
+                int kdepth, int lower_only, int64_t row_off, int64_t col_off, int rb_first, int rb_stride, PushArgs push) {
     static_assert((BM / 32) * (BN / 32) == GM_THREADS / 32, "8 warps of 32x32");
     static_assert(TILE % BM == 0, "row tiles must not straddle 128-row blocks");
     const int bi = blockIdx.x, bj = blockIdx.y;
@@ -137,6 +147,21 @@ dgemm_nt_kernel(const double* A, int64_t lda, const double* __restrict__ B, int6
                 *p = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
             }
         }
+    if (MODE == GM_SET_PUSH) {
+        const int64_t off = (grow + wm * 32 + g) * ldc + (int64_t)bj * BN + wn * 32 + 2 * t;
+        for (int pr = 0; pr < push.n_peers; pr++) {
+            double* Pg = push.peerC[pr] + off;
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++)
+                    *reinterpret_cast<double2*>(Pg + (int64_t)mi * 8 * ldc + ni * 8) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+        }
+        __threadfence_system();          // this thread's peer stores are performed system-wide ...
+        __syncthreads();                 // ... for every thread of the CTA, before the CTA announces its tile
+        if (tid == 0)
+            for (int pr = 0; pr < push.n_peers; pr++) atomicAdd_system(push.peerFlag[pr], 1u);
+    }
 }
 
 template <int BM, int BN, int MODE>
@@ -149,11 +174,13 @@ inline cudaError_t dgemm_nt_configure() {
 template <int BM, int BN, int MODE>
 inline void dgemm_nt_launch(cudaStream_t s, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                             int64_t ldc, int64_t rows, int64_t cols, int kdepth, int lower_only, int64_t row_off,
-                            int64_t col_off, int rb_first = 0, int rb_stride = 1) {
+                            int64_t col_off, int rb_first = 0, int rb_stride = 1, const PushArgs* push = nullptr) {
     if (rows <= 0 || cols <= 0 || kdepth <= 0) return;
     dim3 grid((unsigned)(rows / BM), (unsigned)(cols / BN));
+    PushArgs pa{};
+    if (push) pa = *push;
     dgemm_nt_kernel<BM, BN, MODE><<<grid, GM_THREADS, dgemm_smem_bytes<BM, BN>(), s>>>(A, lda, B, ldb, C, ldc, kdepth,
-                                                                                      lower_only, row_off, col_off, rb_first, rb_stride);
+                                                                                      lower_only, row_off, col_off, rb_first, rb_stride, pa);
 }
 
 }  // namespace gb2

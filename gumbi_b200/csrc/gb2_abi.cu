@@ -138,8 +138,8 @@ int predict_common(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_nois
             kbuild_kernel<false><<<grid, KB_THREADS, kbuild_smem_bytes(h->kp), s>>>(h->kp, h->dBtab, h->dFs, h->dCs, Mp, Mc, h->dF, h->dC, Np, N,
                                                                                      nullptr, h->dAt, Np, 1, 0);
         else
-            kbuild_dmma_kernel<false><<<grid, KB_THREADS, kbuild_dmma_smem_bytes(h->kp), s>>>(h->kp, h->dBtab, h->dFs, h->dCs, Mp, Mc, h->dF, h->dC,
-                                                                                               Np, N, nullptr, h->dAt, Np, 1, 0);
+            kbuild_dmma_launch<false>(s, grid, kbuild_dmma_smem_bytes(h->kp), h->kp, h->dBtab, h->dFs, h->dCs, Mp, Mc, h->dF, h->dC, Np, N, nullptr,
+                                      h->dAt, Np, 1, 0);
         GB2_CUDA(h, cudaEventRecord(h->ev[2], s));
         launches += 2;
         if (tf32) trsm_rec_tf32(h, s, Mp, 0, ncols, ncols, h->opt_tf32_nb, launches);
@@ -171,6 +171,8 @@ int predict_common(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_nois
 }  // namespace
 
 extern "C" {
+
+static void p2p_close(gb2_handle* h);
 
 int gb2_abi_version(void) { return GB2_ABI_VERSION; }
 
@@ -215,8 +217,8 @@ int gb2_create(gb2_handle** out, int device, int precision) {
     h->n_sm = prop.multiProcessorCount;
     if ((e = cudaFuncSetAttribute(kbuild_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
     if ((e = cudaFuncSetAttribute(kbuild_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
-    if ((e = cudaFuncSetAttribute(kbuild_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
-    if ((e = cudaFuncSetAttribute(kbuild_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
+    if ((e = kbuild_dmma_configure<true>()) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
+    if ((e = kbuild_dmma_configure<false>()) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
     {
         double tab[64];
         for (int j = 0; j < 64; j++) tab[j] = std::exp2((double)j / 64.0);
@@ -232,8 +234,9 @@ int gb2_destroy(gb2_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    p2p_close(h);
     if (h->comm && h->nccl) { h->nccl->CommDestroy(h->comm); h->comm = nullptr; }
-    cudaFree(h->dLpack); cudaFree(h->dSend); cudaFree(h->dRecv);
+    cudaFree(h->dLpack); cudaFree(h->dSend); cudaFree(h->dRecv); cudaFree(h->dFlags); cudaFree(h->dIpcXch);
     cudaFree(h->dX); cudaFree(h->dy); cudaFree(h->dBtab); cudaFree(h->dF); cudaFree(h->dC); cudaFree(h->dA);
     cudaFree(h->dDinv); cudaFree(h->dInfo); cudaFree(h->dScal); cudaFree(h->dXs); cudaFree(h->dFs); cudaFree(h->dCs);
     cudaFree(h->dAt); cudaFree(h->dMean); cudaFree(h->dVar);
@@ -338,6 +341,77 @@ int gb2_set_kernel(gb2_handle* h, const gb2_kernel* k) {
     return 0;
 }
 
+// ---- peer-memory exchange setup (multi-GPU): IPC handles of the factor / diagonal-block / counter buffers are all-gathered
+// once per (re)allocation and opened on every peer; afterwards the factorisation's data path is NVLink loads/stores only.
+static void p2p_close(gb2_handle* h) {
+    for (int r = 0; r < 8; r++) {
+        if (r == h->rank) continue;
+        if (h->peerA[r]) cudaIpcCloseMemHandle(h->peerA[r]);
+        if (h->peerDinv[r]) cudaIpcCloseMemHandle(h->peerDinv[r]);
+        if (h->peerLpack[r]) cudaIpcCloseMemHandle(h->peerLpack[r]);
+        if (h->peerFlags[r]) cudaIpcCloseMemHandle(h->peerFlags[r]);
+        h->peerA[r] = h->peerDinv[r] = h->peerLpack[r] = nullptr;
+        h->peerFlags[r] = nullptr;
+    }
+    h->p2p_ready = false;
+}
+
+// tiny collective used as a barrier / agreement: every rank contributes one int, returns the minimum
+static int dist_min_int(gb2_handle* h, int mine, int* out) {
+    int* d = reinterpret_cast<int*>(h->dIpcXch);
+    GB2_CUDA(h, cudaMemcpyAsync(d + 64, &mine, sizeof(int), cudaMemcpyHostToDevice, h->s_main));
+    const int rc = h->nccl->AllGather(d + 64, d, sizeof(int), 0 /*ncclInt8*/, h->comm, h->s_main);
+    if (rc != 0) { h->err = std::string("ncclAllGather: ") + h->nccl->GetErrorString(rc); return -200 - rc; }
+    int all[8];
+    GB2_CUDA(h, cudaMemcpyAsync(all, d, h->world * sizeof(int), cudaMemcpyDeviceToHost, h->s_main));
+    GB2_CUDA(h, cudaStreamSynchronize(h->s_main));
+    int m = all[0];
+    for (int r = 1; r < h->world; r++) m = std::min(m, all[r]);
+    *out = m;
+    return 0;
+}
+
+static int p2p_setup(gb2_handle* h) {
+    const int G = h->world, me = h->rank;
+    struct Pack { cudaIpcMemHandle_t a, dinv, lpack, flags; };
+    static_assert(sizeof(Pack) == 256, "four 64-byte IPC handles");
+    Pack mine{};
+    int ok = 1;
+    if (cudaIpcGetMemHandle(&mine.a, h->dA) != cudaSuccess || cudaIpcGetMemHandle(&mine.dinv, h->dDinv) != cudaSuccess ||
+        cudaIpcGetMemHandle(&mine.lpack, h->dLpack) != cudaSuccess || cudaIpcGetMemHandle(&mine.flags, h->dFlags) != cudaSuccess) {
+        ok = 0;
+        cudaGetLastError();
+    }
+    char* d = h->dIpcXch;   // [0, 8*256) gathered handles, [8*256, +256) mine
+    GB2_CUDA(h, cudaMemcpyAsync(d + 8 * 256, &mine, sizeof(Pack), cudaMemcpyHostToDevice, h->s_main));
+    int rc = h->nccl->AllGather(d + 8 * 256, d, sizeof(Pack), 0 /*ncclInt8*/, h->comm, h->s_main);
+    if (rc != 0) { h->err = std::string("ncclAllGather: ") + h->nccl->GetErrorString(rc); return -200 - rc; }
+    Pack all[8];
+    GB2_CUDA(h, cudaMemcpyAsync(all, d, (size_t)G * sizeof(Pack), cudaMemcpyDeviceToHost, h->s_main));
+    GB2_CUDA(h, cudaStreamSynchronize(h->s_main));
+    for (int r = 0; r < G && ok; r++) {
+        if (r == me) { h->peerA[r] = h->dA; h->peerDinv[r] = h->dDinv; h->peerLpack[r] = h->dLpack; h->peerFlags[r] = h->dFlags; continue; }
+        void *pa = nullptr, *pd = nullptr, *pl = nullptr, *pf = nullptr;
+        if (cudaIpcOpenMemHandle(&pa, all[r].a, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+            cudaIpcOpenMemHandle(&pd, all[r].dinv, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+            cudaIpcOpenMemHandle(&pl, all[r].lpack, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+            cudaIpcOpenMemHandle(&pf, all[r].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            ok = 0;
+            cudaGetLastError();
+        }
+        h->peerA[r] = (double*)pa; h->peerDinv[r] = (double*)pd; h->peerLpack[r] = (double*)pl; h->peerFlags[r] = (unsigned*)pf;
+    }
+    int all_ok = 0;
+    if ((rc = dist_min_int(h, ok, &all_ok))) return rc;
+    if (!all_ok) {   // some rank cannot map its peers (no P2P / IPC in this environment): everyone uses the NCCL exchange
+        p2p_close(h);
+        h->opt_p2p = 0;
+        return 0;
+    }
+    h->p2p_ready = true;
+    return 0;
+}
+
 static int build_K(gb2_handle* h, int& launches) {
     const int64_t Np = h->Np, N = h->N;
     cudaStream_t s = h->s_main;
@@ -346,6 +420,13 @@ static int build_K(gb2_handle* h, int& launches) {
     if ((rc = validate_against_train(h))) return rc;
     if ((rc = ensure(h, h->dF, h->F_cap, (int64_t)std::max(1, h->kp.n_feat) * Np))) return rc;
     if ((rc = ensure(h, h->dC, h->C_cap, (int64_t)std::max(1, h->kp.n_cat) * Np))) return rc;
+    if (h->world > 1 && !h->dIpcXch) GB2_CUDA(h, cudaMalloc(&h->dIpcXch, 16 * 256));
+    if (h->world > 1 && h->p2p_ready && (h->A_cap < Np || h->xch_cap < Np)) {
+        // buffers are about to be re-allocated: every rank first drops its mappings of the peers' old buffers
+        p2p_close(h);
+        int dummy;
+        if ((rc = dist_min_int(h, 1, &dummy))) return rc;
+    }
     if (h->A_cap < Np) {
         if (h->dA) GB2_CUDA(h, cudaFree(h->dA));
         if (h->dDinv) GB2_CUDA(h, cudaFree(h->dDinv));
@@ -382,7 +463,22 @@ static int build_K(gb2_handle* h, int& launches) {
         GB2_CUDA(h, cudaMalloc(&h->dSend, (size_t)per_rank * TILE * TILE * sizeof(double)));
         GB2_CUDA(h, cudaMalloc(&h->dRecv, (size_t)per_rank * h->world * TILE * TILE * sizeof(double)));
         GB2_CUDA(h, cudaMemsetAsync(h->dSend, 0, (size_t)per_rank * TILE * TILE * sizeof(double), s));
+        if (h->dFlags) GB2_CUDA(h, cudaFree(h->dFlags));
+        h->p2p_nbmax = nb;
+        GB2_CUDA(h, cudaMalloc(&h->dFlags, (size_t)4 * nb * sizeof(unsigned)));
+        GB2_CUDA(h, cudaMemsetAsync(h->dFlags, 0, (size_t)4 * nb * sizeof(unsigned), s));
+        h->p2p_parity = 0;
         h->xch_cap = Np;
+    }
+    if (h->world > 1 && h->opt_p2p && !h->p2p_ready) {
+        GB2_CUDA(h, cudaStreamSynchronize(s));
+        if ((rc = p2p_setup(h))) return rc;
+    }
+    if (h->world > 1 && h->p2p_ready) {
+        // counters: this factorisation uses parity p; the other parity (used by the previous one, fully consumed) is cleared for
+        // the next one now -- no peer can be that far ahead, every factorisation needs every rank's panels
+        h->p2p_parity ^= 1;
+        GB2_CUDA(h, cudaMemsetAsync(h->dFlags + (size_t)(h->p2p_parity ^ 1) * 2 * h->p2p_nbmax, 0, (size_t)2 * h->p2p_nbmax * sizeof(unsigned), s));
     }
     GB2_CUDA(h, cudaMemsetAsync(h->dInfo, 0, 4 * sizeof(int), s));
     GB2_CUDA(h, cudaEventRecord(h->ev[0], s));
@@ -393,8 +489,8 @@ static int build_K(gb2_handle* h, int& launches) {
         kbuild_kernel<true><<<grid, KB_THREADS, kbuild_smem_bytes(h->kp), s>>>(h->kp, h->dBtab, h->dF, h->dC, Np, N, h->dF, h->dC, Np, N, h->dy,
                                                                                 h->dA, Np, h->world, h->rank);
     else
-        kbuild_dmma_kernel<true><<<grid, KB_THREADS, kbuild_dmma_smem_bytes(h->kp), s>>>(h->kp, h->dBtab, h->dF, h->dC, Np, N, h->dF, h->dC, Np, N,
-                                                                                          h->dy, h->dA, Np, h->world, h->rank);
+        kbuild_dmma_launch<true>(s, grid, kbuild_dmma_smem_bytes(h->kp), h->kp, h->dBtab, h->dF, h->dC, Np, N, h->dF, h->dC, Np, N, h->dy, h->dA, Np,
+                                 h->world, h->rank);
     GB2_CUDA(h, cudaEventRecord(h->ev[2], s));
     launches += 2;
     return 0;
@@ -642,6 +738,7 @@ int gb2_dist_finalize(gb2_handle* h) {
     if (h->comm) {
         cudaSetDevice(h->device);
         cudaDeviceSynchronize();
+        p2p_close(h);
         h->nccl->CommDestroy(h->comm);
         h->comm = nullptr;
     }
@@ -653,6 +750,11 @@ int gb2_dist_finalize(gb2_handle* h) {
 int gb2_set_option(gb2_handle* h, const char* name, int value) {
     if (!h || !name) return -1;
     if (!strcmp(name, "lookahead")) { h->opt_lookahead = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "p2p")) {   // 1: panel exchange through NVLink peer mappings (default), 0: NCCL broadcast + all-gather
+        GB2_ARG(h, !h->p2p_ready || value, "p2p cannot be switched off once the peer mappings are in use");
+        h->opt_p2p = value ? 1 : 0;
+        return 0;
+    }
     if (!strcmp(name, "kbuild_v1")) { h->opt_kbuild_v1 = value ? 1 : 0; h->factorized = false; return 0; }   // ablation: scalar-FMA + libm exp K-build
     if (!strcmp(name, "tf32_nb")) {   // panel width of the GB2_TF32 factorisation / leaf width of its solve, in 128-column blocks
         GB2_ARG(h, value >= 1 && value <= 16, "tf32_nb must be in [1, 16]");

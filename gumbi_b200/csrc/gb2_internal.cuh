@@ -103,6 +103,14 @@ struct gb2_handle {
     void* comm = nullptr;       // ncclComm_t
     double* dLpack = nullptr;   // (Np/TILE, TILE, TILE) contiguous copies of the diagonal blocks of L (broadcast payload)
     double* dSend = nullptr; double* dRecv = nullptr; int64_t xch_cap = 0;   // panel allgather staging
+    // peer-memory exchange (NVLink): IPC mappings of the peers' factor / diagonal-block buffers and of their counters
+    int opt_p2p = 1;
+    bool p2p_ready = false;
+    double* peerA[8] = {}; double* peerDinv[8] = {}; double* peerLpack[8] = {}; unsigned* peerFlags[8] = {};
+    unsigned* dFlags = nullptr;      // [2 parities][2 kinds][p2p_nbmax] counters bumped by the peers
+    int64_t p2p_nbmax = 0;
+    int p2p_parity = 0;
+    char* dIpcXch = nullptr;
 
     // GB2_TF32: tf32 hi/lo splits + their TMA descriptors (tf32gemm.cuh)
     int n_sm = 148;

@@ -272,7 +272,9 @@ __device__ __forceinline__ void kb_dmma(double& c0, double& c1, double a, double
 
 __host__ __device__ inline int kb2_ka(int d) { return (d + 2 + 3) / 4 * 4; }
 
-template <bool TRAIN>
+// KIND >= 0 with SIMPLE: compile-time specialisation for the common model (one term, that stationary kernel, no Linear, no
+// Coregion) -- the per-entry code then has no kind switch and no term / factor loops.  KIND = -1: everything at run time.
+template <bool TRAIN, int KIND, bool SIMPLE>
 __global__ void __launch_bounds__(KB_THREADS)
 kbuild_dmma_kernel(KParams kp, const double* __restrict__ Btab,
                    const double* __restrict__ Fi, const int* __restrict__ Ci, int64_t stride_i, int64_t n_i,
@@ -343,9 +345,11 @@ kbuild_dmma_kernel(KParams kp, const double* __restrict__ Btab,
         for (int ni = 0; ni < 4; ni++) val[mi][ni][0] = val[mi][ni][1] = 0.0;
 
     int aoff = 0, loff = 0;
-    for (int t = 0; t < kp.n_terms; t++) {
+    const int n_terms = SIMPLE ? 1 : kp.n_terms;
+    for (int t = 0; t < n_terms; t++) {
         const TermDev& T = kp.t[t];
         const int ka = kb2_ka(T.d);
+        const int kind = KIND >= 0 ? KIND : T.kind;
         double acc[2][4][2];
 #pragma unroll
         for (int mi = 0; mi < 2; mi++)
@@ -367,8 +371,9 @@ kbuild_dmma_kernel(KParams kp, const double* __restrict__ Btab,
             for (int ni = 0; ni < 4; ni++)
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
+                    double v = T.eta2 * stationary_x(kind, acc[mi][ni][e], sTab);
+                    if (SIMPLE) { val[mi][ni][e] = v; continue; }
                     const int pr = r0 + mi * 8 + g, pc = c0 + ni * 8 + 2 * t4 + e;
-                    double v = T.eta2 * stationary_x(T.kind, acc[mi][ni][e], sTab);
                     if (T.n_lin > 0) {
                         double lin = 0.0;
                         for (int l = 0; l < T.n_lin; l++) lin = fma(sLi[(loff + l) * KB2_TS + pr], sLj[(loff + l) * KB2_TS + pc], lin);
@@ -381,6 +386,16 @@ kbuild_dmma_kernel(KParams kp, const double* __restrict__ Btab,
         aoff += ka; loff += T.n_lin;
     }
 
+    // interior tiles (no diagonal, no augmented row, no padding): plain stores
+    if ((!TRAIN || bi != bj) && i0 + KB_T <= n_i && j0 + KB_T <= n_j) {
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++) {
+            double* dst = out + (i0 + r0 + mi * 8 + g) * ld + j0 + c0 + 2 * t4;
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) *reinterpret_cast<double2*>(dst + ni * 8) = make_double2(val[mi][ni][0], val[mi][ni][1]);
+        }
+        return;
+    }
 #pragma unroll
     for (int mi = 0; mi < 2; mi++) {
         const int pr = r0 + mi * 8 + g;
@@ -415,6 +430,29 @@ kbuild_dmma_kernel(KParams kp, const double* __restrict__ Btab,
             *reinterpret_cast<double2*>(out + gi * ld + j0 + c0 + ni * 8 + 2 * t4) = make_double2(o[0], o[1]);
         }
     }
+}
+
+// host-side dispatch over the specialisations
+template <bool TRAIN>
+inline void kbuild_dmma_launch(cudaStream_t s, dim3 grid, size_t smem, const KParams& kp, const double* Btab, const double* Fi, const int* Ci,
+                               int64_t stride_i, int64_t n_i, const double* Fj, const int* Cj, int64_t stride_j, int64_t n_j, const double* y,
+                               double* out, int64_t ld, int own_stride, int own_rank) {
+    const bool simple = kp.n_terms == 1 && kp.t[0].n_lin == 0 && kp.t[0].n_coreg == 0;
+#define GB2_KB_LAUNCH(KIND, SIMPLE)                                                                                             \
+    kbuild_dmma_kernel<TRAIN, KIND, SIMPLE><<<grid, KB_THREADS, smem, s>>>(kp, Btab, Fi, Ci, stride_i, n_i, Fj, Cj, stride_j, n_j, y, out, ld, \
+                                                                           own_stride, own_rank)
+    if (simple && kp.t[0].kind == GB2_EXPQUAD) GB2_KB_LAUNCH(GB2_EXPQUAD, true);
+    else if (simple && kp.t[0].kind == GB2_MATERN52) GB2_KB_LAUNCH(GB2_MATERN52, true);
+    else GB2_KB_LAUNCH(-1, false);
+#undef GB2_KB_LAUNCH
+}
+
+template <bool TRAIN>
+inline cudaError_t kbuild_dmma_configure() {
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(kbuild_dmma_kernel<TRAIN, GB2_EXPQUAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(kbuild_dmma_kernel<TRAIN, GB2_MATERN52, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kbuild_dmma_kernel<TRAIN, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
 }
 
 inline size_t kbuild_dmma_smem_bytes(const KParams& kp) {

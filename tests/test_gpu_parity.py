@@ -359,7 +359,7 @@ def test_tf32_mode_against_oracle(engine_tf32, n, d, P, kind, M_res):
         # regression guards, tighter than the gate
         assert np.max(np.abs(mu - mu0)) < 5e-3 * np.abs(mu0).max()
         assert np.max(np.abs(var - var0)) < 1e-4
-    np.testing.assert_allclose(eng.mll(), orc.mll(spec, X, y), rtol=1e-3)
+    np.testing.assert_allclose(eng.mll(), orc.mll(spec, X, y), rtol=5e-3)
 
 
 def test_tf32_small_problem_falls_back_to_fp64_kernels(engine_tf32):

@@ -24,10 +24,13 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     sizes = [int(a) for a in sys.argv[1:]] or [1000, 3000, 8192]
     with_oracle = os.environ.get("GB2_DIST_ORACLE", "1") == "1"
-    eng = GPEngine(local_rank)
+    prec = os.environ.get("GB2_DIST_PRECISION", "fp64")
+    eng = GPEngine(local_rank, prec)
+    if os.environ.get("GB2_DIST_P2P", "1") == "0":
+        eng.set_option("p2p", 0)     # ablation: NCCL broadcast + all-gather instead of NVLink peer stores
     r, w = gdist.init_engine(eng)
     assert (r, w) == (rank, world)
-    ref = GPEngine(local_rank)  # same GPU, not sharded
+    ref = GPEngine(local_rank, prec)  # same GPU, not sharded
     ok = True
     out = []
     for n in sizes:
@@ -42,7 +45,7 @@ def main():
         for _ in range(2):
             t0 = time.perf_counter(); ref.factorize(); t_one = time.perf_counter() - t0
         tm1 = ref.timings()
-        rec = {"N": len(y), "world": world, "rank": rank, "chol_ms_sharded": tm["cholesky_ms"], "chol_ms_single": tm1["cholesky_ms"],
+        rec = {"N": len(y), "world": world, "rank": rank, "precision": prec, "p2p": os.environ.get("GB2_DIST_P2P", "1"), "chol_ms_sharded": tm["cholesky_ms"], "chol_ms_single": tm1["cholesky_ms"],
                "wall_ms_sharded": t_shard * 1e3, "wall_ms_single": t_one * 1e3}
         if len(y) <= 8192:
             L, L1 = eng.get_L(), ref.get_L()
