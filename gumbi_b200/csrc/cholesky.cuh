@@ -324,6 +324,17 @@ __global__ void wait_counter_kernel(const unsigned* flag, unsigned expected) {
     if (threadIdx.x == 0) wait_counter(flag, expected);
 }
 
+// Device-side barrier over the peers at the start of a factorisation: the one-sided panel pushes of this factorisation must
+// not land in a peer's factor while that peer still reads the previous one (predict / gradient run on the same stream as this
+// kernel, so "my stream reached this point" means "I am done with the old factor").  Counters are cumulative.
+__global__ void p2p_barrier_kernel(PushArgs peers, const unsigned* own, unsigned expected) {
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        for (int pr = 0; pr < peers.n_peers; pr++) atomicAdd_system(peers.peerFlag[pr], 1u);
+        wait_counter(own, expected);
+    }
+}
+
 // Non-owners of block step k: wait for the owner's announcement, then pull inv(L_kk) and L_kk (2 x 128 KB) from the owner's
 // memory through the peer mapping into the local copies, and L_kk into the local factor.  grid = 32 CTAs x 256 threads.
 __global__ void __launch_bounds__(256)
@@ -438,6 +449,17 @@ inline int factor_steps(gb2_handle* h, int k0, int k1, int col_limit) {
     int launches = 0;
     cudaStream_t sm = h->s_main, sp = (h->opt_lookahead || G > 1) ? h->s_panel : h->s_main;
     const bool two = sp != sm;
+    if (G > 1 && h->p2p_ready && k0 == 0) {
+        // one barrier per factorisation, queued behind this rank's previous use of the factor
+        PushArgs peers{};
+        const size_t slot = (size_t)4 * h->p2p_nbmax;
+        for (int r = 0, q = 0; r < G; r++)
+            if (r != me) peers.peerFlag[q++] = h->peerFlags[r] + slot;
+        peers.n_peers = G - 1;
+        h->p2p_epoch++;
+        p2p_barrier_kernel<<<1, 32, 0, sm>>>(peers, h->dFlags + slot, (unsigned)(h->p2p_epoch * (G - 1)));
+        launches++;
+    }
     if (two) {  // the panel stream starts after everything already queued on main (the K build / the previous trailing update)
         cudaEvent_t e = pool_event(h, 2 * nb);
         cudaEventRecord(e, sm);

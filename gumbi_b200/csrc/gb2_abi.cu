@@ -465,9 +465,10 @@ static int build_K(gb2_handle* h, int& launches) {
         GB2_CUDA(h, cudaMemsetAsync(h->dSend, 0, (size_t)per_rank * TILE * TILE * sizeof(double), s));
         if (h->dFlags) GB2_CUDA(h, cudaFree(h->dFlags));
         h->p2p_nbmax = nb;
-        GB2_CUDA(h, cudaMalloc(&h->dFlags, (size_t)4 * nb * sizeof(unsigned)));
-        GB2_CUDA(h, cudaMemsetAsync(h->dFlags, 0, (size_t)4 * nb * sizeof(unsigned), s));
+        GB2_CUDA(h, cudaMalloc(&h->dFlags, ((size_t)4 * nb + 4) * sizeof(unsigned)));   // + the barrier counter
+        GB2_CUDA(h, cudaMemsetAsync(h->dFlags, 0, ((size_t)4 * nb + 4) * sizeof(unsigned), s));
         h->p2p_parity = 0;
+        h->p2p_epoch = 0;
         h->xch_cap = Np;
     }
     if (h->world > 1 && h->opt_p2p && !h->p2p_ready) {

@@ -110,6 +110,7 @@ struct gb2_handle {
     unsigned* dFlags = nullptr;      // [2 parities][2 kinds][p2p_nbmax] counters bumped by the peers
     int64_t p2p_nbmax = 0;
     int p2p_parity = 0;
+    int64_t p2p_epoch = 0;
     char* dIpcXch = nullptr;
 
     // GB2_TF32: tf32 hi/lo splits + their TMA descriptors (tf32gemm.cuh)

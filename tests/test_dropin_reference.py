@@ -1,0 +1,90 @@
+"""Drop-in check against the REAL reference wrappers (only where /root/reference exists, i.e. the build container; the GPU box
+replays the committed goldens instead).  ``make_backend(gumbi.regression.base.Regressor)`` must give a class that the
+reference's own DataSet / specify_model / prepare_grid / predict_grid / cross-validation-style re-construction drive without
+modification -- with the oracle standing in for the GPU engine (tests/ only)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "gumbi")), reason="reference tree not present (GPU box)")
+
+
+@pytest.fixture(scope="module")
+def ref_env():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gen_golden
+
+    gmb = gen_golden.import_reference()
+    from gumbi.regression.base import Regressor
+
+    from gumbi_b200 import make_backend
+    from test_backend_host import OracleEngine
+
+    B200GP = make_backend(Regressor)
+
+    class HostB200GP(B200GP):
+        """The drop-in class with the engine double injected (no GPU in this container)."""
+
+        def build_model(self, *a, **k):
+            self.engine = OracleEngine()
+            return super().build_model(*a, **k)
+
+    import pandas as pd
+
+    return gmb, HostB200GP, pd
+
+
+def test_fit_predict_grid_through_the_reference_wrappers(ref_env):
+    gmb, GP, pd = ref_env
+    g = load_golden("simple_regression_ExpQuad")
+    df = pd.read_pickle(os.path.join(REF, "gumbi", "data", "Example_DataSet.pkl")).query('Metric=="mean"')
+    ds = gmb.DataSet(df, outputs=["a", "b", "c", "d", "e", "f"], log_vars=["Y", "b", "c", "d", "f"], logit_vars=["X", "e"])
+    ds.tidy = ds.tidy[ds.tidy.Color.isin(["cyan", "magenta"]) & (ds.tidy.Pair == "burrata+barbaresco")]
+    gp = GP(ds, outputs=["d"])
+    # README.md:28-36 flow: fit -> prepare_grid -> predict_grid
+    gp.fit(continuous_dims=["X", "Y", "lg10_Z"], linear_dims=["X", "Y", "lg10_Z"], MAP_kwargs={"options": {"maxiter": 15}})
+    assert isinstance(gp.MAP, dict) and {"ls_total", "η_total", "σ", "c_total", "τ_total"} <= set(gp.MAP)
+    # the shaped arrays crossing the boundary are exactly the committed golden inputs (same wrappers, same data)
+    np.testing.assert_array_equal(gp._X, g["X"])
+    np.testing.assert_array_equal(gp._y, g["y"])
+    gp.prepare_grid(at=gp.parray(lg10_Z=8, X=0.5))
+    up = gp.predict_grid()
+    assert type(up).__name__ == "UncertainParameterArray" and up.shape == (100,)
+    assert np.all(np.isfinite(up.μ)) and np.all(up.σ2 > 0)
+    # pinning the hyper-parameters reproduces the golden posterior through the reference's own point preparation
+    gp.find_MAP(point=g["meta"]["point"])
+    pts_grid, _, _ = gp._prepare_points_for_prediction(gp.grid_points, output=gp._parse_prediction_output(None))
+    mu, var = gp.predict(pts_grid, with_noise=True)
+    np.testing.assert_allclose(mu, g["mean"][1:], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(var, g["var"][1:], rtol=1e-8, atol=1e-11)
+
+
+def test_multioutput_predict_points_reads_W_and_kappa_from_MAP(ref_env):
+    """base.py:585-599: the base class splits by the output column and builds the correlation from MAP['W_*'], MAP['κ_*']."""
+    gmb, GP, pd = ref_env
+    g = load_golden("multioutput_regression")
+    df = pd.read_pickle(os.path.join(REF, "gumbi", "data", "Example_DataSet.pkl"))
+    df = df[(df.Name == "binary-pollen") & (df.Color == "cyan") & (df.Metric == "mean")]
+    ds = gmb.DataSet(df, outputs=["a", "b", "c", "d", "e", "f"], log_vars=["Y", "b", "c", "d", "f"], logit_vars=["X", "e"])
+    gp = GP(ds, outputs=["a", "b", "c", "d", "e"])
+    gp.specify_model(continuous_dims="lg10_Z", linear_dims="lg10_Z")
+    gp.build_model()
+    gp.find_MAP(point=g["meta"]["point"])
+    np.testing.assert_array_equal(gp._X, g["X"])
+    gp.prepare_grid(limits=gp.parray(lg10_Z=[1, 9]), resolution=17)
+    mv = gp.predict_grid()
+    assert type(mv).__name__ == "MVUncertainParameterArray" and mv.shape == (17,)
+    pts, _, _ = gp._prepare_points_for_prediction(gp.grid_points, output=gp._parse_prediction_output(None))
+    np.testing.assert_array_equal(pts, g["points"])
+    mu, var = gp.predict(pts)
+    np.testing.assert_allclose(mu, g["mean"], rtol=1e-9, atol=1e-11)
+    # cross_validate-style reconstruction (base.py:1060-1068): same class, model_specs round-trip
+    gp2 = GP(ds, outputs=["a", "b", "c", "d", "e"])
+    gp2.specify_model(continuous_dims="lg10_Z", linear_dims="lg10_Z")
+    gp2.build_model(**gp.model_specs)
+    assert gp2.model_specs == gp.model_specs
