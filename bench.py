@@ -106,6 +106,14 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "B200_PROFILING.md fallback"}
 
 
+def measured_traffic(key):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu pass (profiles/traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(key)
+    return None
+
+
 def cublas_dgemm_peak(torch, dev):
     """fp64 tensor roofline denominator: MEASURED_PEAKS.json carries no fp64 figure, so cuBLAS DGEMM 8192^3 is measured
     live (burst, best of 5) outside the timed region.  tcgen05 has no fp64 kind; DMMA is the fp64 tensor path."""
@@ -332,17 +340,27 @@ def run_ours(args):
         gp = ArrayGP(X, y, cont, device=local_rank, precision=precision, distributed=use_dist, **cat)
         e2e_opts = list(args.opt)
 
+        host_ms = {"build_model": 0.0, "find_MAP": 0.0, "predict": 0.0}
+
         def step_e2e():
+            t0 = time.perf_counter()
             gp.build_model(continuous_kernel=kind_)   # H2D X, y
             while e2e_opts:
                 kv = e2e_opts.pop()
                 gp.engine.set_option(kv.split("=")[0], int(kv.split("=")[1]))
+            t1 = time.perf_counter()
             gp.find_MAP(point=point)
-            return gp.predict(Xs, with_noise=True)      # K-build + Cholesky + solve; H2D grid (slice), D2H mean/var (+ gather)
+            t2 = time.perf_counter()
+            out = gp.predict(Xs, with_noise=True)       # K-build + Cholesky + solve; H2D grid (slice), D2H mean/var (+ gather)
+            t3 = time.perf_counter()
+            host_ms["build_model"] += (t1 - t0) * 1e3; host_ms["find_MAP"] += (t2 - t1) * 1e3; host_ms["predict"] += (t3 - t2) * 1e3
+            return out
 
         for _ in range(3):
             mu_h, var_h = step_e2e()
         barrier()
+        for k in host_ms:
+            host_ms[k] = 0.0
         t0 = time.perf_counter()
         for _ in range(args.steps):
             mu_h, var_h = step_e2e()
@@ -354,6 +372,7 @@ def run_ours(args):
         tol = 1e-6 if precision == "fp64" else 1e-2
         assert np.max(np.abs(mu_h - mu_dev)) <= tol * np.max(np.abs(mu_dev)), "e2e and device arms disagree"
         e2e["device_phases_ms_last_step"] = {k: v for k, v in gp.engine.timings().items() if k.endswith("_ms")}
+        e2e["host_call_ms_per_step"] = {k: v / args.steps for k, v in host_ms.items()}
         gp.engine.close()
 
     if rank != 0:
@@ -377,7 +396,9 @@ def run_ours(args):
             "bound": "tensor", "achieved": solve_tflops, "peak": dgemm_peak, "unit": "TFLOP/s", "frac": solve_tflops / dgemm_peak,
             "peak_source": "cuBLAS DGEMM 8192^3 burst measured live in this run (MEASURED_PEAKS.json has no fp64 entry; tcgen05 has no fp64 kind)",
             "algorithmic_flop_per_step": float(N) * N * Ml, "launches_per_step": solve_launches,
-            "avg_launch_ms": phase["solve_ms"] / solve_launches, "traffic": None,
+            "avg_launch_ms": phase["solve_ms"] / solve_launches,
+            "traffic": (measured_traffic(f"{args.workload}:fp64:solve") or {}).get("dram_bytes_per_launch") if world == 1 else None,
+            "traffic_source": (measured_traffic(f"{args.workload}:fp64:solve") or {}).get("source"),
         }
     else:
         tf32_peak = peaks["bf16_tflops"] / 2.0

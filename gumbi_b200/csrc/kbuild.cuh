@@ -432,26 +432,199 @@ kbuild_dmma_kernel(KParams kp, const double* __restrict__ Btab,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// K-build v3 (the common model: one stationary term, no Linear, no Coregion): a CTA keeps its 64 row points resident and walks
+// a strip of up to KB3_JG column tiles; the column-side features of tile j+1 are prefetched with cp.async into the other
+// half of a double buffer while tile j is computed, so the global-load latency that v2 paid once per 64x64 tile
+// (ncu: 25 % of the samples in the tile prologue + barrier) is off the critical path.  Same DMMA Gram + table exp as v2, with
+// eta^2 folded into the exp table and the range clamp reduced to one compare + select.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int KB3_JG = 8;
+
+__device__ __forceinline__ void kb_cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem_src));
+}
+
+// eta^2 * exp(x), x <= ~0; tab = eta^2 * 2^(j/64).  x < -700 returns 0 (exp < 1e-304).
+__device__ __forceinline__ double exp_tab_scaled(double x, const double* __restrict__ tab) {
+    const double t = fma(x, 92.33248261689366, 6755399441055744.0);
+    const int n = __double2loint(t);
+    const double kf = t - 6755399441055744.0;
+    double r = fma(kf, -0.01083042469326756, x);
+    r = fma(kf, -2.9815858269852933e-12, r);
+    const double r2 = r * r;
+    double q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    q = fma(q, r, 1.0 / 6.0);
+    q = fma(q, r, 0.5);
+    const double p = fma(q, r2, r);
+    const double T = tab[n & 63];
+    const double res = fma(T, p, T);
+    const double sc = __hiloint2double(__double2hiint(res) + ((n >> 6) << 20), __double2loint(res));
+    return x < -700.0 ? 0.0 : sc;
+}
+
+template <bool TRAIN, int KIND>
+__global__ void __launch_bounds__(KB_THREADS, 3)
+kbuild_strip_kernel(KParams kp, const double* __restrict__ Fi, int64_t stride_i, int64_t n_i, const double* __restrict__ Fj,
+                    int64_t stride_j, int64_t n_j, int n_col_tiles, const double* __restrict__ y, double* __restrict__ out, int64_t ld,
+                    int own_stride, int own_rank) {
+    const int bi = blockIdx.y;
+    const int jt0 = blockIdx.x * KB3_JG;
+    if (TRAIN && jt0 > bi) return;
+    if (TRAIN && own_stride > 1 && ((bi * KB_T) / TILE) % own_stride != own_rank) return;
+    int jt1 = jt0 + KB3_JG < n_col_tiles ? jt0 + KB3_JG : n_col_tiles;
+    if (TRAIN && jt1 > bi + 1) jt1 = bi + 1;
+    extern __shared__ __align__(16) unsigned char kb_smem[];
+    const TermDev& T = kp.t[0];
+    const int d = T.d, ka = kb2_ka(d);
+    double* sA = reinterpret_cast<double*>(kb_smem);      // [ka][TS]
+    double* sB = sA + ka * KB2_TS;                         // [2][ka][TS]
+    double* sTab = sB + 2 * ka * KB2_TS;                   // [64]
+    const int tid = threadIdx.x;
+    const int64_t i0 = (int64_t)bi * KB_T;
+    const double* Fjt = Fj + (int64_t)T.feat_off * stride_j;
+
+    auto prefetch = [&](int jt, int buf) {
+        double* dst = sB + buf * ka * KB2_TS;
+        const int64_t j0 = (int64_t)jt * KB_T;
+        for (int c = tid; c < d * 32; c += KB_THREADS) {     // d rows x 32 chunks of 16 bytes
+            const int k = c >> 5, ch = c & 31;
+            kb_cp_async16(dst + k * KB2_TS + ch * 2, Fjt + (int64_t)k * stride_j + j0 + ch * 2);
+        }
+        if (tid < KB_T) dst[(d + 1) * KB2_TS + tid] = -0.5 * Fjt[(int64_t)d * stride_j + j0 + tid];
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+
+    // one-time: exp table (scaled by eta^2), constant rows, row-side features
+    if (tid < 64) sTab[tid] = T.eta2 * g_exp2_tab[tid];
+    for (int e = tid; e < 2 * KB_T; e += KB_THREADS) {
+        const int buf = e / KB_T, p = e % KB_T;
+        sB[buf * ka * KB2_TS + d * KB2_TS + p] = 1.0;
+        for (int k = d + 2; k < ka; k++) sB[buf * ka * KB2_TS + k * KB2_TS + p] = 0.0;
+    }
+    {
+        const int p = tid & 63;
+        for (int k = tid >> 6; k < ka; k += KB_THREADS / 64) {
+            double a;
+            if (k < d) a = Fi[(int64_t)(T.feat_off + k) * stride_i + i0 + p];
+            else if (k == d) a = -0.5 * Fi[(int64_t)(T.feat_off + d) * stride_i + i0 + p];
+            else a = (k == d + 1) ? 1.0 : 0.0;
+            sA[k * KB2_TS + p] = a;
+        }
+    }
+    prefetch(jt0, 0);
+
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int r0 = (warp >> 1) * 16, c0 = (warp & 1) * 32;
+    for (int jt = jt0; jt < jt1; jt++) {
+        const int buf = (jt - jt0) & 1;
+        asm volatile("cp.async.wait_group 0;\n" ::);
+        __syncthreads();
+        if (jt + 1 < jt1) prefetch(jt + 1, buf ^ 1);
+        const double* cB = sB + buf * ka * KB2_TS;
+        double acc[2][4][2];
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        for (int kk = 0; kk < ka; kk += 4) {
+            const double* pa = sA + (kk + t4) * KB2_TS + r0 + g;
+            const double* pb = cB + (kk + t4) * KB2_TS + c0 + g;
+            const double a0 = pa[0], a1 = pa[8];
+            const double b0 = pb[0], b1 = pb[8], b2 = pb[16], b3 = pb[24];
+            kb_dmma(acc[0][0][0], acc[0][0][1], a0, b0); kb_dmma(acc[0][1][0], acc[0][1][1], a0, b1);
+            kb_dmma(acc[0][2][0], acc[0][2][1], a0, b2); kb_dmma(acc[0][3][0], acc[0][3][1], a0, b3);
+            kb_dmma(acc[1][0][0], acc[1][0][1], a1, b0); kb_dmma(acc[1][1][0], acc[1][1][1], a1, b1);
+            kb_dmma(acc[1][2][0], acc[1][2][1], a1, b2); kb_dmma(acc[1][3][0], acc[1][3][1], a1, b3);
+        }
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const double x = acc[mi][ni][e];
+                    if (KIND == GB2_EXPQUAD) {
+                        acc[mi][ni][e] = exp_tab_scaled(x, sTab);
+                    } else {  // GB2_MATERN52
+                        const double r = sqrt(fmax(-2.0 * x, 0.0) + 1e-12);
+                        const double s5 = 2.23606797749978969641;
+                        acc[mi][ni][e] = (1.0 + s5 * r + (5.0 / 3.0) * (r * r)) * exp_tab_scaled(-s5 * r, sTab);
+                    }
+                }
+        const int64_t j0 = (int64_t)jt * KB_T;
+        if ((!TRAIN || bi != jt) && i0 + KB_T <= n_i && j0 + KB_T <= n_j) {
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++) {
+                double* dst = out + (i0 + r0 + mi * 8 + g) * ld + j0 + c0 + 2 * t4;
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) *reinterpret_cast<double2*>(dst + ni * 8) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+            }
+            continue;
+        }
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++) {
+            const int64_t gi = i0 + r0 + mi * 8 + g;
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) {
+                double o[2];
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int64_t gj = j0 + c0 + ni * 8 + 2 * t4 + e;
+                    double v = acc[mi][ni][e];
+                    if (TRAIN) {
+                        if (gi < n_i && gj < n_j) {
+                            if (gi == gj) v += kp.sigma2 + kp.jitter;     // SIMPLE: no noise Coregion (it needs an output column)
+                        } else if (gi == n_i && gj < n_j) {
+                            v = y[gj];
+                        } else {
+                            v = (gi == gj) ? 1.0 : 0.0;
+                        }
+                    } else {
+                        if (gi >= n_i || gj >= n_j) v = 0.0;
+                    }
+                    o[e] = v;
+                }
+                *reinterpret_cast<double2*>(out + gi * ld + j0 + c0 + ni * 8 + 2 * t4) = make_double2(o[0], o[1]);
+            }
+        }
+    }
+}
+
+inline size_t kbuild_strip_smem_bytes(const KParams& kp) { return (size_t)(3 * kb2_ka(kp.t[0].d) * KB2_TS + 64) * sizeof(double); }
+
 // host-side dispatch over the specialisations
 template <bool TRAIN>
 inline void kbuild_dmma_launch(cudaStream_t s, dim3 grid, size_t smem, const KParams& kp, const double* Btab, const double* Fi, const int* Ci,
                                int64_t stride_i, int64_t n_i, const double* Fj, const int* Cj, int64_t stride_j, int64_t n_j, const double* y,
                                double* out, int64_t ld, int own_stride, int own_rank) {
-    const bool simple = kp.n_terms == 1 && kp.t[0].n_lin == 0 && kp.t[0].n_coreg == 0;
+    const bool simple = kp.n_terms == 1 && kp.t[0].n_lin == 0 && kp.t[0].n_coreg == 0 && kp.noise_cat < 0;
+    if (simple && (kp.t[0].kind == GB2_EXPQUAD || kp.t[0].kind == GB2_MATERN52)) {
+        // grid: x = strips of KB3_JG column tiles, y = row tiles
+        dim3 sgrid((grid.x + KB3_JG - 1) / KB3_JG, grid.y);
+        const size_t ssm = kbuild_strip_smem_bytes(kp);
+        if (kp.t[0].kind == GB2_EXPQUAD)
+            kbuild_strip_kernel<TRAIN, GB2_EXPQUAD><<<sgrid, KB_THREADS, ssm, s>>>(kp, Fi, stride_i, n_i, Fj, stride_j, n_j, (int)grid.x, y, out, ld,
+                                                                                  own_stride, own_rank);
+        else
+            kbuild_strip_kernel<TRAIN, GB2_MATERN52><<<sgrid, KB_THREADS, ssm, s>>>(kp, Fi, stride_i, n_i, Fj, stride_j, n_j, (int)grid.x, y, out, ld,
+                                                                                   own_stride, own_rank);
+        return;
+    }
 #define GB2_KB_LAUNCH(KIND, SIMPLE)                                                                                             \
     kbuild_dmma_kernel<TRAIN, KIND, SIMPLE><<<grid, KB_THREADS, smem, s>>>(kp, Btab, Fi, Ci, stride_i, n_i, Fj, Cj, stride_j, n_j, y, out, ld, \
                                                                            own_stride, own_rank)
-    if (simple && kp.t[0].kind == GB2_EXPQUAD) GB2_KB_LAUNCH(GB2_EXPQUAD, true);
-    else if (simple && kp.t[0].kind == GB2_MATERN52) GB2_KB_LAUNCH(GB2_MATERN52, true);
-    else GB2_KB_LAUNCH(-1, false);
+    GB2_KB_LAUNCH(-1, false);
 #undef GB2_KB_LAUNCH
 }
 
 template <bool TRAIN>
 inline cudaError_t kbuild_dmma_configure() {
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(kbuild_dmma_kernel<TRAIN, GB2_EXPQUAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(kbuild_dmma_kernel<TRAIN, GB2_MATERN52, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(kbuild_strip_kernel<TRAIN, GB2_EXPQUAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(kbuild_strip_kernel<TRAIN, GB2_MATERN52>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(kbuild_dmma_kernel<TRAIN, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
 }
 

@@ -65,7 +65,7 @@ def main():
 
             mu0, var0 = orc.predict(spec, X, y, Xs, True)
             rec["oracle_max_rel"] = float(max(np.max(np.abs(mu - mu0)) / np.abs(mu0).max(), np.max(np.abs(var - var0) / np.abs(var0))))
-            ok &= rec["oracle_max_rel"] < 1e-6
+            ok &= rec["oracle_max_rel"] < (1e-6 if prec == "fp64" else 1e-2)
         out.append(rec)
         if rank == 0:
             print(json.dumps(rec), flush=True)
