@@ -23,14 +23,19 @@ namespace gb2 {
 namespace tc {
 
 constexpr int TM = 128, TN = 128, TK = 32;       // output tile; K columns per stage (32 fp32 = one 128-byte swizzle row)
-constexpr int STAGES = 3;
+// NB = number of 128-column B tiles a CTA tile spans (output tile 128 x 128*NB).  NB = 2 halves the L2->SM operand traffic per
+// flop (the A tile is staged once for 256 columns): at NB = 1 the kernel is capped by L2 bandwidth at ~50 % tensor-pipe
+// utilisation (ncu, profiles/r01e), which is what a 3xTF32 product with hi+lo operands costs on 128 x 128 tiles.
 constexpr int TILE_BYTES = TM * TK * 4;          // 16 KB per operand tile
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // A_hi, A_lo, B_hi, B_lo
 constexpr int THREADS = 192;
-constexpr int TMEM_COLS = 256;                   // two 128-column fp32 accumulators
 constexpr int EPI_LD = 33;                       // padded row of the per-warp 32 x 32 fp32 transpose buffer (conflict-free both ways)
 constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;   // one buffer per epilogue warp
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + EPI_BYTES;
+template <int NB> struct Cfg {
+    static constexpr int STAGES = NB == 1 ? 3 : 2;
+    static constexpr int STAGE_BYTES = (2 + 2 * NB) * TILE_BYTES;     // A_hi, A_lo, NB x (B_hi, B_lo)
+    static constexpr int TMEM_COLS = 2 * NB * TN;                     // two accumulators of NB x 128 fp32 columns
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + EPI_BYTES;
+};
 constexpr int TC_MAX_K = 1024;                   // fp32 accumulation depth per launch
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -105,7 +110,7 @@ constexpr uint32_t IDESC_TF32_128x128 = (1u << 4) | (2u << 7) | (2u << 10) | ((u
 
 struct GemmArgs {
     double* C; int64_t ldc;          // C points at global (row 0, column 0); tile (bi, bj) covers row block rb(bi), column block cblk0 + bj
-    int n_bi, n_bj;                  // tile grid (128 x 128 tiles)
+    int n_bi, n_bj;                  // tile grid: n_bi row tiles of 128, n_bj = number of 128-column blocks (CTA tiles span NB of them)
     int rb_first, rb_stride;         // row block of tile row bi = rb_first + bi * rb_stride  (block-cyclic row ownership; dense: stride 1)
     int cblk0;                       // first column block
     int lower;                       // 1: skip tiles whose column block lies above their row block (trailing SYRK)
@@ -117,23 +122,31 @@ struct GemmArgs {
 constexpr int RASTER_GROUP = 16;     // tile rows per raster band: concurrently running CTAs share ~16 A and ~9 B operand panels in L2
 
 // t -> (bi, bj), banded column-major order inside bands of RASTER_GROUP tile rows; false if the tile is skipped (lower mode).
-__device__ __forceinline__ bool tile_coords(const GemmArgs& g, int t, int& bi, int& bj) {
-    const int band_sz = RASTER_GROUP * g.n_bj;
+// bj is returned in units of 128-column blocks (first block of the CTA tile); nh = number of live 128-column halves (1..NB).
+template <int NB>
+__device__ __forceinline__ bool tile_coords(const GemmArgs& g, int t, int& bi, int& bj, int& nh) {
+    const int n_sj = (g.n_bj + NB - 1) / NB;
+    const int band_sz = RASTER_GROUP * n_sj;
     const int band = t / band_sz, r = t % band_sz;
     const int rows_in_band = min(RASTER_GROUP, g.n_bi - band * RASTER_GROUP);
     bi = band * RASTER_GROUP + r % rows_in_band;
-    bj = r / rows_in_band;
-    if (bj >= g.n_bj) return false;   // the last band may be short
-    if (g.lower && g.cblk0 + bj > g.rb_first + bi * g.rb_stride) return false;
-    return true;
+    const int sj = r / rows_in_band;
+    if (sj >= n_sj) return false;   // the last band may be short
+    bj = sj * NB;
+    int last = min(bj + NB, g.n_bj) - 1;                                           // last 128-column block inside the matrix
+    if (g.lower) last = min(last, g.rb_first + bi * g.rb_stride - g.cblk0);        // ... and not above the diagonal
+    nh = last - bj + 1;
+    return nh >= 1;
 }
 
+template <int NB>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
                    const __grid_constant__ CUtensorMap mBhi, const __grid_constant__ CUtensorMap mBlo, GemmArgs g) {
     extern __shared__ unsigned char tc_smem_raw[];
     // operand stages need 1024-byte alignment (128B swizzle atoms)
     unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int STAGES = Cfg<NB>::STAGES, STAGE_BYTES = Cfg<NB>::STAGE_BYTES, TMEM_COLS = Cfg<NB>::TMEM_COLS;
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + STAGES * STAGE_BYTES);
     uint64_t* full = bars;                  // [STAGES]  TMA bytes landed
     uint64_t* empty = bars + STAGES;        // [STAGES]  MMAs that read the stage have completed
@@ -143,7 +156,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
     float* epi = reinterpret_cast<float*>(base + STAGES * STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tiles = ((g.n_bi + RASTER_GROUP - 1) / RASTER_GROUP) * RASTER_GROUP * g.n_bj;   // raster slots (some are skipped)
+    const int n_tiles = ((g.n_bi + RASTER_GROUP - 1) / RASTER_GROUP) * RASTER_GROUP * ((g.n_bj + NB - 1) / NB);   // raster slots (some are skipped)
     const int nk = g.K / TK;
 
     if (warp == 0 && lane == 0) {
@@ -162,17 +175,19 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                int bi, bj;
-                if (!tile_coords(g, t, bi, bj)) continue;
+                int bi, bj, nh;
+                if (!tile_coords<NB>(g, t, bi, bj, nh)) continue;
                 const int arow = (g.rb_first + bi * g.rb_stride) * TM, brow = g.b_row0 + bj * TN;
                 for (int kb = 0; kb < nk; kb++) {
                     mbar_wait(empty + stage, phase ^ 1);
                     unsigned char* st = base + stage * STAGE_BYTES;
-                    mbar_expect_tx(full + stage, STAGE_BYTES);
+                    mbar_expect_tx(full + stage, (2 + 2 * nh) * TILE_BYTES);
                     tma_load_2d(st, &mAhi, g.a_k0 + kb * TK, arow, full + stage);
                     tma_load_2d(st + TILE_BYTES, &mAlo, g.a_k0 + kb * TK, arow, full + stage);
-                    tma_load_2d(st + 2 * TILE_BYTES, &mBhi, g.b_k0 + kb * TK, brow, full + stage);
-                    tma_load_2d(st + 3 * TILE_BYTES, &mBlo, g.b_k0 + kb * TK, brow, full + stage);
+                    for (int hh = 0; hh < nh; hh++) {
+                        tma_load_2d(st + (2 + 2 * hh) * TILE_BYTES, &mBhi, g.b_k0 + kb * TK, brow + hh * TN, full + stage);
+                        tma_load_2d(st + (3 + 2 * hh) * TILE_BYTES, &mBlo, g.b_k0 + kb * TK, brow + hh * TN, full + stage);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -183,27 +198,30 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
             int stage = 0; uint32_t phase = 0;
             int it = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                int bi_, bj_;
-                if (!tile_coords(g, t, bi_, bj_)) continue;
+                int bi_, bj_, nh;
+                if (!tile_coords<NB>(g, t, bi_, bj_, nh)) continue;
                 const int buf = it & 1;
                 const uint32_t tphase = (uint32_t)(it >> 1) & 1;
                 it++;
                 mbar_wait(tempty + buf, tphase ^ 1);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * TN);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * NB * TN);
                 for (int kb = 0; kb < nk; kb++) {
                     mbar_wait(full + stage, phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(base + stage * STAGE_BYTES);
                     const uint64_t dAhi = make_smem_desc(sa), dAlo = make_smem_desc(sa + TILE_BYTES);
-                    const uint64_t dBhi = make_smem_desc(sa + 2 * TILE_BYTES), dBlo = make_smem_desc(sa + 3 * TILE_BYTES);
+                    for (int hh = 0; hh < nh; hh++) {
+                        const uint64_t dBhi = make_smem_desc(sa + (2 + 2 * hh) * TILE_BYTES), dBlo = make_smem_desc(sa + (3 + 2 * hh) * TILE_BYTES);
+                        const uint32_t td = tmem_d + (uint32_t)(hh * TN);
 #pragma unroll
-                    for (int k = 0; k < TK / 8; k++) {
-                        // advancing 8 tf32 = 32 bytes along K inside the swizzle row: +2 in the 16-byte address field
-                        const uint64_t o = (uint64_t)(k * 2);
-                        umma_tf32(tmem_d, dAlo + o, dBhi + o, IDESC_TF32_128x128, (kb | k) != 0);   // small terms first
-                        umma_tf32(tmem_d, dAhi + o, dBlo + o, IDESC_TF32_128x128, 1);
-                        umma_tf32(tmem_d, dAhi + o, dBhi + o, IDESC_TF32_128x128, 1);
+                        for (int k = 0; k < TK / 8; k++) {
+                            // advancing 8 tf32 = 32 bytes along K inside the swizzle row: +2 in the 16-byte address field
+                            const uint64_t o = (uint64_t)(k * 2);
+                            umma_tf32(td, dAlo + o, dBhi + o, IDESC_TF32_128x128, (kb | k) != 0);   // small terms first
+                            umma_tf32(td, dAhi + o, dBlo + o, IDESC_TF32_128x128, 1);
+                            umma_tf32(td, dAhi + o, dBhi + o, IDESC_TF32_128x128, 1);
+                        }
                     }
                     umma_commit(empty + stage);                 // frees the stage once these MMAs have read it
                     if (kb == nk - 1) umma_commit(tfull + buf); // accumulator complete
@@ -216,8 +234,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
         const int q = warp & 3;  // TMEM lane quadrant this warp may access
         int it = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            int bi, bj;
-            if (!tile_coords(g, t, bi, bj)) continue;
+            int bi, bj, nh;
+            if (!tile_coords<NB>(g, t, bi, bj, nh)) continue;
             const int buf = it & 1;
             const uint32_t tphase = (uint32_t)(it >> 1) & 1;
             it++;
@@ -228,14 +246,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
             float* S = epi + (warp - 2) * 32 * EPI_LD;
             double* cbase = g.C + ((int64_t)(g.rb_first + bi * g.rb_stride) * TM + q * 32) * g.ldc + (int64_t)(g.cblk0 + bj) * TN + lane;
 #pragma unroll 1
-            for (int c0 = 0; c0 < TN; c0 += 32) {
+            for (int c0 = 0; c0 < nh * TN; c0 += 32) {
                 // 32 independent 256-byte row requests per warp in flight (32 KB per SM) before anything is consumed
                 double* cp = cbase + c0;
                 double o[32];
 #pragma unroll
                 for (int u = 0; u < 32; u++) o[u] = cp[(int64_t)u * g.ldc];
                 float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TN + c0), v);
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * NB * TN + c0), v);
 #pragma unroll
                 for (int c = 0; c < 32; c++) S[lane * EPI_LD + c] = v[c];
                 __syncwarp();
@@ -303,13 +321,17 @@ inline CUresult make_tmap(CUtensorMap* map, const float* ptr, uint64_t rows, uin
 }
 
 inline cudaError_t gemm_tf32x3_configure() {
-    return cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(gemm_tf32x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES);
 }
 
 // C -= A B^T over the tile grid, K split into launches of <= TC_MAX_K columns (fp64 carry between launches).
 inline void gemm_tf32x3_launch(cudaStream_t s, int n_sm, const CUtensorMap& mAhi, const CUtensorMap& mAlo, const CUtensorMap& mBhi,
-                               const CUtensorMap& mBlo, GemmArgs g, int K_total, int& launches) {
-    const int n_tiles = g.n_bi * g.n_bj;
+                               const CUtensorMap& mBlo, GemmArgs g, int K_total, int& launches, int nb_tile = 2) {
+    // 128 x 256 CTA tiles whenever there are enough of them to fill the machine, else 128 x 128
+    const int NBsel = (nb_tile == 2 && g.n_bi * ((g.n_bj + 1) / 2) >= n_sm) ? 2 : 1;
+    const int n_tiles = g.n_bi * ((g.n_bj + NBsel - 1) / NBsel);
     if (n_tiles <= 0 || K_total <= 0) return;
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;
     const int a_k0 = g.a_k0, b_k0 = g.b_k0;
@@ -317,7 +339,8 @@ inline void gemm_tf32x3_launch(cudaStream_t s, int n_sm, const CUtensorMap& mAhi
         g.K = K_total - k0 < TC_MAX_K ? K_total - k0 : TC_MAX_K;
         g.a_k0 = a_k0 + k0;
         g.b_k0 = b_k0 + k0;
-        gemm_tf32x3_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(mAhi, mAlo, mBhi, mBlo, g);
+        if (NBsel == 2) gemm_tf32x3_kernel<2><<<grid, THREADS, Cfg<2>::SMEM_BYTES, s>>>(mAhi, mAlo, mBhi, mBlo, g);
+        else gemm_tf32x3_kernel<1><<<grid, THREADS, Cfg<1>::SMEM_BYTES, s>>>(mAhi, mAlo, mBhi, mBlo, g);
         launches++;
     }
 }

@@ -9,7 +9,7 @@
 using namespace gb2;
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); return 2; } } while (0)
 
-int run(int M, int N, int K, int lower, bool check) {
+int run(int M, int N, int K, int lower, bool check, int nbt = 2) {
     std::mt19937_64 rng(1234);
     std::normal_distribution<double> nd(0.0, 1.0);
     std::vector<double> A((size_t)M * K), B((size_t)N * K), C((size_t)M * N), C0;
@@ -36,7 +36,7 @@ int run(int M, int N, int K, int lower, bool check) {
     g.a_k0 = g.b_row0 = g.b_k0 = 0;
     int launches = 0;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    tc::gemm_tf32x3_launch(0, n_sm, mAhi, mAlo, mBhi, mBlo, g, K, launches);
+    tc::gemm_tf32x3_launch(0, n_sm, mAhi, mAlo, mBhi, mBlo, g, K, launches, nbt);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     int rc = 0;
@@ -53,19 +53,19 @@ int run(int M, int N, int K, int lower, bool check) {
                 if (fabs(ref) > maxref) maxref = fabs(ref);
                 if (err > 1e-3 * sqrt((double)K)) { if (bad < 5) printf("  bad (%d,%d): got %.9g want %.9g\n", i, j, C[(size_t)i * N + j], ref); bad++; }
             }
-        printf("check M=%d N=%d K=%d lower=%d launches=%d: max|err|=%.3e (max|ref|=%.3e, rel %.2e) bad=%ld -> %s\n", M, N, K, lower, launches,
+        printf("check nbt=%d M=%d N=%d K=%d lower=%d launches=%d: max|err|=%.3e (max|ref|=%.3e, rel %.2e) bad=%ld -> %s\n", nbt, M, N, K, lower, launches,
                maxerr, maxref, maxerr / maxref, bad, bad ? "FAIL" : "ok");
         rc = bad ? 1 : 0;
     } else {
         const int reps = 5;
         cudaEventRecord(e0);
-        for (int i = 0; i < reps; i++) tc::gemm_tf32x3_launch(0, n_sm, mAhi, mAlo, mBhi, mBlo, g, K, launches);
+        for (int i = 0; i < reps; i++) tc::gemm_tf32x3_launch(0, n_sm, mAhi, mAlo, mBhi, mBlo, g, K, launches, nbt);
         cudaEventRecord(e1);
         CK(cudaDeviceSynchronize());
         float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
         const double tiles = lower ? (double)g.n_bi * (g.n_bi + 1) / 2 : (double)g.n_bi * g.n_bj;
         const double flop = 2.0 * tiles * 128 * 128 * K;
-        printf("time  M=%d N=%d K=%d lower=%d: %.3f ms  %.1f TFLOP/s fp64-equivalent (x3 tf32 MMA = %.1f TFLOP/s tensor)\n", M, N, K, lower, ms,
+        printf("time  nbt=%d M=%d N=%d K=%d lower=%d: %.3f ms  %.1f TFLOP/s fp64-equivalent (x3 tf32 MMA = %.1f TFLOP/s tensor)\n", nbt, M, N, K, lower, ms,
                flop / ms / 1e9, 3 * flop / ms / 1e9);
     }
     cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(Ahi); cudaFree(Alo); cudaFree(Bhi); cudaFree(Blo);
@@ -74,16 +74,19 @@ int run(int M, int N, int K, int lower, bool check) {
 
 int main() {
     int rc = 0;
-    rc |= run(128, 128, 32, 0, true);
-    rc |= run(128, 128, 128, 0, true);
-    rc |= run(256, 384, 512, 0, true);
-    rc |= run(1024, 1024, 512, 1, true);
-    rc |= run(2048, 1280, 2048 + 1024, 0, true);   // K split over 3 launches
+    for (int nbt = 1; nbt <= 2; nbt++) {
+        rc |= run(128, 128, 32, 0, true, nbt);
+        rc |= run(256, 384, 512, 0, true, nbt);
+        rc |= run(1024, 1024, 512, 1, true, nbt);
+        rc |= run(2432, 2432, 256, 1, true, nbt);            // odd number of 128-column blocks (19): ragged last CTA tile
+        rc |= run(2560, 2432, 2048 + 1024, 0, true, nbt);    // K split over 3 launches, 19 column blocks
+    }
     if (rc) { printf("CORRECTNESS FAILED\n"); return rc; }
-    run(8192, 8192, 512, 1, false);
-    run(16384, 16384, 512, 1, false);
-    run(32768, 32768, 512, 1, false);
-    run(10112, 8192, 1024, 0, false);
-    run(10112, 16384, 4096, 0, false);
+    for (int nbt = 1; nbt <= 2; nbt++) {
+        run(8192, 8192, 512, 1, false, nbt);
+        run(32768, 32768, 512, 1, false, nbt);
+        run(10112, 8192, 1024, 0, false, nbt);
+        run(10112, 16384, 4096, 0, false, nbt);
+    }
     return 0;
 }
