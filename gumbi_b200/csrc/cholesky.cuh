@@ -588,7 +588,7 @@ inline int cholesky_enqueue(gb2_handle* h) {
     const int64_t Np = h->Np, ld = h->Np;
     const int nb = (int)(Np / TILE);
     int launches = 0;
-    const int pw = h->opt_tf32_nb;
+    const int pw = h->tf32_nb();
     if (h->precision == GB2_TF32 && nb > pw) {
         cudaStream_t sm = h->s_main;
         const int G = h->world, me = h->rank;

@@ -82,7 +82,7 @@ int predict_common(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_nois
     const int ncols = (int)((N + TILE - 1) / TILE);  // column blocks that carry training points
     int rc;
     if ((rc = ensure(h, h->dAt, h->At_cap, chunk * Np))) return rc;
-    const bool tf32 = h->precision == GB2_TF32 && ncols > h->opt_tf32_nb;
+    const bool tf32 = h->precision == GB2_TF32 && ncols > h->opt_tf32_leaf;
     if (tf32) {
         // tf32 hi/lo copies: the factor (once per factorisation) and the solved panel (per chunk)
         if (h->Lsplit_cap < Np * Np) {
@@ -142,7 +142,7 @@ int predict_common(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_nois
                                       h->dAt, Np, 1, 0);
         GB2_CUDA(h, cudaEventRecord(h->ev[2], s));
         launches += 2;
-        if (tf32) trsm_rec_tf32(h, s, Mp, 0, ncols, ncols, h->opt_tf32_nb, launches);
+        if (tf32) trsm_rec_tf32(h, s, Mp, 0, ncols, ncols, h->opt_tf32_leaf, launches);
         else trsm_rec(s, h->dA, Np, h->dDinv, h->dAt, Np, Mp, 0, ncols, launches);
         GB2_CUDA(h, cudaEventRecord(h->ev[3], s));
         posterior_reduce_kernel<<<(unsigned)((Mc + 7) / 8), 256, 0, s>>>(h->kp, h->dBtab, h->dFs, h->dCs, Mp, h->dAt, Np, h->dA + N * Np, N, Mc,
@@ -438,7 +438,7 @@ static int build_K(gb2_handle* h, int& launches) {
         h->A_cap = Np;
     }
     if (h->precision == GB2_TF32) {
-        const int64_t pld = (int64_t)h->opt_tf32_nb * TILE;
+        const int64_t pld = (int64_t)h->tf32_nb() * TILE;
         if (h->P_cap < Np * pld) {
             if (h->dPhi) GB2_CUDA(h, cudaFree(h->dPhi));
             if (h->dPlo) GB2_CUDA(h, cudaFree(h->dPlo));
@@ -751,6 +751,11 @@ int gb2_dist_finalize(gb2_handle* h) {
 int gb2_set_option(gb2_handle* h, const char* name, int value) {
     if (!h || !name) return -1;
     if (!strcmp(name, "lookahead")) { h->opt_lookahead = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "tf32_leaf")) {
+        GB2_ARG(h, value >= 1 && value <= 16, "tf32_leaf must be in [1, 16]");
+        h->opt_tf32_leaf = value;
+        return 0;
+    }
     if (!strcmp(name, "p2p")) {   // 1: panel exchange through NVLink peer mappings (default), 0: NCCL broadcast + all-gather
         GB2_ARG(h, !h->p2p_ready || value, "p2p cannot be switched off once the peer mappings are in use");
         h->opt_p2p = value ? 1 : 0;
@@ -758,7 +763,7 @@ int gb2_set_option(gb2_handle* h, const char* name, int value) {
     }
     if (!strcmp(name, "kbuild_v1")) { h->opt_kbuild_v1 = value ? 1 : 0; h->factorized = false; return 0; }   // ablation: scalar-FMA + libm exp K-build
     if (!strcmp(name, "tf32_nb")) {   // panel width of the GB2_TF32 factorisation / leaf width of its solve, in 128-column blocks
-        GB2_ARG(h, value >= 1 && value <= 16, "tf32_nb must be in [1, 16]");
+        GB2_ARG(h, value >= 0 && value <= 16, "tf32_nb must be in [0, 16] (0 = auto)");
         h->opt_tf32_nb = value; h->P_cap = 0; h->factorized = false;
         if (h->dPhi) { cudaFree(h->dPhi); h->dPhi = nullptr; }
         if (h->dPlo) { cudaFree(h->dPlo); h->dPlo = nullptr; }

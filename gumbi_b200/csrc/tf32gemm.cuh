@@ -8,12 +8,13 @@
 // dropped).  Accumulation is fp32 in TMEM over at most TC_MAX_K columns per launch; the epilogue converts to fp64 and
 // subtracts from the fp64 matrix in HBM, so long sums are carried in fp64 across launches.
 //
-// Structure (one CTA per SM, persistent over 128x128 output tiles, 192 threads):
+// Structure (one CTA per SM, persistent over 128 x 128 or 128 x 256 output tiles, 320 threads):
 //   warp 0   : TMA producer   -- cp.async.bulk.tensor.2d of the four operand tiles (A_hi, A_lo, B_hi, B_lo; 128 rows x
 //                                32 fp32 = 128-byte swizzled rows) into a 3-stage shared-memory ring (64 KB / stage)
 //   warp 1   : MMA issuer     -- one elected lane issues 4 k-steps x 3 tcgen05.mma (M=128, N=128, K=8) per stage into one
 //                                of two 128-column TMEM accumulators; tcgen05.commit releases the stage / publishes the tile
-//   warps 2-5: epilogue       -- tcgen05.ld (32 lanes x 32 columns), fp32 -> fp64, C -= acc, release the accumulator
+//   warps 2-9: epilogue       -- tcgen05.ld (32 lanes x 32 columns), transpose through shared memory, fp32 -> fp64, coalesced
+//                                C -= acc with the next chunk's loads already in flight, release the accumulator
 // Synchronisation is mbarrier-only (full/empty per stage, tmem_full/tmem_empty per accumulator).
 #pragma once
 #include <cuda.h>
@@ -27,9 +28,10 @@ constexpr int TM = 128, TN = 128, TK = 32;       // output tile; K columns per s
 // flop (the A tile is staged once for 256 columns): at NB = 1 the kernel is capped by L2 bandwidth at ~50 % tensor-pipe
 // utilisation (ncu, profiles/r01e), which is what a 3xTF32 product with hi+lo operands costs on 128 x 128 tiles.
 constexpr int TILE_BYTES = TM * TK * 4;          // 16 KB per operand tile
-constexpr int THREADS = 192;
+constexpr int EPI_WARPS = 8;                     // two epilogue warps per TMEM lane quadrant (each takes every other 32-column chunk)
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr int EPI_LD = 33;                       // padded row of the per-warp 32 x 32 fp32 transpose buffer (conflict-free both ways)
-constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;   // one buffer per epilogue warp
+constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_LD * 4;   // one buffer per epilogue warp
 template <int NB> struct Cfg {
     static constexpr int STAGES = NB == 1 ? 3 : 2;
     static constexpr int STAGE_BYTES = (2 + 2 * NB) * TILE_BYTES;     // A_hi, A_lo, NB x (B_hi, B_lo)
@@ -161,7 +163,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 4); }
+        for (int b = 0; b < 2; b++) { mbar_init(tfull + b, 1); mbar_init(tempty + b, EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -230,7 +232,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
             }
         }
     } else {
-        // ================= epilogue (warps 2..5) =================
+        // ================= epilogue (warps 2..9) =================
         const int q = warp & 3;  // TMEM lane quadrant this warp may access
         int it = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -243,15 +245,27 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
             tc_fence_after();
             // TMEM hands every thread one ROW (32 consecutive columns); the fp64 read-modify-write of C wants one row spread
             // over the warp (lane = column, 256 contiguous bytes per request).  Transpose through a padded 32 x 32 buffer.
+            // The C traffic of a depth-512 update is as large as its operand traffic, and with one chunk per warp in flight the
+            // kernel was bound by the epilogue's memory-level parallelism (4 warps x 8 KB per SM): 8 warps, and the loads of a
+            // warp's next chunk are issued before the current chunk is transposed and stored (2 x 8 KB per warp in flight).
             float* S = epi + (warp - 2) * 32 * EPI_LD;
+            const int half = (warp - 2) >> 2;                      // which of the two warps of this lane quadrant
             double* cbase = g.C + ((int64_t)(g.rb_first + bi * g.rb_stride) * TM + q * 32) * g.ldc + (int64_t)(g.cblk0 + bj) * TN + lane;
-#pragma unroll 1
-            for (int c0 = 0; c0 < nh * TN; c0 += 32) {
-                // 32 independent 256-byte row requests per warp in flight (32 KB per SM) before anything is consumed
-                double* cp = cbase + c0;
-                double o[32];
+            const int n_chunks = nh * (TN / 32);
+            double o[32], o2[32];
+            if (half < n_chunks) {
 #pragma unroll
-                for (int u = 0; u < 32; u++) o[u] = cp[(int64_t)u * g.ldc];
+                for (int u = 0; u < 32; u++) o[u] = cbase[half * 32 + (int64_t)u * g.ldc];
+            }
+#pragma unroll 1
+            for (int ch = half; ch < n_chunks; ch += 2) {
+                const int c0 = ch * 32;
+                double* cp = cbase + c0;
+                const bool more = ch + 2 < n_chunks;
+                if (more) {
+#pragma unroll
+                    for (int u = 0; u < 32; u++) o2[u] = cp[64 + (int64_t)u * g.ldc];
+                }
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * NB * TN + c0), v);
 #pragma unroll
@@ -260,6 +274,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
 #pragma unroll
                 for (int u = 0; u < 32; u++) cp[(int64_t)u * g.ldc] = o[u] - (double)S[u * EPI_LD + lane];
                 __syncwarp();
+                if (more) {
+#pragma unroll
+                    for (int u = 0; u < 32; u++) o[u] = o2[u];
+                }
             }
             tc_fence_before();
             __syncwarp();

@@ -388,3 +388,23 @@ def test_tf32_full_size_config2(engine_tf32):
     np.testing.assert_allclose(mu[sel], mu0, rtol=RTOL_TF32_GATE, atol=RTOL_TF32_GATE * np.abs(mu0).max())
     np.testing.assert_allclose(var[sel], var0, rtol=RTOL_TF32_GATE, atol=1e-6)
     print("tf32 c2: max rel err mean %.2e var %.2e" % (np.max(np.abs(mu[sel] - mu0)) / np.abs(mu0).max(), np.max(np.abs(var[sel] - var0) / var0)))
+
+
+def test_kbuild_extreme_distances_and_clamp(engine):
+    """Table-driven exp: huge scaled distances underflow to exactly 0 (the oracle's exp does), nothing turns into NaN/Inf;
+    both the strip kernel (simple model) and the generic kernel (with a Linear term) are exercised."""
+    rng = np.random.default_rng(5)
+    for kind in ("ExpQuad", "Matern52", "Matern12"):
+        for linear in (False, True):
+            spec, X, y, Xs = orc.synthetic_problem(260, 3, kind=kind, M_res=6)
+            X = X * np.array([1.0, 40.0, 3000.0])          # r^2 up to ~1e9 after scaling by ls ~ 2..3
+            X[:20] = X[20:40] + 1e-9 * rng.standard_normal((20, 3))   # near-duplicates: r^2 ~ 1e-18 (clip / +1e-12 path)
+            if linear:
+                spec["terms"][0].update(lin_idx=[0], c=[0.1], tau=0.02)
+            engine.set_train(X, y)
+            engine.set_kernel(spec)
+            K = engine.get_K()
+            K0 = orc.train_cov(spec, X)
+            assert np.all(np.isfinite(K))
+            np.testing.assert_allclose(K, K0, rtol=1e-9 if kind == "Matern12" else 5e-12, atol=1e-300)
+            assert np.all(K[K0 == 0.0] == 0.0)   # exact zeros where the reference underflows (ours cuts off at exp(-700) ~ 1e-304)
