@@ -122,9 +122,9 @@ struct gb2_handle {
     bool L_split_valid = false;
 
     // options
-    int opt_tf32_nb = 0;     // GB2_TF32 factor-panel width in 128-column blocks; 0 = auto (8 for N >= 16384, else 4)
+    int opt_tf32_nb = 0;     // GB2_TF32 factor-panel width in 128-column blocks; 0 = auto (8 for N >= 8192, else 4)
     int opt_tf32_leaf = 4;   // GB2_TF32 solve: sub-solves up to this many blocks stay on the fp64 kernels
-    int tf32_nb() const { return opt_tf32_nb > 0 ? opt_tf32_nb : (Np >= 16384 ? 8 : 4); }
+    int tf32_nb() const { return opt_tf32_nb > 0 ? opt_tf32_nb : (Np >= 8192 ? 8 : 4); }
     int opt_kbuild_v1 = 0;
     int opt_lookahead = 1;
 
