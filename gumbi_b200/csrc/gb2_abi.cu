@@ -31,10 +31,11 @@ int set_train_common(gb2_handle* h, const double* X, int64_t N, int32_t D_in, co
     GB2_ARG(h, D_in >= 1 && D_in <= 64, "D_in must be in [1, 64]");
     GB2_CUDA(h, cudaSetDevice(h->device));
     const int64_t Np = round_up(N + 1, TILE);
-    if (h->dX) { GB2_CUDA(h, cudaFree(h->dX)); h->dX = nullptr; }
-    if (h->dy) { GB2_CUDA(h, cudaFree(h->dy)); h->dy = nullptr; }
-    GB2_CUDA(h, cudaMalloc(&h->dX, (size_t)N * D_in * sizeof(double)));
-    GB2_CUDA(h, cudaMalloc(&h->dy, (size_t)N * sizeof(double)));
+    // buffers are re-used across calls and only ever grow: cudaFree / cudaMalloc are device-wide synchronisation points and get
+    // far more expensive once peer mappings exist (the 4-GPU end-to-end arm lost ~250 ms per step with per-call re-allocation)
+    int rc;
+    if ((rc = ensure(h, h->dX, h->X_cap, N * (int64_t)D_in))) return rc;
+    if ((rc = ensure(h, h->dy, h->y_cap, N))) return rc;
     GB2_CUDA(h, cudaMemcpyAsync(h->dX, X, (size_t)N * D_in * sizeof(double), kind, h->s_main));
     GB2_CUDA(h, cudaMemcpyAsync(h->dy, y, (size_t)N * sizeof(double), kind, h->s_main));
     GB2_CUDA(h, cudaStreamSynchronize(h->s_main));
@@ -761,6 +762,7 @@ int gb2_set_option(gb2_handle* h, const char* name, int value) {
         h->opt_p2p = value ? 1 : 0;
         return 0;
     }
+    if (!strcmp(name, "fastdiag")) { h->opt_fastdiag = value ? 1 : 0; return 0; }   // ablation: Cholesky critical-path fast path
     if (!strcmp(name, "kbuild_v1")) { h->opt_kbuild_v1 = value ? 1 : 0; h->factorized = false; return 0; }   // ablation: scalar-FMA + libm exp K-build
     if (!strcmp(name, "tf32_nb")) {   // panel width of the GB2_TF32 factorisation / leaf width of its solve, in 128-column blocks
         GB2_ARG(h, value >= 0 && value <= 16, "tf32_nb must be in [0, 16] (0 = auto)");
