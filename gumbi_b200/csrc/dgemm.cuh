@@ -104,19 +104,23 @@ dgemm_nt_kernel(const double* A, int64_t lda, const double* __restrict__ B, int6
         for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
     const int nk = kdepth / GM_BK;
+    // lower_only == 2: both operands are rows of an upper-triangular matrix (W = L^-T: W[r][k] = 0 for k < r), so the product
+    // of this tile only has terms from k >= max(first row of the A tile, first row of the B tile)
+    const int kt0 = lower_only == 2 ? (int)(((grow > (int64_t)bj * BN) ? grow : (int64_t)bj * BN) / GM_BK) : 0;
 #pragma unroll
     for (int s = 0; s < GM_STAGES - 1; s++) {
-        if (s < nk) load_stage(s, s);
+        if (kt0 + s < nk) load_stage(s, kt0 + s);
         cp_async_commit();
     }
-    for (int kt = 0; kt < nk; kt++) {
+    for (int kt = kt0; kt < nk; kt++) {
         cp_async_wait<GM_STAGES - 2>();
         __syncthreads();
         const int nxt = kt + GM_STAGES - 1;
-        if (nxt < nk) load_stage(nxt % GM_STAGES, nxt);
+        if (nxt < nk) load_stage((nxt - kt0) % GM_STAGES, nxt);
         cp_async_commit();
-        const double* cA = sA + (kt % GM_STAGES) * BM * GM_LDS + (wm * 32 + g) * GM_LDS + t;
-        const double* cB = sB + (kt % GM_STAGES) * BN * GM_LDS + (wn * 32 + g) * GM_LDS + t;
+        const int st = (kt - kt0) % GM_STAGES;
+        const double* cA = sA + st * BM * GM_LDS + (wm * 32 + g) * GM_LDS + t;
+        const double* cB = sB + st * BN * GM_LDS + (wn * 32 + g) * GM_LDS + t;
 #pragma unroll
         for (int kk = 0; kk < GM_BK / 4; kk++) {
             double a[4], b[4];

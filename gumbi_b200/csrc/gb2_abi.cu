@@ -559,10 +559,10 @@ int gb2_mll_grad(gb2_handle* h, double* mll_out, double* grad_out) {
     int launches = 0;
     // 1. W = L^-T (rows), alpha from the augmented column
     set_identity_kernel<<<(unsigned)((Np * (Np / 2) + 255) / 256), 256, 0, s>>>(h->dW, Np, Np);
-    trsm_rec(s, h->dA, Np, h->dDinv, h->dW, Np, Np, 0, nb, launches);
+    trsm_rec(s, h->dA, Np, h->dDinv, h->dW, Np, Np, 0, nb, launches, /*tri=*/true);
     extract_alpha_kernel<<<(unsigned)((Np + 255) / 256), 256, 0, s>>>(h->dW, Np, N, Np, h->dAlpha);
     // 2. S = W W^T = K^-1 (lower tiles)
-    dgemm_nt_launch<128, 64, GM_SET>(s, h->dW, Np, h->dW, Np, h->dS, Np, Np, Np, (int)Np, 1, 0, 0);
+    dgemm_nt_launch<128, 64, GM_SET>(s, h->dW, Np, h->dW, Np, h->dS, Np, Np, Np, (int)Np, /*lower, triangular k-range*/ 2, 0, 0);
     // 3. one pass over G = alpha alpha^T - S
     GB2_CUDA(h, cudaMemsetAsync(h->dGrad, 0, GR_LEN * sizeof(double), s));
     dim3 grid((unsigned)(Np / KB_T), (unsigned)(Np / KB_T));

@@ -230,9 +230,8 @@ constexpr int KB2_TS = 68;   // shared row stride (doubles): 68 = 4 mod 16 makes
 
 __device__ double g_exp2_tab[64];   // 2^(j/64), filled by the host at gb2_create
 
-// exp(x) for x <= ~0 (clamped at -708, where exp is 3e-308).  |relative error| ~ 2e-16.
+// exp(x) for x <= ~0; exactly 0 below x = -700 (exp < 1e-304).  |relative error| ~ 2e-16.
 __device__ __forceinline__ double exp_tab(double x, const double* __restrict__ tab) {
-    x = fmax(x, -708.0);
     const double t = fma(x, 92.33248261689366, 6755399441055744.0);   // 64/ln2, 1.5*2^52: low word of t = round(64 x / ln 2)
     const int n = __double2loint(t);
     const double kf = t - 6755399441055744.0;
@@ -245,7 +244,8 @@ __device__ __forceinline__ double exp_tab(double x, const double* __restrict__ t
     const double p = fma(q, r2, r);                                     // e^r - 1, |r| <= ln2/128
     const double T = tab[n & 63];
     const double res = fma(T, p, T);
-    return __hiloint2double(__double2hiint(res) + ((n >> 6) << 20), __double2loint(res));
+    const double sc = __hiloint2double(__double2hiint(res) + ((n >> 6) << 20), __double2loint(res));
+    return x < -700.0 ? 0.0 : sc;
 }
 
 // value of the stationary kernel from x = -r^2/2

@@ -4,25 +4,30 @@
 // K-contiguous for dgemm.cuh.  The solve  At <- At L^-T  is a recursive blocked TRSM: leaves multiply by the
 // inverted 128x128 diagonal blocks (computed during the factorisation), everything else is one large DMMA GEMM.
 #pragma once
+#include <algorithm>
 #include "cholesky.cuh"
 #include "kbuild.cuh"
 
 namespace gb2 {
 
+// tri: the right-hand side is the identity (At starts as I, rows = columns), whose solution W = L^-T is upper triangular as
+// rows: row block m is zero left of column block m, so every step only touches the rows above its last column block.
 inline void trsm_rec(cudaStream_t s, const double* L, int64_t ld, const double* Dinv, double* At, int64_t ldt,
-                     int64_t Mp, int c0, int c1, int& launches) {
+                     int64_t Mp, int c0, int c1, int& launches, bool tri = false) {
     if (c1 - c0 == 1) {
         double* X = At + (int64_t)c0 * TILE;
-        dgemm_nt_launch<64, 128, GM_SET>(s, X, ldt, Dinv + (int64_t)c0 * TILE * TILE, TILE, X, ldt, Mp, TILE, TILE, 0, 0, 0);
+        const int64_t rows = tri ? std::min<int64_t>(Mp, (int64_t)(c0 + 1) * TILE) : Mp;
+        dgemm_nt_launch<64, 128, GM_SET>(s, X, ldt, Dinv + (int64_t)c0 * TILE * TILE, TILE, X, ldt, rows, TILE, TILE, 0, 0, 0);
         launches++;
         return;
     }
     const int mid = c0 + (c1 - c0 + 1) / 2;
-    trsm_rec(s, L, ld, Dinv, At, ldt, Mp, c0, mid, launches);
+    trsm_rec(s, L, ld, Dinv, At, ldt, Mp, c0, mid, launches, tri);
+    const int64_t rows = tri ? std::min<int64_t>(Mp, (int64_t)mid * TILE) : Mp;
     dgemm_nt_launch<128, 64, GM_SUB>(s, At + (int64_t)c0 * TILE, ldt, L + (int64_t)mid * TILE * ld + (int64_t)c0 * TILE, ld,
-                                     At + (int64_t)mid * TILE, ldt, Mp, (int64_t)(c1 - mid) * TILE, (mid - c0) * TILE, 0, 0, 0);
+                                     At + (int64_t)mid * TILE, ldt, rows, (int64_t)(c1 - mid) * TILE, (mid - c0) * TILE, 0, 0, 0);
     launches++;
-    trsm_rec(s, L, ld, Dinv, At, ldt, Mp, mid, c1, launches);
+    trsm_rec(s, L, ld, Dinv, At, ldt, Mp, mid, c1, launches, tri);
 }
 
 // GB2_TF32 variant: sub-solves of up to `leaf` column blocks stay in fp64 (DMMA); every larger off-diagonal product of the
