@@ -410,3 +410,59 @@ def test_kbuild_extreme_distances_and_clamp(engine):
             # rounding noise in r^2 -- of either implementation; the entrywise gate is loosened accordingly for this case only
             np.testing.assert_allclose(K, K0, rtol=1e-4 if kind == "Matern12" else 2e-7, atol=1e-290)
             assert np.all(K[K0 == 0.0] == 0.0)   # exact zeros where the reference underflows (ours cuts off at exp(-700) ~ 1e-304)
+
+
+def _random_model(seed):
+    """A random admissible model: 1-3 additive terms, any stationary kernel, optional Linear, 0-2 Coregion factors per term
+    (one of them shared by all terms like the output Coregion, GP.py:724-727), optional heteroskedastic noise Coregion."""
+    rng = np.random.default_rng(seed)
+    kinds = ["ExpQuad", "Matern52", "Matern32", "Matern12", "Exponential"]
+    n = int(rng.integers(40, 420))
+    d = int(rng.integers(1, 7))
+    n_cat = int(rng.integers(0, 3))
+    P = [int(rng.integers(2, 5)) for _ in range(n_cat)]
+    Xc = rng.standard_normal((n, d))
+    cats = [rng.integers(0, p, size=n).astype(float) for p in P]
+    X = np.column_stack([Xc] + cats) if n_cat else Xc
+    y = rng.standard_normal(n)
+    M = int(rng.integers(1, 150))
+    Xs = np.column_stack([rng.standard_normal((M, d))] + [rng.integers(0, p, size=M).astype(float) for p in P]) if n_cat else rng.standard_normal((M, d))
+    shared = {"col": d + n_cat - 1, "W": rng.standard_normal((P[-1], 2)).tolist(), "kappa": rng.uniform(0.5, 1.5, P[-1]).tolist()} if n_cat else None
+    terms = []
+    for t in range(int(rng.integers(1, 4))):
+        nd = int(rng.integers(1, d + 1))
+        idx = sorted(rng.choice(d, nd, replace=False).tolist())
+        term = {"kind": kinds[int(rng.integers(0, 5))], "cont_idx": idx, "ls": rng.uniform(0.6, 2.5, nd).tolist(),
+                "eta": float(rng.uniform(0.5, 1.5)), "lin_idx": [], "c": [], "tau": 0.0, "coreg": []}
+        if rng.random() < 0.5:
+            nl = int(rng.integers(1, nd + 1))
+            term.update(lin_idx=idx[:nl], c=rng.normal(0, 0.5, nl).tolist(), tau=float(rng.uniform(0.01, 0.3)))
+        if n_cat == 2 and rng.random() < 0.6:
+            term["coreg"].append({"col": d, "W": rng.standard_normal((P[0], 2)).tolist(), "kappa": rng.uniform(0.5, 1.5, P[0]).tolist()})
+        if shared is not None:
+            term["coreg"].append(shared)
+        terms.append(term)
+    spec = {"terms": terms, "sigma": float(rng.uniform(0.05, 0.4)), "noise_coreg": None, "jitter": 1e-6}
+    if shared is not None and rng.random() < 0.7:
+        spec["noise_coreg"] = {"col": shared["col"], "W": (0.3 * rng.standard_normal((P[-1], 2))).tolist(), "kappa": rng.uniform(0.5, 2.0, P[-1]).tolist()}
+    return spec, np.ascontiguousarray(X), y, np.ascontiguousarray(Xs)
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_models_against_oracle(engine, seed):
+    spec, X, y, Xs = _random_model(1000 + seed)
+    engine.set_train(X, y)
+    engine.set_kernel(spec)
+    K = engine.get_K()
+    np.testing.assert_allclose(K, orc.train_cov(spec, X), rtol=1e-9, atol=1e-13)
+    engine.factorize()
+    L0, v0 = orc.factorize(spec, X, y)
+    for noise in (True, False):
+        mu, var = engine.predict(Xs, noise)
+        mu0, var0 = orc.conditional(spec, X, L0, v0, Xs, noise)
+        np.testing.assert_allclose(mu, mu0, rtol=1e-7, atol=1e-9)
+        np.testing.assert_allclose(var, var0, rtol=1e-7, atol=1e-9)
+    val, g = engine.mll_grad(spec)
+    val0, g0 = orc.mll_grad(spec, X, y)
+    np.testing.assert_allclose(val, val0, rtol=1e-10)
+    _tree_close(g, g0, rtol=2e-6, atol=1e-6 * max(1.0, abs(g0["sigma"])))

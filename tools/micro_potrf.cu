@@ -17,7 +17,7 @@ int main() {
     for (int rep = 0; rep < 3; rep++) {
         cudaMemcpy(dA, A.data(), n * n * 8, cudaMemcpyHostToDevice);
         cudaMemset(dClk, 0, 64 * 8);
-        potrf_diag_kernel<<<1, PD_THREADS, PD_SMEM>>>(dA, n, 0, n, dD, dInfo, dClk);
+        potrf_diag_kernel<<<1, PD_THREADS, PD_SMEM>>>(dA, n, 0, n, dD, dInfo, nullptr, PushArgs{}, dClk);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
         cudaMemcpy(clk, dClk, 64 * 8, cudaMemcpyDeviceToHost);
