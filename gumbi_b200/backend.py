@@ -270,7 +270,7 @@ class B200Backend:
             raise TypeError(f"unsupported predict arguments for the B200 backend: {sorted(kwargs)}")
         self._ensure_factorized()
         points_array = np.atleast_2d(np.asarray(points_array, dtype=np.float64))
-        if getattr(self.engine, "world", 1) > 1:
+        if getattr(self.engine, "world", 1) > 1 and not getattr(self.engine, "shard_storage", False):
             # every rank holds the factor: each serves a contiguous slice of the points, slices are gathered on all ranks
             from . import dist as gdist
 

@@ -348,8 +348,10 @@ pull_diag_kernel(const unsigned* flag, unsigned expected, const double* __restri
         const double2 l = reinterpret_cast<const double2*>(ownerLpack)[e];
         reinterpret_cast<double2*>(Dinv)[e] = d;
         reinterpret_cast<double2*>(Lpack)[e] = l;
-        const int r = (e * 2) / TILE, c = (e * 2) % TILE;
-        *reinterpret_cast<double2*>(Adiag + (int64_t)r * ld + c) = l;
+        if (Adiag) {   // replicated storage: the factor copy of every rank also gets the diagonal block
+            const int r = (e * 2) / TILE, c = (e * 2) % TILE;
+            *reinterpret_cast<double2*>(Adiag + (int64_t)r * ld + c) = l;
+        }
     }
 }
 
@@ -625,6 +627,136 @@ inline int factor_steps(gb2_handle* h, int k0, int k1, int col_limit) {
     return launches;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Storage-sharded factorisation (N beyond one GPU's HBM): rank r keeps only the row blocks i with i % G == r, contiguously.
+// Same block steps as factor_steps; what changes is where the panel lives.  Column block k of L is needed by everybody as
+// the B operand of the trailing update, but only for the duration of step k: it is pushed (by the fused panel-solve kernel,
+// over NVLink, and into the sender's own copy too) into slot k % ring_slots of a ring of (Np x 128) panel buffers in GLOBAL row
+// order.  No credit protocol is needed: a rank can only push panel k+2 after its own trailing update k, and panel k+3 cannot
+// start before every rank has pushed panel k+2, so at most panels k, k+1, k+2 are live while a rank still reads panel k.
+// fp64 kernels only (the tf32 panels are not wired into this mode yet).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void mll_terms_compact_kernel(const double* __restrict__ A, int64_t ld, int64_t n, int G, int me, double* __restrict__ part) {
+    __shared__ double s0[32], s1[32];
+    double a = 0.0, b = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x)
+        if ((i / TILE) % G == me) a += log(A[(((i / TILE) - me) / G * TILE + i % TILE) * ld + i]);
+    if ((n / TILE) % G == me) {
+        const double* vrow = A + (((n / TILE) - me) / G * TILE + n % TILE) * ld;
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) b = fma(vrow[i], vrow[i], b);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s0[threadIdx.x >> 5] = a; s1[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a = b = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { a += s0[w]; b += s1[w]; }
+        part[0] = a; part[1] = b;
+    }
+}
+__global__ void sum_pairs_kernel(const double* __restrict__ all, int G, double* __restrict__ out) {
+    if (threadIdx.x < 2) {
+        double s = 0.0;
+        for (int r = 0; r < G; r++) s += all[2 * r + threadIdx.x];
+        out[threadIdx.x] = s;
+    }
+}
+
+inline int factor_steps_compact(gb2_handle* h) {
+    const int64_t Np = h->Np, ld = h->Np;
+    const int nb = (int)(Np / TILE);
+    const int G = h->world, me = h->rank;
+    double* A = h->dA;   // (nloc * 128, Np): local block li = global block li * G + me
+    int launches = 0;
+    cudaStream_t sm = h->s_main, sp = h->s_panel;
+    {   // barrier + panel stream start
+        PushArgs peers{};
+        const size_t slot = (size_t)4 * h->p2p_nbmax;
+        for (int r = 0, q = 0; r < G; r++)
+            if (r != me) peers.peerFlag[q++] = h->peerFlags[r] + slot;
+        peers.n_peers = G - 1;
+        h->p2p_epoch++;
+        p2p_barrier_kernel<<<1, 32, 0, sm>>>(peers, h->dFlags + slot, (unsigned)(h->p2p_epoch * (G - 1)));
+        launches++;
+        cudaEvent_t e = pool_event(h, 3 * nb + 2);
+        cudaEventRecord(e, sm);
+        cudaStreamWaitEvent(sp, e, 0);
+    }
+    auto first_owned_after = [&](int k, int r) { return k + 1 + (((r - (k + 1)) % G) + G) % G; };
+    auto count_from = [&](int first) { return first < nb ? (nb - first + G - 1) / G : 0; };
+    for (int k = 0; k < nb; k++) {
+        const int64_t g0 = (int64_t)k * TILE;
+        const int64_t below = Np - g0 - TILE;
+        const int owner = k % G;
+        double* Dk = h->dDinv + (int64_t)k * TILE * TILE;
+        double* Lk = h->dLpack + (int64_t)k * TILE * TILE;
+        const size_t fl = ((size_t)h->p2p_parity * 2) * h->p2p_nbmax + k;
+        const int64_t ring_off = (int64_t)(k % h->ring_slots) * h->ring_slot_elems;
+        if (owner == me) {
+            PushArgs sig{};
+            for (int r = 0, q = 0; r < G; r++)
+                if (r != me) sig.peerFlag[q++] = h->peerFlags[r] + fl;
+            sig.n_peers = G - 1;
+            const int64_t li = (k - me) / G;
+            // the kernel addresses the block as A + g0*ld + g0: shift the base so that this lands on local row block li
+            potrf_diag_kernel<<<1, PD_THREADS, PD_SMEM, sp>>>(A + (li * TILE - g0) * ld, ld, g0, h->N, Dk, h->dInfo, Lk, sig);
+        } else {
+            pull_diag_kernel<<<32, 256, 0, sp>>>(h->dFlags + fl, 1u, h->peerDinv[owner] + (int64_t)k * TILE * TILE,
+                                                 h->peerLpack[owner] + (int64_t)k * TILE * TILE, Dk, Lk, nullptr, ld);
+        }
+        launches++;
+        if (below <= 0) break;
+        const int f1 = first_owned_after(k, me), c1 = count_from(f1);
+        const int l1 = (f1 - me) / G;
+        double* colk = A + g0;                        // column block k of the local rows
+        const double* Pk = h->dRing + ring_off;       // panel k, global row order, ld = 128
+        if (c1 > 0) {
+            PushArgs push{};
+            int q = 0;
+            for (int r = 0; r < G; r++) {
+                push.peerC[q] = h->peerRing[r] + ring_off;                                   // includes this rank's own ring
+                push.peerFlag[q] = r == me ? nullptr : h->peerFlags[r] + fl + h->p2p_nbmax;
+                q++;
+            }
+            push.n_peers = G;
+            push.ld = TILE;
+            dgemm_nt_launch<64, 128, GM_SET_PUSH>(sp, colk, ld, Dk, TILE, colk, ld, (int64_t)c1 * TILE, TILE, TILE, 0, 0, 0, f1, G, &push, l1);
+            launches++;
+        }
+        const unsigned expected = (unsigned)(2 * ((nb - (k + 1)) - c1));
+        if (expected > 0) {
+            wait_counter_kernel<<<1, 32, 0, sp>>>(h->dFlags + fl + h->p2p_nbmax, expected);
+            launches++;
+        }
+        cudaEvent_t e0 = pool_event(h, 2 * k);
+        cudaEventRecord(e0, sp);
+        cudaStreamWaitEvent(sm, e0, 0);
+        if (c1 > 0) {   // next column first
+            dgemm_nt_launch<128, 64, GM_SUB>(sm, colk, ld, Pk + (g0 + TILE) * TILE, TILE, A + g0 + TILE, ld, (int64_t)c1 * TILE, TILE, TILE, 1, 0,
+                                             g0 + TILE, f1, G, nullptr, l1);
+            launches++;
+        }
+        cudaEvent_t e1 = pool_event(h, 2 * k + 1);
+        cudaEventRecord(e1, sm);
+        cudaStreamWaitEvent(sp, e1, 0);
+        if (below > TILE) {
+            const int f2 = first_owned_after(k + 1, me), c2 = count_from(f2);
+            if (c2 > 0) {
+                dgemm_nt_launch<128, 64, GM_SUB>(sm, colk, ld, Pk + (g0 + 2 * TILE) * TILE, TILE, A + g0 + 2 * TILE, ld, (int64_t)c2 * TILE,
+                                                 below - TILE, TILE, 1, 0, g0 + 2 * TILE, f2, G, nullptr, (f2 - me) / G);
+                launches++;
+            }
+        }
+    }
+    cudaEvent_t e = pool_event(h, 3 * nb + 3);
+    cudaEventRecord(e, sp);
+    cudaStreamWaitEvent(sm, e, 0);
+    return launches;
+}
+
 // Enqueue the whole factorisation of h->dA (Np x Np).  Returns the number of kernel launches enqueued.
 //
 // Multi-GPU (h->world > 1): 128-row blocks are owned block-cyclically (block i -> rank i % world).  Every rank
@@ -645,6 +777,21 @@ inline int cholesky_enqueue(gb2_handle* h) {
     const int nb = (int)(Np / TILE);
     int launches = 0;
     const int pw = h->tf32_nb();
+    if (h->compact) {
+        launches += factor_steps_compact(h);
+        // log-determinant / |v|^2: per-rank partial sums over the owned rows, all-gathered and summed; v broadcast to everybody
+        const int G = h->world, me = h->rank;
+        double* part = h->dScal + 2;                        // [2] mine, gathered into dPart
+        mll_terms_compact_kernel<<<1, 1024, 0, h->s_main>>>(h->dA, ld, h->N, G, me, part);
+        h->nccl->AllGather(part, h->dPart, 2, NCCL_FLOAT64, h->comm, h->s_main);
+        sum_pairs_kernel<<<1, 32, 0, h->s_main>>>(h->dPart, G, h->dScal);
+        const int vb = (int)(h->N / TILE), vowner = vb % G;
+        if (vowner == me)
+            cudaMemcpyAsync(h->dV, h->dA + (((int64_t)(vb - me) / G) * TILE + h->N % TILE) * ld, (size_t)Np * sizeof(double),
+                            cudaMemcpyDeviceToDevice, h->s_main);
+        h->nccl->Broadcast(h->dV, h->dV, (size_t)Np, NCCL_FLOAT64, vowner, h->comm, h->s_main);
+        return launches + 4;
+    }
     if (h->precision == GB2_TF32 && nb > pw) {
         cudaStream_t sm = h->s_main;
         const int G = h->world, me = h->rank;

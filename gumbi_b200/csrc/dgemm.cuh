@@ -40,11 +40,12 @@ enum { GM_SUB = 0, GM_SET = 1, GM_SET_PUSH = 2 };
 // GM_SET_PUSH (multi-GPU panel solve fused with its exchange): every output tile is also stored, at the same offset, into the
 // factor buffers of the peer GPUs (NVLink peer mappings obtained with cudaIpcOpenMemHandle), and each CTA then bumps a
 // counter in every peer's memory so that the peer knows when the whole panel has landed (fence.sys + red.release.sys).
-constexpr int GB2_MAX_PEERS = 7;
+constexpr int GB2_MAX_PEERS = 8;           // push targets: up to 7 peers + (storage-sharded mode) this GPU's own panel ring
 struct PushArgs {
-    double* peerC[GB2_MAX_PEERS];        // peer's C base (same layout/offset as the local C argument)
-    unsigned* peerFlag[GB2_MAX_PEERS];   // counter to bump in the peer's memory
+    double* peerC[GB2_MAX_PEERS];        // target base: element (global row r, column c of the launch) lives at peerC + r * ld + c
+    unsigned* peerFlag[GB2_MAX_PEERS];   // counter to bump in the target's memory (nullptr: no signal, e.g. the local ring)
     int n_peers;
+    int64_t ld;                          // row stride of the targets (0: same as the local C)
 };
 
 template <int BM, int BN>
@@ -62,12 +63,16 @@ constexpr size_t dgemm_smem_bytes() { return (size_t)GM_STAGES * (BM + BN) * GM_
 template <int BM, int BN, int MODE>
 __global__ void __launch_bounds__(GM_THREADS, 2)
 dgemm_nt_kernel(const double* A, int64_t lda, const double* __restrict__ B, int64_t ldb, double* C, int64_t ldc,
-                int kdepth, int lower_only, int64_t row_off, int64_t col_off, int rb_first, int rb_stride, PushArgs push) {
+                int kdepth, int lower_only, int64_t row_off, int64_t col_off, int rb_first, int rb_stride, PushArgs push,
+                int rb_local_first) {
     static_assert((BM / 32) * (BN / 32) == GM_THREADS / 32, "8 warps of 32x32");
     static_assert(TILE % BM == 0, "row tiles must not straddle 128-row blocks");
     const int bi = blockIdx.x, bj = blockIdx.y;
     constexpr int TPB = TILE / BM;
     const int64_t grow = ((int64_t)rb_first + (int64_t)(bi / TPB) * rb_stride) * TILE + (int64_t)(bi % TPB) * BM;
+    // storage-sharded mode: the rows this rank owns are stored contiguously (local block rb_local_first + bi / TPB); `grow` stays
+    // the global row (triangle predicate, push targets), `lrow` addresses A and C
+    const int64_t lrow = rb_local_first >= 0 ? ((int64_t)rb_local_first + (int64_t)(bi / TPB)) * TILE + (int64_t)(bi % TPB) * BM : grow;
     if (lower_only && col_off + (int64_t)bj * BN > row_off + grow + (BM - 1)) return;
 
     extern __shared__ __align__(16) unsigned char gm_smem[];
@@ -78,7 +83,7 @@ dgemm_nt_kernel(const double* A, int64_t lda, const double* __restrict__ B, int6
     const int wm = warp % (BM / 32), wn = warp / (BM / 32);
     const int g = lane >> 2, t = lane & 3;
 
-    const double* Ag = A + grow * lda;
+    const double* Ag = A + lrow * lda;
     const double* Bg = B + (int64_t)bj * BN * ldb;
 
     auto load_stage = [&](int stage, int kt) {
@@ -136,7 +141,7 @@ dgemm_nt_kernel(const double* A, int64_t lda, const double* __restrict__ B, int6
     }
     cp_async_wait<0>();
 
-    double* Cg = C + (grow + wm * 32 + g) * ldc + (int64_t)bj * BN + wn * 32 + 2 * t;
+    double* Cg = C + (lrow + wm * 32 + g) * ldc + (int64_t)bj * BN + wn * 32 + 2 * t;
 #pragma unroll
     for (int mi = 0; mi < 4; mi++)
 #pragma unroll
@@ -152,19 +157,21 @@ dgemm_nt_kernel(const double* A, int64_t lda, const double* __restrict__ B, int6
             }
         }
     if (MODE == GM_SET_PUSH) {
-        const int64_t off = (grow + wm * 32 + g) * ldc + (int64_t)bj * BN + wn * 32 + 2 * t;
+        const int64_t pld = push.ld ? push.ld : ldc;
+        const int64_t off = (grow + wm * 32 + g) * pld + (int64_t)bj * BN + wn * 32 + 2 * t;
         for (int pr = 0; pr < push.n_peers; pr++) {
             double* Pg = push.peerC[pr] + off;
 #pragma unroll
             for (int mi = 0; mi < 4; mi++)
 #pragma unroll
                 for (int ni = 0; ni < 4; ni++)
-                    *reinterpret_cast<double2*>(Pg + (int64_t)mi * 8 * ldc + ni * 8) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+                    *reinterpret_cast<double2*>(Pg + (int64_t)mi * 8 * pld + ni * 8) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
         }
         __threadfence_system();          // this thread's peer stores are performed system-wide ...
         __syncthreads();                 // ... for every thread of the CTA, before the CTA announces its tile
         if (tid == 0)
-            for (int pr = 0; pr < push.n_peers; pr++) atomicAdd_system(push.peerFlag[pr], 1u);
+            for (int pr = 0; pr < push.n_peers; pr++)
+                if (push.peerFlag[pr]) atomicAdd_system(push.peerFlag[pr], 1u);
     }
 }
 
@@ -178,13 +185,15 @@ inline cudaError_t dgemm_nt_configure() {
 template <int BM, int BN, int MODE>
 inline void dgemm_nt_launch(cudaStream_t s, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                             int64_t ldc, int64_t rows, int64_t cols, int kdepth, int lower_only, int64_t row_off,
-                            int64_t col_off, int rb_first = 0, int rb_stride = 1, const PushArgs* push = nullptr) {
+                            int64_t col_off, int rb_first = 0, int rb_stride = 1, const PushArgs* push = nullptr,
+                            int rb_local_first = -1) {
     if (rows <= 0 || cols <= 0 || kdepth <= 0) return;
     dim3 grid((unsigned)(rows / BM), (unsigned)(cols / BN));
     PushArgs pa{};
     if (push) pa = *push;
     dgemm_nt_kernel<BM, BN, MODE><<<grid, GM_THREADS, dgemm_smem_bytes<BM, BN>(), s>>>(A, lda, B, ldb, C, ldc, kdepth,
-                                                                                      lower_only, row_off, col_off, rb_first, rb_stride, pa);
+                                                                                      lower_only, row_off, col_off, rb_first, rb_stride, pa,
+                                                                                      rb_local_first);
 }
 
 }  // namespace gb2

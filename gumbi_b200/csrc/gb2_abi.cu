@@ -70,12 +70,117 @@ double ms_between(cudaEvent_t a, cudaEvent_t b) {
     return (double)ms;
 }
 
+// Storage-sharded prediction (see predict.cuh).  Collective: every rank calls it with the same points.
+int predict_compact(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_noise, double* mean, double* var, bool dev) {
+    const int64_t Np = h->Np, N = h->N;
+    const int G = h->world, me = h->rank;
+    const int nb = (int)(Np / TILE);
+    const int ncols = (int)((N + TILE - 1) / TILE);              // column blocks that carry training points
+    const int64_t chunk = std::min<int64_t>(16384, round_up(M, TILE));   // ring slots hold up to 16384 x 128
+    const int64_t ldt = h->nloc * TILE;                            // local columns of At
+    cudaStream_t s = h->s_main;
+    int rc;
+    if ((rc = ensure(h, h->dAt, h->At_cap, chunk * ldt))) return rc;
+    if ((rc = ensure(h, h->dFs, h->Fs_cap, (int64_t)std::max(1, h->kp.n_feat) * chunk))) return rc;
+    if ((rc = ensure(h, h->dCs, h->Cs_cap, (int64_t)std::max(1, h->kp.n_cat) * chunk))) return rc;
+    const double* dXs_all = Xs;
+    double* dmean_all = mean; double* dvar_all = var;
+    if (!dev) {
+        if ((rc = ensure(h, h->dXs, h->Xs_cap, M * h->D_in))) return rc;
+        int64_t oc = h->out_cap;
+        if ((rc = ensure(h, h->dMean, oc, M))) return rc;
+        if ((rc = ensure(h, h->dVar, h->out_cap, M))) return rc;
+        GB2_CUDA(h, cudaMemcpyAsync(h->dXs, Xs, (size_t)M * h->D_in * sizeof(double), cudaMemcpyHostToDevice, s));
+        dXs_all = h->dXs; dmean_all = h->dMean; dvar_all = h->dVar;
+    }
+    auto first_owned_after = [&](int k, int r) { return k + 1 + (((r - (k + 1)) % G) + G) % G; };
+    auto count_from = [&](int first) { return first < nb ? (nb - first + G - 1) / G : 0; };
+    int launches = 0;
+    double t_ks = 0, t_solve = 0, t_red = 0;
+    GB2_CUDA(h, cudaMemsetAsync(h->dInfo + 1, 0, sizeof(int), s));
+    for (int64_t m0 = 0; m0 < M; m0 += chunk) {
+        const int64_t Mc = std::min(chunk, M - m0);
+        const int64_t Mp = round_up(Mc, TILE);
+        GB2_CUDA(h, cudaEventRecord(h->ev[0], s));
+        prep_features<<<(unsigned)((Mp + 255) / 256), 256, 0, s>>>(dXs_all + m0 * h->D_in, Mc, Mp, h->pp, h->dFs, h->dCs, h->dInfo + 1);
+        dim3 grid((unsigned)(Np / KB_T), (unsigned)(Mp / KB_T));
+        kbuild_dmma_launch<false>(s, grid, kbuild_dmma_smem_bytes(h->kp), h->kp, h->dBtab, h->dFs, h->dCs, Mp, Mc, h->dF, h->dC, Np, N, nullptr,
+                                  h->dAt, ldt, G, me, 1);
+        GB2_CUDA(h, cudaEventRecord(h->ev[1], s));
+        launches += 2;
+        // Step counters of this chunk: two buffers behind the factorisation's counters; the one used now was cleared one chunk
+        // ago, the other one (used by the previous chunk) is cleared for the next.  No barrier is needed: every chunk -- and the
+        // factorisation -- ends with a collective that a rank only enters after its last push and its last ring read.
+        h->x_parity ^= 1;
+        unsigned* xbase = h->dFlags + (size_t)4 * h->p2p_nbmax + 4;
+        const size_t xoff = (size_t)h->x_parity * h->p2p_nbmax;
+        unsigned* cnt = xbase + xoff;                                                    // [j] = solved panel j has landed
+        GB2_CUDA(h, cudaMemsetAsync(xbase + (size_t)(h->x_parity ^ 1) * h->p2p_nbmax, 0, (size_t)h->p2p_nbmax * sizeof(unsigned), s));
+        for (int j = 0; j < ncols; j++) {
+            const int owner = j % G;
+            const int64_t ring_off = (int64_t)(j % h->ring_slots) * h->ring_slot_elems;
+            double* Xj = h->dRing + ring_off;                                            // (Mp x 128), ld 128
+            if (owner == me) {
+                const int64_t lj = (j - me) / G;
+                double* X = h->dAt + lj * TILE;
+                PushArgs push{};
+                for (int r = 0; r < G; r++) {
+                    push.peerC[r] = h->peerRing[r] + ring_off;
+                    push.peerFlag[r] = r == me ? nullptr : h->peerFlags[r] + (size_t)4 * h->p2p_nbmax + 4 + xoff + j;
+                }
+                push.n_peers = G;
+                push.ld = TILE;
+                dgemm_nt_launch<64, 128, GM_SET_PUSH>(s, X, ldt, h->dDinv + (int64_t)j * TILE * TILE, TILE, X, ldt, Mp, TILE, TILE, 0, 0, 0, 0, 1,
+                                                      &push, -1);
+            } else {
+                wait_counter_kernel<<<1, 32, 0, s>>>(cnt + j, (unsigned)(Mp / 64));
+            }
+            launches++;
+            const int f = first_owned_after(j, me), c = count_from(f);
+            if (c > 0) {
+                const int64_t lf = (f - me) / G;
+                dgemm_nt_launch<128, 64, GM_SUB>(s, Xj, TILE, h->dA + lf * TILE * Np + (int64_t)j * TILE, Np, h->dAt + lf * TILE, ldt, Mp,
+                                                 (int64_t)c * TILE, TILE, 0, 0, 0);
+                launches++;
+            }
+        }
+        GB2_CUDA(h, cudaEventRecord(h->ev[2], s));
+        // partial reduction over the owned columns, all-gather, final
+        const int64_t pstride = Mp;
+        double* mine = h->dPart;                                   // [2 * Mp] mine, then [G][2 * Mp] gathered
+        double* all = h->dPart + 2 * pstride;
+        posterior_partial_kernel<<<(unsigned)((Mc + 7) / 8), 256, 0, s>>>(h->dAt, ldt, h->dV, N, Mc, ldt, G, me, mine, pstride);
+        const int nrc = h->nccl->AllGather(mine, all, (size_t)2 * pstride, NCCL_FLOAT64, h->comm, s);
+        if (nrc != 0) { h->err = std::string("ncclAllGather: ") + h->nccl->GetErrorString(nrc); return -200 - nrc; }
+        posterior_final_kernel<<<(unsigned)((Mc + 255) / 256), 256, 0, s>>>(h->kp, h->dBtab, h->dFs, h->dCs, Mp, all, G, pstride, Mc, pred_noise,
+                                                                           dmean_all + m0, dvar_all + m0);
+        launches += 3;
+        GB2_CUDA(h, cudaEventRecord(h->ev[3], s));
+        GB2_CUDA(h, cudaGetLastError());
+        GB2_CUDA(h, cudaStreamSynchronize(s));
+        t_ks += ms_between(h->ev[0], h->ev[1]);
+        t_solve += ms_between(h->ev[1], h->ev[2]);
+        t_red += ms_between(h->ev[2], h->ev[3]);
+    }
+    if (!dev) {
+        GB2_CUDA(h, cudaMemcpyAsync(mean, h->dMean, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, s));
+        GB2_CUDA(h, cudaMemcpyAsync(var, h->dVar, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    int bad = 0;
+    GB2_CUDA(h, cudaMemcpyAsync(&bad, h->dInfo + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
+    GB2_CUDA(h, cudaStreamSynchronize(s));
+    h->timings[3] = t_ks; h->timings[4] = t_solve; h->timings[5] = t_red; h->timings[7] = launches;
+    GB2_ARG(h, bad == 0, "a Coregion column of Xs holds a level index outside [0, P)");
+    return 0;
+}
+
 int predict_common(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_noise, double* mean, double* var, bool dev) {
     GB2_ARG(h, h->factorized, "gb2_predict called before a successful gb2_factorize");
     GB2_ARG(h, Xs && mean && var, "null pointer");
     GB2_ARG(h, M >= 0, "M must be >= 0");
     if (M == 0) return 0;
     GB2_CUDA(h, cudaSetDevice(h->device));
+    if (h->compact) return predict_compact(h, Xs, M, pred_noise, mean, var, dev);
     const int64_t Np = h->Np, N = h->N;
     // chunk the prediction points so that the (chunk x Np) solve panel stays within ~8 GiB
     int64_t chunk = std::max<int64_t>(TILE, ((int64_t)8 << 30) / (Np * (int64_t)sizeof(double)) / TILE * TILE);
@@ -238,6 +343,7 @@ int gb2_destroy(gb2_handle* h) {
     p2p_close(h);
     if (h->comm && h->nccl) { h->nccl->CommDestroy(h->comm); h->comm = nullptr; }
     cudaFree(h->dLpack); cudaFree(h->dSend); cudaFree(h->dRecv); cudaFree(h->dFlags); cudaFree(h->dIpcXch);
+    cudaFree(h->dRing); cudaFree(h->dV); cudaFree(h->dPart);
     cudaFree(h->dX); cudaFree(h->dy); cudaFree(h->dBtab); cudaFree(h->dF); cudaFree(h->dC); cudaFree(h->dA);
     cudaFree(h->dDinv); cudaFree(h->dInfo); cudaFree(h->dScal); cudaFree(h->dXs); cudaFree(h->dFs); cudaFree(h->dCs);
     cudaFree(h->dAt); cudaFree(h->dMean); cudaFree(h->dVar);
@@ -351,7 +457,8 @@ static void p2p_close(gb2_handle* h) {
         if (h->peerDinv[r]) cudaIpcCloseMemHandle(h->peerDinv[r]);
         if (h->peerLpack[r]) cudaIpcCloseMemHandle(h->peerLpack[r]);
         if (h->peerFlags[r]) cudaIpcCloseMemHandle(h->peerFlags[r]);
-        h->peerA[r] = h->peerDinv[r] = h->peerLpack[r] = nullptr;
+        if (h->peerRing[r]) cudaIpcCloseMemHandle(h->peerRing[r]);
+        h->peerA[r] = h->peerDinv[r] = h->peerLpack[r] = h->peerRing[r] = nullptr;
         h->peerFlags[r] = nullptr;
     }
     h->p2p_ready = false;
@@ -374,33 +481,39 @@ static int dist_min_int(gb2_handle* h, int mine, int* out) {
 
 static int p2p_setup(gb2_handle* h) {
     const int G = h->world, me = h->rank;
-    struct Pack { cudaIpcMemHandle_t a, dinv, lpack, flags; };
-    static_assert(sizeof(Pack) == 256, "four 64-byte IPC handles");
+    struct Pack { cudaIpcMemHandle_t a, dinv, lpack, flags, ring; };
+    static_assert(sizeof(Pack) == 320, "five 64-byte IPC handles");
     Pack mine{};
     int ok = 1;
     if (cudaIpcGetMemHandle(&mine.a, h->dA) != cudaSuccess || cudaIpcGetMemHandle(&mine.dinv, h->dDinv) != cudaSuccess ||
-        cudaIpcGetMemHandle(&mine.lpack, h->dLpack) != cudaSuccess || cudaIpcGetMemHandle(&mine.flags, h->dFlags) != cudaSuccess) {
+        cudaIpcGetMemHandle(&mine.lpack, h->dLpack) != cudaSuccess || cudaIpcGetMemHandle(&mine.flags, h->dFlags) != cudaSuccess ||
+        (h->dRing && cudaIpcGetMemHandle(&mine.ring, h->dRing) != cudaSuccess)) {
         ok = 0;
         cudaGetLastError();
     }
-    char* d = h->dIpcXch;   // [0, 8*256) gathered handles, [8*256, +256) mine
-    GB2_CUDA(h, cudaMemcpyAsync(d + 8 * 256, &mine, sizeof(Pack), cudaMemcpyHostToDevice, h->s_main));
-    int rc = h->nccl->AllGather(d + 8 * 256, d, sizeof(Pack), 0 /*ncclInt8*/, h->comm, h->s_main);
+    char* d = h->dIpcXch;   // [0, 8*320) gathered handles, [8*320, +320) mine
+    GB2_CUDA(h, cudaMemcpyAsync(d + 8 * 320, &mine, sizeof(Pack), cudaMemcpyHostToDevice, h->s_main));
+    int rc = h->nccl->AllGather(d + 8 * 320, d, sizeof(Pack), 0 /*ncclInt8*/, h->comm, h->s_main);
     if (rc != 0) { h->err = std::string("ncclAllGather: ") + h->nccl->GetErrorString(rc); return -200 - rc; }
     Pack all[8];
     GB2_CUDA(h, cudaMemcpyAsync(all, d, (size_t)G * sizeof(Pack), cudaMemcpyDeviceToHost, h->s_main));
     GB2_CUDA(h, cudaStreamSynchronize(h->s_main));
     for (int r = 0; r < G && ok; r++) {
-        if (r == me) { h->peerA[r] = h->dA; h->peerDinv[r] = h->dDinv; h->peerLpack[r] = h->dLpack; h->peerFlags[r] = h->dFlags; continue; }
-        void *pa = nullptr, *pd = nullptr, *pl = nullptr, *pf = nullptr;
+        if (r == me) {
+            h->peerA[r] = h->dA; h->peerDinv[r] = h->dDinv; h->peerLpack[r] = h->dLpack; h->peerFlags[r] = h->dFlags; h->peerRing[r] = h->dRing;
+            continue;
+        }
+        void *pa = nullptr, *pd = nullptr, *pl = nullptr, *pf = nullptr, *pg = nullptr;
         if (cudaIpcOpenMemHandle(&pa, all[r].a, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
             cudaIpcOpenMemHandle(&pd, all[r].dinv, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
             cudaIpcOpenMemHandle(&pl, all[r].lpack, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
-            cudaIpcOpenMemHandle(&pf, all[r].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaIpcOpenMemHandle(&pf, all[r].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+            (h->dRing && cudaIpcOpenMemHandle(&pg, all[r].ring, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)) {
             ok = 0;
             cudaGetLastError();
         }
         h->peerA[r] = (double*)pa; h->peerDinv[r] = (double*)pd; h->peerLpack[r] = (double*)pl; h->peerFlags[r] = (unsigned*)pf;
+        h->peerRing[r] = (double*)pg;
     }
     int all_ok = 0;
     if ((rc = dist_min_int(h, ok, &all_ok))) return rc;
@@ -421,7 +534,9 @@ static int build_K(gb2_handle* h, int& launches) {
     if ((rc = validate_against_train(h))) return rc;
     if ((rc = ensure(h, h->dF, h->F_cap, (int64_t)std::max(1, h->kp.n_feat) * Np))) return rc;
     if ((rc = ensure(h, h->dC, h->C_cap, (int64_t)std::max(1, h->kp.n_cat) * Np))) return rc;
-    if (h->world > 1 && !h->dIpcXch) GB2_CUDA(h, cudaMalloc(&h->dIpcXch, 16 * 256));
+    if (h->world > 1 && !h->dIpcXch) GB2_CUDA(h, cudaMalloc(&h->dIpcXch, 16 * 320));
+    const bool want_compact = h->world > 1 && h->opt_shard_storage;
+    if (want_compact != h->compact) { h->A_cap = 0; h->xch_cap = 0; }   // storage layout changes: everything is re-allocated
     if (h->world > 1 && h->p2p_ready && (h->A_cap < Np || h->xch_cap < Np)) {
         // buffers are about to be re-allocated: every rank first drops its mappings of the peers' old buffers
         p2p_close(h);
@@ -432,7 +547,9 @@ static int build_K(gb2_handle* h, int& launches) {
         if (h->dA) GB2_CUDA(h, cudaFree(h->dA));
         if (h->dDinv) GB2_CUDA(h, cudaFree(h->dDinv));
         h->dA = nullptr; h->dDinv = nullptr; h->A_cap = 0;
-        GB2_CUDA(h, cudaMalloc(&h->dA, (size_t)Np * Np * sizeof(double)));
+        h->compact = want_compact;
+        h->nloc = want_compact ? (Np / TILE + h->world - 1) / h->world : Np / TILE;   // same allocation on every rank
+        GB2_CUDA(h, cudaMalloc(&h->dA, (size_t)h->nloc * TILE * Np * sizeof(double)));
         GB2_CUDA(h, cudaMalloc(&h->dDinv, (size_t)Np * TILE * sizeof(double)));
         // the diagonal-panel kernel writes the lower block-triangle of each inverse only; the rest stays zero
         GB2_CUDA(h, cudaMemsetAsync(h->dDinv, 0, (size_t)Np * TILE * sizeof(double), s));
@@ -466,16 +583,30 @@ static int build_K(gb2_handle* h, int& launches) {
         GB2_CUDA(h, cudaMemsetAsync(h->dSend, 0, (size_t)per_rank * TILE * TILE * sizeof(double), s));
         if (h->dFlags) GB2_CUDA(h, cudaFree(h->dFlags));
         h->p2p_nbmax = nb;
-        GB2_CUDA(h, cudaMalloc(&h->dFlags, ((size_t)4 * nb + 4) * sizeof(unsigned)));   // + the barrier counter
-        GB2_CUDA(h, cudaMemsetAsync(h->dFlags, 0, ((size_t)4 * nb + 4) * sizeof(unsigned), s));
+        // [2 parities][2 kinds][nb] factorisation counters, 4 barrier words, [2 parities][nb] prediction-step counters
+        GB2_CUDA(h, cudaMalloc(&h->dFlags, ((size_t)6 * nb + 4) * sizeof(unsigned)));
+        GB2_CUDA(h, cudaMemsetAsync(h->dFlags, 0, ((size_t)6 * nb + 4) * sizeof(unsigned), s));
         h->p2p_parity = 0;
+        h->x_parity = 0;
         h->p2p_epoch = 0;
+        if (h->dRing) { GB2_CUDA(h, cudaFree(h->dRing)); h->dRing = nullptr; }
+        if (want_compact) {
+            // panel ring (factorisation: >= 3 live panels) doubling as the ring of solved prediction panels (a rank may lag
+            // world-1 steps behind there): slots of max(Np, 16384) x 128 doubles
+            h->ring_slots = std::max(4, h->world + 2);
+            h->ring_slot_elems = std::max<int64_t>(Np, 16384) * TILE;
+            GB2_CUDA(h, cudaMalloc(&h->dRing, (size_t)h->ring_slots * h->ring_slot_elems * sizeof(double)));
+            if ((rc = ensure(h, h->dV, h->V_cap, Np))) return rc;
+        }
+        if ((rc = ensure(h, h->dPart, h->part_cap, std::max<int64_t>(64, (int64_t)2 * 16384 * (h->world + 1))))) return rc;
         h->xch_cap = Np;
     }
     if (h->world > 1 && h->opt_p2p && !h->p2p_ready) {
         GB2_CUDA(h, cudaStreamSynchronize(s));
         if ((rc = p2p_setup(h))) return rc;
     }
+    GB2_ARG(h, !h->compact || h->p2p_ready, "shard_storage needs the NVLink peer exchange (CUDA IPC / P2P unavailable or p2p=0)");
+    GB2_ARG(h, !h->compact || !h->opt_kbuild_v1, "shard_storage is not available with the kbuild_v1 ablation");
     if (h->world > 1 && h->p2p_ready) {
         // counters: this factorisation uses parity p; the other parity (used by the previous one, fully consumed) is cleared for
         // the next one now -- no peer can be that far ahead, every factorisation needs every rank's panels
@@ -492,7 +623,7 @@ static int build_K(gb2_handle* h, int& launches) {
                                                                                 h->dA, Np, h->world, h->rank);
     else
         kbuild_dmma_launch<true>(s, grid, kbuild_dmma_smem_bytes(h->kp), h->kp, h->dBtab, h->dF, h->dC, Np, N, h->dF, h->dC, Np, N, h->dy, h->dA, Np,
-                                 h->world, h->rank);
+                                 h->world, h->rank, h->compact ? 1 : 0);
     GB2_CUDA(h, cudaEventRecord(h->ev[2], s));
     launches += 2;
     return 0;
@@ -541,6 +672,7 @@ int gb2_mll_grad(gb2_handle* h, double* mll_out, double* grad_out) {
     if (!h) return -1;
     GB2_ARG(h, mll_out && grad_out, "null pointer");
     GB2_ARG(h, h->factorized, "gb2_mll_grad called before a successful gb2_factorize");
+    GB2_ARG(h, !h->compact, "gb2_mll_grad is not available in the storage-sharded mode yet");
     GB2_CUDA(h, cudaSetDevice(h->device));
     const int64_t Np = h->Np, N = h->N;
     const int nb = (int)(Np / TILE);
@@ -603,6 +735,7 @@ int gb2_get_K(gb2_handle* h, double* K_out) {
     if (!h) return -1;
     GB2_ARG(h, K_out, "null pointer");
     GB2_ARG(h, h->have_train && h->have_kernel, "gb2_get_K needs training data and a kernel");
+    GB2_ARG(h, !(h->world > 1 && h->opt_shard_storage), "gb2_get_K is a single-GPU test hook");
     GB2_CUDA(h, cudaSetDevice(h->device));
     int launches = 0, rc;
     h->factorized = false;  // the factor storage is overwritten
@@ -620,6 +753,18 @@ int gb2_get_L(gb2_handle* h, double* L_out) {
     GB2_ARG(h, L_out, "null pointer");
     GB2_ARG(h, h->factorized, "gb2_get_L called before a successful gb2_factorize");
     GB2_CUDA(h, cudaSetDevice(h->device));
+    if (h->compact) {   // storage-sharded: this rank's row blocks, zeros elsewhere (the caller sums over ranks)
+        const int64_t N = h->N, Np = h->Np;
+        memset(L_out, 0, (size_t)N * N * sizeof(double));
+        for (int64_t b = h->rank; b * TILE < N; b += h->world) {
+            const int64_t rows = std::min<int64_t>(TILE, N - b * TILE);
+            GB2_CUDA(h, cudaMemcpy2D(L_out + b * TILE * N, N * sizeof(double), h->dA + ((b - h->rank) / h->world) * TILE * Np, Np * sizeof(double),
+                                     N * sizeof(double), rows, cudaMemcpyDeviceToHost));
+        }
+        for (int64_t i = 0; i < N; i++)
+            for (int64_t j = i + 1; j < N; j++) L_out[i * N + j] = 0.0;
+        return 0;
+    }
     const int64_t N = h->N, Np = h->Np;
     GB2_CUDA(h, cudaMemcpy2D(L_out, N * sizeof(double), h->dA, Np * sizeof(double), N * sizeof(double), N, cudaMemcpyDeviceToHost));
     for (int64_t i = 0; i < N; i++)
@@ -632,6 +777,10 @@ int gb2_get_v(gb2_handle* h, double* v_out) {
     GB2_ARG(h, v_out, "null pointer");
     GB2_ARG(h, h->factorized, "gb2_get_v called before a successful gb2_factorize");
     GB2_CUDA(h, cudaSetDevice(h->device));
+    if (h->compact) {
+        GB2_CUDA(h, cudaMemcpy(v_out, h->dV, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost));
+        return 0;
+    }
     GB2_CUDA(h, cudaMemcpy(v_out, h->dA + h->N * h->Np, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost));
     return 0;
 }
@@ -755,6 +904,11 @@ int gb2_set_option(gb2_handle* h, const char* name, int value) {
     if (!strcmp(name, "tf32_leaf")) {
         GB2_ARG(h, value >= 1 && value <= 16, "tf32_leaf must be in [1, 16]");
         h->opt_tf32_leaf = value;
+        return 0;
+    }
+    if (!strcmp(name, "shard_storage")) {   // 1: every rank stores only the row blocks it owns (N beyond one GPU's HBM); collective choice
+        h->opt_shard_storage = value ? 1 : 0;
+        h->factorized = false;
         return 0;
     }
     if (!strcmp(name, "p2p")) {   // 1: panel exchange through NVLink peer mappings (default), 0: NCCL broadcast + all-gather

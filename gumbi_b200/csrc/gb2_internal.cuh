@@ -111,8 +111,18 @@ struct gb2_handle {
     unsigned* dFlags = nullptr;      // [2 parities][2 kinds][p2p_nbmax] counters bumped by the peers
     int64_t p2p_nbmax = 0;
     int p2p_parity = 0;
+    int x_parity = 0;
     int64_t p2p_epoch = 0;
     char* dIpcXch = nullptr;
+    // storage-sharded mode (set_option("shard_storage", 1)): every rank keeps only the 128-row blocks of the factor it owns
+    // (contiguously: local block li <-> global block li * world + rank) plus a ring of panel buffers the peers push into
+    int opt_shard_storage = 0;
+    bool compact = false;            // state of the current allocation / factorisation
+    int64_t nloc = 0;                // 128-row blocks held locally (same allocation size on every rank: ceil(nb / world))
+    double* dRing = nullptr; double* peerRing[8] = {};
+    int ring_slots = 0; int64_t ring_slot_elems = 0;
+    double* dV = nullptr; int64_t V_cap = 0;           // v = L^-1 y replicated on every rank (broadcast after the factorisation)
+    double* dPart = nullptr; int64_t part_cap = 0;     // per-rank partial sums of the posterior reduction, all-gathered
 
     // GB2_TF32: tf32 hi/lo splits + their TMA descriptors (tf32gemm.cuh)
     int n_sm = 148;

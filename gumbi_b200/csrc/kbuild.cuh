@@ -272,6 +272,13 @@ __device__ __forceinline__ void kb_dmma(double& c0, double& c1, double a, double
 
 __host__ __device__ inline int kb2_ka(int d) { return (d + 2 + 3) / 4 * 4; }
 
+// Row of the output buffer that holds global row gi: identity, or -- storage-sharded multi-GPU mode -- the position inside the
+// contiguous run of 128-row blocks this rank owns (block b -> local block (b - rank) / stride).
+__device__ __forceinline__ int64_t kb_out_row(int64_t gi, int own_stride, int own_rank, int compact) {
+    if (!compact) return gi;
+    return ((gi / TILE - own_rank) / own_stride) * TILE + gi % TILE;
+}
+
 // KIND >= 0 with SIMPLE: compile-time specialisation for the common model (one term, that stationary kernel, no Linear, no
 // Coregion) -- the per-entry code then has no kind switch and no term / factor loops.  KIND = -1: everything at run time.
 template <bool TRAIN, int KIND, bool SIMPLE>
@@ -279,10 +286,12 @@ __global__ void __launch_bounds__(KB_THREADS)
 kbuild_dmma_kernel(KParams kp, const double* __restrict__ Btab,
                    const double* __restrict__ Fi, const int* __restrict__ Ci, int64_t stride_i, int64_t n_i,
                    const double* __restrict__ Fj, const int* __restrict__ Cj, int64_t stride_j, int64_t n_j,
-                   const double* __restrict__ y, double* __restrict__ out, int64_t ld, int own_stride, int own_rank) {
+                   const double* __restrict__ y, double* __restrict__ out, int64_t ld, int own_stride, int own_rank, int compact) {
     const int bi = blockIdx.y, bj = blockIdx.x;
     if (TRAIN && bj > bi) return;
     if (TRAIN && own_stride > 1 && ((bi * KB_T) / TILE) % own_stride != own_rank) return;
+    // K(X*, X) in the storage-sharded mode: this rank builds only the column blocks (training points) it owns, stored contiguously
+    if (!TRAIN && compact && ((bj * KB_T) / TILE) % own_stride != own_rank) return;
     extern __shared__ __align__(16) unsigned char kb_smem[];
     // total augmented / linear rows over the terms
     int ka_tot = 0, nl_tot = 0;
@@ -296,6 +305,7 @@ kbuild_dmma_kernel(KParams kp, const double* __restrict__ Btab,
     int* sCi = reinterpret_cast<int*>(sTab + 64);              // [nc][64]
     int* sCj = sCi + (nc > 0 ? nc : 1) * KB_T;
     const int64_t i0 = (int64_t)bi * KB_T, j0 = (int64_t)bj * KB_T;
+    const int64_t jc0 = (!TRAIN && compact) ? kb_out_row(j0, own_stride, own_rank, 1) : j0;   // output column of the tile's first column
     if (threadIdx.x < 64) sTab[threadIdx.x] = g_exp2_tab[threadIdx.x];
     {
         int aoff = 0, loff = 0;
@@ -390,7 +400,7 @@ kbuild_dmma_kernel(KParams kp, const double* __restrict__ Btab,
     if ((!TRAIN || bi != bj) && i0 + KB_T <= n_i && j0 + KB_T <= n_j) {
 #pragma unroll
         for (int mi = 0; mi < 2; mi++) {
-            double* dst = out + (i0 + r0 + mi * 8 + g) * ld + j0 + c0 + 2 * t4;
+            double* dst = out + kb_out_row(i0 + r0 + mi * 8 + g, own_stride, own_rank, TRAIN ? compact : 0) * ld + jc0 + c0 + 2 * t4;
 #pragma unroll
             for (int ni = 0; ni < 4; ni++) *reinterpret_cast<double2*>(dst + ni * 8) = make_double2(val[mi][ni][0], val[mi][ni][1]);
         }
@@ -427,7 +437,8 @@ kbuild_dmma_kernel(KParams kp, const double* __restrict__ Btab,
                 }
                 o[e] = v;
             }
-            *reinterpret_cast<double2*>(out + gi * ld + j0 + c0 + ni * 8 + 2 * t4) = make_double2(o[0], o[1]);
+            *reinterpret_cast<double2*>(out + kb_out_row(gi, own_stride, own_rank, TRAIN ? compact : 0) * ld + jc0 + c0 + ni * 8 + 2 * t4) =
+                make_double2(o[0], o[1]);
         }
     }
 }
@@ -468,7 +479,7 @@ template <bool TRAIN, int KIND>
 __global__ void __launch_bounds__(KB_THREADS, 3)
 kbuild_strip_kernel(KParams kp, const double* __restrict__ Fi, int64_t stride_i, int64_t n_i, const double* __restrict__ Fj,
                     int64_t stride_j, int64_t n_j, int n_col_tiles, const double* __restrict__ y, double* __restrict__ out, int64_t ld,
-                    int own_stride, int own_rank) {
+                    int own_stride, int own_rank, int compact) {
     const int bi = blockIdx.y;
     const int jt0 = blockIdx.x * KB3_JG;
     if (TRAIN && jt0 > bi) return;
@@ -558,7 +569,7 @@ kbuild_strip_kernel(KParams kp, const double* __restrict__ Fi, int64_t stride_i,
         if ((!TRAIN || bi != jt) && i0 + KB_T <= n_i && j0 + KB_T <= n_j) {
 #pragma unroll
             for (int mi = 0; mi < 2; mi++) {
-                double* dst = out + (i0 + r0 + mi * 8 + g) * ld + j0 + c0 + 2 * t4;
+                double* dst = out + kb_out_row(i0 + r0 + mi * 8 + g, own_stride, own_rank, TRAIN ? compact : 0) * ld + j0 + c0 + 2 * t4;
 #pragma unroll
                 for (int ni = 0; ni < 4; ni++) *reinterpret_cast<double2*>(dst + ni * 8) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
             }
@@ -587,7 +598,8 @@ kbuild_strip_kernel(KParams kp, const double* __restrict__ Fi, int64_t stride_i,
                     }
                     o[e] = v;
                 }
-                *reinterpret_cast<double2*>(out + gi * ld + j0 + c0 + ni * 8 + 2 * t4) = make_double2(o[0], o[1]);
+                *reinterpret_cast<double2*>(out + kb_out_row(gi, own_stride, own_rank, TRAIN ? compact : 0) * ld + j0 + c0 + ni * 8 + 2 * t4) =
+                    make_double2(o[0], o[1]);
             }
         }
     }
@@ -599,23 +611,24 @@ inline size_t kbuild_strip_smem_bytes(const KParams& kp) { return (size_t)(3 * k
 template <bool TRAIN>
 inline void kbuild_dmma_launch(cudaStream_t s, dim3 grid, size_t smem, const KParams& kp, const double* Btab, const double* Fi, const int* Ci,
                                int64_t stride_i, int64_t n_i, const double* Fj, const int* Cj, int64_t stride_j, int64_t n_j, const double* y,
-                               double* out, int64_t ld, int own_stride, int own_rank) {
-    const bool simple = kp.n_terms == 1 && kp.t[0].n_lin == 0 && kp.t[0].n_coreg == 0 && kp.noise_cat < 0;
+                               double* out, int64_t ld, int own_stride, int own_rank, int compact = 0) {
+    // (the strip kernel's prefetch pipeline walks consecutive column tiles; the column-sharded K* build uses the per-tile kernel)
+    const bool simple = kp.n_terms == 1 && kp.t[0].n_lin == 0 && kp.t[0].n_coreg == 0 && kp.noise_cat < 0 && (TRAIN || !compact);
     if (simple && (kp.t[0].kind == GB2_EXPQUAD || kp.t[0].kind == GB2_MATERN52)) {
         // grid: x = strips of KB3_JG column tiles, y = row tiles
         dim3 sgrid((grid.x + KB3_JG - 1) / KB3_JG, grid.y);
         const size_t ssm = kbuild_strip_smem_bytes(kp);
         if (kp.t[0].kind == GB2_EXPQUAD)
             kbuild_strip_kernel<TRAIN, GB2_EXPQUAD><<<sgrid, KB_THREADS, ssm, s>>>(kp, Fi, stride_i, n_i, Fj, stride_j, n_j, (int)grid.x, y, out, ld,
-                                                                                  own_stride, own_rank);
+                                                                                  own_stride, own_rank, compact);
         else
             kbuild_strip_kernel<TRAIN, GB2_MATERN52><<<sgrid, KB_THREADS, ssm, s>>>(kp, Fi, stride_i, n_i, Fj, stride_j, n_j, (int)grid.x, y, out, ld,
-                                                                                   own_stride, own_rank);
+                                                                                   own_stride, own_rank, compact);
         return;
     }
 #define GB2_KB_LAUNCH(KIND, SIMPLE)                                                                                             \
     kbuild_dmma_kernel<TRAIN, KIND, SIMPLE><<<grid, KB_THREADS, smem, s>>>(kp, Btab, Fi, Ci, stride_i, n_i, Fj, Cj, stride_j, n_j, y, out, ld, \
-                                                                           own_stride, own_rank)
+                                                                           own_stride, own_rank, compact)
     GB2_KB_LAUNCH(-1, false);
 #undef GB2_KB_LAUNCH
 }

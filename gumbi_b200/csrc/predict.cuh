@@ -93,4 +93,50 @@ posterior_reduce_kernel(KParams kp, const double* __restrict__ Btab, const doubl
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Storage-sharded prediction: L is distributed by row blocks, so the solve  At <- At L^-T  is distributed by COLUMN blocks of
+// At (rank r holds At[:, j] for j % G == r, contiguously) and runs right-looking, one 128-column block per step:
+//   owner(j):  X_j = At[:, j] inv(L_jj)^T   -- the same fused kernel as the factor panel: stored locally and pushed into slot
+//              j % ring_slots of every rank's ring (Mp x 128, ld 128), counters bumped
+//   others:    wait for the counter
+//   all:       At[:, i] -= X_j L[i, j]^T  for the owned column blocks i > j   (L[i, j] is local: row block i, column block j)
+// then every rank reduces its own columns (mean and sum-of-squares partials) and the partials are all-gathered and summed.
+// All ranks pass the SAME prediction points; all ranks return the full result.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+posterior_partial_kernel(const double* __restrict__ At, int64_t ldt, const double* __restrict__ v, int64_t n, int64_t M, int64_t ncols_loc,
+                         int G, int me, double* __restrict__ part, int64_t pstride) {
+    const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (m >= M) return;
+    const int lane = threadIdx.x & 31;
+    const double* row = At + m * ldt;
+    double mu = 0.0, ss = 0.0;
+    for (int64_t lc = lane; lc < ncols_loc; lc += 32) {
+        const int64_t i = ((lc / TILE) * G + me) * TILE + lc % TILE;   // global training index of local column lc
+        if (i < n) {
+            const double a = row[lc];
+            mu = fma(a, v[i], mu);
+            ss = fma(a, a, ss);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mu += __shfl_xor_sync(0xffffffffu, mu, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if (lane == 0) { part[m] = mu; part[pstride + m] = ss; }
+}
+
+__global__ void posterior_final_kernel(KParams kp, const double* __restrict__ Btab, const double* __restrict__ Fs, const int* __restrict__ Cs,
+                                       int64_t stride_s, const double* __restrict__ all, int G, int64_t pstride, int64_t M, int pred_noise,
+                                       double* __restrict__ mean, double* __restrict__ var) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    double mu = 0.0, ss = 0.0;
+    for (int r = 0; r < G; r++) { mu += all[(int64_t)r * 2 * pstride + m]; ss += all[(int64_t)r * 2 * pstride + pstride + m]; }
+    double kss, nz;
+    point_diag(kp, Btab, Fs, Cs, stride_s, m, kss, nz);
+    mean[m] = mu;
+    var[m] = (kss - ss) + (pred_noise ? nz : 0.0);
+}
+
 }  // namespace gb2

@@ -41,6 +41,7 @@ class GPEngine:
         self.N = 0
         self.D_in = 0
         self.rank, self.world = 0, 1
+        self.options = {}
 
     # -- lifetime ------------------------------------------------------------------------------------
     def close(self):
@@ -88,6 +89,12 @@ class GPEngine:
 
     def set_option(self, name: str, value: int):
         self._check(self._lib.gb2_set_option(self._h, name.encode(), int(value)), "set_option")
+        self.options[name] = int(value)
+
+    @property
+    def shard_storage(self) -> bool:
+        """True: the factor is stored row-block-sharded across the ranks and predict() is a collective over ALL points."""
+        return self.world > 1 and bool(self.options.get("shard_storage"))
 
     # -- multi-GPU ------------------------------------------------------------------------------------
     def nccl_unique_id(self) -> bytes:

@@ -28,6 +28,9 @@ def main():
     eng = GPEngine(local_rank, prec)
     if os.environ.get("GB2_DIST_P2P", "1") == "0":
         eng.set_option("p2p", 0)     # ablation: NCCL broadcast + all-gather instead of NVLink peer stores
+    shard = os.environ.get("GB2_DIST_SHARD", "0") == "1"
+    if shard:
+        eng.set_option("shard_storage", 1)   # every rank stores only its own row blocks; predict is a collective over all points
     r, w = gdist.init_engine(eng)
     assert (r, w) == (rank, world)
     ref = GPEngine(local_rank, prec)  # same GPU, not sharded
@@ -45,21 +48,29 @@ def main():
         for _ in range(2):
             t0 = time.perf_counter(); ref.factorize(); t_one = time.perf_counter() - t0
         tm1 = ref.timings()
-        rec = {"N": len(y), "world": world, "rank": rank, "precision": prec, "p2p": os.environ.get("GB2_DIST_P2P", "1"), "chol_ms_sharded": tm["cholesky_ms"], "chol_ms_single": tm1["cholesky_ms"],
+        rec = {"N": len(y), "world": world, "rank": rank, "precision": prec, "p2p": os.environ.get("GB2_DIST_P2P", "1"), "shard_storage": shard, "chol_ms_sharded": tm["cholesky_ms"], "chol_ms_single": tm1["cholesky_ms"],
                "wall_ms_sharded": t_shard * 1e3, "wall_ms_single": t_one * 1e3}
         if len(y) <= 8192:
             L, L1 = eng.get_L(), ref.get_L()
+            if shard:   # each rank returns its own row blocks (zeros elsewhere): sum over the ranks
+                Lt = torch.from_numpy(L).cuda()
+                dist.all_reduce(Lt)
+                L = Lt.cpu().numpy()
             rec["L_bit_identical"] = bool(np.array_equal(L, L1))
             rec["L_max_abs_diff"] = float(np.max(np.abs(L - L1)))
             rec["v_max_abs_diff"] = float(np.max(np.abs(eng.get_v() - ref.get_v())))
             rec["mll_diff"] = abs(eng.mll() - ref.mll())
             ok &= rec["L_max_abs_diff"] < 1e-9 and rec["v_max_abs_diff"] < 1e-9
-        lo, hi = gdist.grid_slice(len(Xs), rank, world)
-        mu_l, var_l = eng.predict(Xs[lo:hi], True)
-        mu, var = gdist.gather_grid(mu_l, var_l, len(Xs))
+        if shard:
+            mu, var = eng.predict(Xs, True)
+        else:
+            lo, hi = gdist.grid_slice(len(Xs), rank, world)
+            mu_l, var_l = eng.predict(Xs[lo:hi], True)
+            mu, var = gdist.gather_grid(mu_l, var_l, len(Xs))
         mu1, var1 = ref.predict(Xs, True)
         rec["pred_max_abs_diff"] = float(max(np.max(np.abs(mu - mu1)), np.max(np.abs(var - var1))))
         ok &= rec["pred_max_abs_diff"] < 1e-8
+        rec["pred_ms"] = eng.timings()["solve_ms"] + eng.timings()["kstar_ms"] + eng.timings()["reduce_ms"]
         if with_oracle and rank == 0 and len(y) <= 4096:
             from oracle import gp_oracle as orc
 
