@@ -154,7 +154,13 @@ int gb2_dist_finalize(gb2_handle* h);
 /* Gather `count` doubles from every rank (rank-major) on the handle's stream: the per-rank slices of the posterior.  */
 int gb2_dist_allgather_dev(gb2_handle* h, const double* dsend, double* drecv, int64_t count);
 
-/* Tunables (for benchmarking/ablation): name in {"lookahead","graph"}; returns <0 if unknown.   */
+/* Options; returns <0 if the name is unknown.
+ *   "shard_storage" 0|1  multi-GPU: every rank stores only the row blocks of the factor it owns (N beyond one GPU's HBM);
+ *                        gb2_predict* then becomes a collective over ALL points (same Xs on every rank, full result on every
+ *                        rank).  Must be set identically on all ranks before gb2_factorize.  fp64 only.
+ *   "p2p"           1|0  multi-GPU panel exchange through NVLink peer mappings (default) or NCCL broadcast + all-gather
+ *   "tf32_nb"       0..16  GB2_TF32 factor-panel width in 128-column blocks (0 = auto); "tf32_leaf" 1..16 fp64 leaf width of the solve
+ *   "lookahead"     1|0  panel look-ahead on a second stream;  "fastdiag", "kbuild_v1": ablations               */
 int gb2_set_option(gb2_handle* h, const char* name, int value);
 
 #ifdef __cplusplus

@@ -79,14 +79,24 @@ def test_unique_id_exchange_and_gather_over_gloo(tmp_path):
 
 
 @pytest.mark.gpu
-def test_sharded_cholesky_matches_single_gpu():
+@pytest.mark.parametrize("mode", ["p2p", "nccl", "shard_storage", "tf32"])
+def test_sharded_cholesky_matches_single_gpu(mode):
+    """Factor bit-identical to the single-GPU one; predictions equal (replicated storage) or within 1e-8 (storage-sharded:
+    different summation order); through torchrun + tools/dist_check.py."""
     import torch
 
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs (run: gpurun --gpus 2 -- python -m pytest tests/test_dist.py -m gpu)")
     world = 2 if n < 4 else 4
+    env = dict(os.environ)
+    if mode == "nccl":
+        env["GB2_DIST_P2P"] = "0"
+    if mode == "shard_storage":
+        env["GB2_DIST_SHARD"] = "1"
+    if mode == "tf32":
+        env["GB2_DIST_PRECISION"] = "tf32"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", "29541", os.path.join(ROOT, "tools", "dist_check.py"), "1000", "3000"]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert res.returncode == 0 and "DIST_CHECK OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
