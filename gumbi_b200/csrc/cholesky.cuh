@@ -665,14 +665,17 @@ __global__ void sum_pairs_kernel(const double* __restrict__ all, int G, double* 
     }
 }
 
-inline int factor_steps_compact(gb2_handle* h) {
+// k0 <= k < k1, trailing updates restricted to column blocks < col_limit (as factor_steps).  split_c0 >= 0 (GB2_TF32): as soon as
+// panel k is complete in its ring slot, its rows below block col_limit are split into the tf32 hi/lo panel buffers (column block
+// k - split_c0), because the ring slot is recycled a few steps later while the tcgen05 update needs the whole 8-block panel.
+inline int factor_steps_compact(gb2_handle* h, int k0, int k1, int col_limit, int split_c0 = -1) {
     const int64_t Np = h->Np, ld = h->Np;
     const int nb = (int)(Np / TILE);
     const int G = h->world, me = h->rank;
     double* A = h->dA;   // (nloc * 128, Np): local block li = global block li * G + me
     int launches = 0;
     cudaStream_t sm = h->s_main, sp = h->s_panel;
-    {   // barrier + panel stream start
+    if (k0 == 0) {   // one barrier per factorisation
         PushArgs peers{};
         const size_t slot = (size_t)4 * h->p2p_nbmax;
         for (int r = 0, q = 0; r < G; r++)
@@ -681,13 +684,15 @@ inline int factor_steps_compact(gb2_handle* h) {
         h->p2p_epoch++;
         p2p_barrier_kernel<<<1, 32, 0, sm>>>(peers, h->dFlags + slot, (unsigned)(h->p2p_epoch * (G - 1)));
         launches++;
+    }
+    {   // the panel stream starts after everything queued on main (K build / barrier / previous tcgen05 update)
         cudaEvent_t e = pool_event(h, 3 * nb + 2);
         cudaEventRecord(e, sm);
         cudaStreamWaitEvent(sp, e, 0);
     }
     auto first_owned_after = [&](int k, int r) { return k + 1 + (((r - (k + 1)) % G) + G) % G; };
     auto count_from = [&](int first) { return first < nb ? (nb - first + G - 1) / G : 0; };
-    for (int k = 0; k < nb; k++) {
+    for (int k = k0; k < k1; k++) {
         const int64_t g0 = (int64_t)k * TILE;
         const int64_t below = Np - g0 - TILE;
         const int owner = k % G;
@@ -731,10 +736,17 @@ inline int factor_steps_compact(gb2_handle* h) {
             wait_counter_kernel<<<1, 32, 0, sp>>>(h->dFlags + fl + h->p2p_nbmax, expected);
             launches++;
         }
+        if (split_c0 >= 0 && col_limit < nb) {
+            const int64_t rows = Np - (int64_t)col_limit * TILE, pld = (int64_t)h->tf32_nb() * TILE;
+            tc::split_tf32_kernel<<<(unsigned)((rows * TILE / 2 + 255) / 256), 256, 0, sp>>>(
+                Pk + (int64_t)col_limit * TILE * TILE, TILE, rows, TILE, h->dPhi + (int64_t)col_limit * TILE * pld + (int64_t)(k - split_c0) * TILE,
+                h->dPlo + (int64_t)col_limit * TILE * pld + (int64_t)(k - split_c0) * TILE, pld);
+            launches++;
+        }
         cudaEvent_t e0 = pool_event(h, 2 * k);
         cudaEventRecord(e0, sp);
         cudaStreamWaitEvent(sm, e0, 0);
-        if (c1 > 0) {   // next column first
+        if (c1 > 0 && k + 1 < col_limit) {   // next column first
             dgemm_nt_launch<128, 64, GM_SUB>(sm, colk, ld, Pk + (g0 + TILE) * TILE, TILE, A + g0 + TILE, ld, (int64_t)c1 * TILE, TILE, TILE, 1, 0,
                                              g0 + TILE, f1, G, nullptr, l1);
             launches++;
@@ -742,11 +754,11 @@ inline int factor_steps_compact(gb2_handle* h) {
         cudaEvent_t e1 = pool_event(h, 2 * k + 1);
         cudaEventRecord(e1, sm);
         cudaStreamWaitEvent(sp, e1, 0);
-        if (below > TILE) {
+        if (k + 2 < col_limit) {
             const int f2 = first_owned_after(k + 1, me), c2 = count_from(f2);
             if (c2 > 0) {
                 dgemm_nt_launch<128, 64, GM_SUB>(sm, colk, ld, Pk + (g0 + 2 * TILE) * TILE, TILE, A + g0 + 2 * TILE, ld, (int64_t)c2 * TILE,
-                                                 below - TILE, TILE, 1, 0, g0 + 2 * TILE, f2, G, nullptr, (f2 - me) / G);
+                                                 (int64_t)(col_limit - (k + 2)) * TILE, TILE, 1, 0, g0 + 2 * TILE, f2, G, nullptr, (f2 - me) / G);
                 launches++;
             }
         }
@@ -778,7 +790,26 @@ inline int cholesky_enqueue(gb2_handle* h) {
     int launches = 0;
     const int pw = h->tf32_nb();
     if (h->compact) {
-        launches += factor_steps_compact(h);
+        if (h->precision == GB2_TF32 && nb > pw) {
+            // tf32 panels on the storage-sharded layout: fp64 panel [c0, c1) (its column blocks are split to tf32 as they complete in
+            // the ring), then one tcgen05 update of the owned row blocks >= c1 with the whole panel as the B operand
+            const int G = h->world, me = h->rank;
+            for (int c0 = 0; c0 < nb; c0 += pw) {
+                const int c1 = c0 + pw < nb ? c0 + pw : nb;
+                launches += factor_steps_compact(h, c0, c1, c1, c0);
+                if (c1 >= nb) break;
+                const int f = c1 + (((me - c1) % G) + G) % G;
+                const int cnt = f < nb ? (nb - f + G - 1) / G : 0;
+                tc::GemmArgs g{};
+                g.C = h->dA; g.ldc = ld;
+                g.n_bi = cnt; g.n_bj = nb - c1;
+                g.rb_first = f; g.rb_stride = G; g.rb_local_first = (f - me) / G; g.cblk0 = c1; g.lower = 1;
+                g.a_k0 = 0; g.b_row0 = c1 * TILE; g.b_k0 = 0;
+                tc::gemm_tf32x3_launch(h->s_main, h->n_sm, h->mPhi, h->mPlo, h->mPhi, h->mPlo, g, (c1 - c0) * TILE, launches);
+            }
+        } else {
+            launches += factor_steps_compact(h, 0, nb, nb);
+        }
         // log-determinant / |v|^2: per-rank partial sums over the owned rows, all-gathered and summed; v broadcast to everybody
         const int G = h->world, me = h->rank;
         double* part = h->dScal + 2;                        // [2] mine, gathered into dPart
@@ -812,7 +843,7 @@ inline int cholesky_enqueue(gb2_handle* h) {
             tc::GemmArgs g{};
             g.C = h->dA; g.ldc = ld;
             g.n_bi = cnt; g.n_bj = nb - c1;
-            g.rb_first = f; g.rb_stride = G; g.cblk0 = c1; g.lower = 1;
+            g.rb_first = f; g.rb_stride = G; g.rb_local_first = -1; g.cblk0 = c1; g.lower = 1;
             g.a_k0 = 0; g.b_row0 = c1 * TILE; g.b_k0 = 0;
             tc::gemm_tf32x3_launch(sm, h->n_sm, h->mPhi, h->mPlo, h->mPhi, h->mPlo, g, (int)cols, launches);
         }

@@ -53,7 +53,7 @@ inline void trsm_rec_tf32(gb2_handle* h, cudaStream_t s, int64_t Mp, int c0, int
     tc::GemmArgs g{};
     g.C = h->dAt; g.ldc = Np;
     g.n_bi = (int)(Mp / TILE); g.n_bj = c1 - mid;
-    g.rb_first = 0; g.rb_stride = 1; g.cblk0 = mid; g.lower = 0;
+    g.rb_first = 0; g.rb_stride = 1; g.rb_local_first = -1; g.cblk0 = mid; g.lower = 0;
     g.a_k0 = c0 * TILE; g.b_row0 = mid * TILE; g.b_k0 = c0 * TILE;
     tc::gemm_tf32x3_launch(s, h->n_sm, h->mAthi, h->mAtlo, h->mLhi, h->mLlo, g, (mid - c0) * TILE, launches);
     trsm_rec_tf32(h, s, Mp, mid, c1, n_total, leaf, launches);

@@ -114,6 +114,8 @@ struct GemmArgs {
     double* C; int64_t ldc;          // C points at global (row 0, column 0); tile (bi, bj) covers row block rb(bi), column block cblk0 + bj
     int n_bi, n_bj;                  // tile grid: n_bi row tiles of 128, n_bj = number of 128-column blocks (CTA tiles span NB of them)
     int rb_first, rb_stride;         // row block of tile row bi = rb_first + bi * rb_stride  (block-cyclic row ownership; dense: stride 1)
+    int rb_local_first;              // >= 0: C holds only the owned row blocks, contiguously: tile row bi is local block rb_local_first + bi
+                                     // (storage-sharded multi-GPU mode; A rows / the triangle predicate keep using the global block)
     int cblk0;                       // first column block
     int lower;                       // 1: skip tiles whose column block lies above their row block (trailing SYRK)
     int K;                           // multiple of TK, <= TC_MAX_K
@@ -250,7 +252,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
             // warp's next chunk are issued before the current chunk is transposed and stored (2 x 8 KB per warp in flight).
             float* S = epi + (warp - 2) * 32 * EPI_LD;
             const int half = (warp - 2) >> 2;                      // which of the two warps of this lane quadrant
-            double* cbase = g.C + ((int64_t)(g.rb_first + bi * g.rb_stride) * TM + q * 32) * g.ldc + (int64_t)(g.cblk0 + bj) * TN + lane;
+            const int64_t crow_blk = g.rb_local_first >= 0 ? (int64_t)(g.rb_local_first + bi) : (int64_t)(g.rb_first + bi * g.rb_stride);
+            double* cbase = g.C + (crow_blk * TM + q * 32) * g.ldc + (int64_t)(g.cblk0 + bj) * TN + lane;
             const int n_chunks = nh * (TN / 32);
             double o[32], o2[32];
             if (half < n_chunks) {

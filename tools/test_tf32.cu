@@ -32,7 +32,7 @@ int run(int M, int N, int K, int lower, bool check, int nbt = 2) {
         (r = tc::make_tmap(&mBlo, Blo, N, K, K))) { printf("cuTensorMapEncodeTiled failed: %d\n", (int)r); return 3; }
     CK(tc::gemm_tf32x3_configure());
     int n_sm = 0; CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0));
-    tc::GemmArgs g{}; g.C = dC; g.ldc = N; g.n_bi = M / 128; g.n_bj = N / 128; g.lower = lower; g.rb_first = 0; g.rb_stride = 1; g.cblk0 = 0;
+    tc::GemmArgs g{}; g.C = dC; g.ldc = N; g.n_bi = M / 128; g.n_bj = N / 128; g.lower = lower; g.rb_first = 0; g.rb_stride = 1; g.rb_local_first = -1; g.cblk0 = 0;
     g.a_k0 = g.b_row0 = g.b_k0 = 0;
     int launches = 0;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
