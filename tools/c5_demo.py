@@ -19,9 +19,10 @@ torch.cuda.set_device(local_rank)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 passes = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+precision = sys.argv[3] if len(sys.argv) > 3 else "fp64"   # "tf32": split-TF32 tcgen05 trailing updates (the sharded solve stays fp64)
 spec, X, y, Xs = synthetic_problem(n, 16, P=4, M_res=100, kind="ExpQuad", Q=2)
 N, M = len(y), len(Xs)
-eng = GPEngine(local_rank)
+eng = GPEngine(local_rank, precision)
 eng.set_option("shard_storage", 1)
 gdist.init_engine(eng)
 eng.set_train(X, y)
@@ -36,7 +37,7 @@ for p in range(passes):
     t2 = time.perf_counter()
     tm = eng.timings()
     free, total = torch.cuda.mem_get_info()
-    out = {"config": "c5: 4-output LCM (Q=2), n=%d, stacked N=%d, d=16, M=%d, fp64, %d GPUs, storage-sharded" % (n, N, M, world),
+    out = {"config": "c5: 4-output LCM (Q=2), n=%d, stacked N=%d, d=16, M=%d, %s, %d GPUs, storage-sharded" % (n, N, M, precision, world),
            "pass": p, "factorize_s": t1 - t0, "predict_s": t2 - t1, "cold_step_s": t2 - t0, "predictions_per_s": M / (t2 - t0),
            "phases_ms": {k: v for k, v in tm.items() if k.endswith("_ms")},
            "cholesky_tflops_aggregate": N ** 3 / 3 / (tm["cholesky_ms"] * 1e-3) / 1e12,

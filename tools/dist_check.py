@@ -70,7 +70,7 @@ def main():
         mu1, var1 = ref.predict(Xs, True)
         rec["pred_max_abs_diff"] = float(max(np.max(np.abs(mu - mu1)), np.max(np.abs(var - var1))))
         # (tf32 + shard_storage: the sharded solve is fp64 while the single-GPU reference solve is split-TF32)
-        ok &= rec["pred_max_abs_diff"] < (1e-8 if not (shard and prec == "tf32") else 5e-3)
+        ok &= rec["pred_max_abs_diff"] < (1e-8 if not (shard and prec == "tf32") else 2e-2)
         rec["pred_ms"] = eng.timings()["solve_ms"] + eng.timings()["kstar_ms"] + eng.timings()["reduce_ms"]
         if with_oracle and rank == 0 and len(y) <= 4096:
             from oracle import gp_oracle as orc
