@@ -279,6 +279,60 @@ class B200Backend:
             return gdist.gather_grid(mu, var, len(points_array))
         return self.engine.predict(points_array, pred_noise=bool(with_noise))
 
+    # -- conditional / posterior samples (GP.py:861-979) ------------------------------------------------------------
+    def conditional(self, points_array, pred_noise=False):
+        """Mean and full covariance of ``gp_dict["total"].conditional(var_name, points_array)`` (GP.py:913-914), on device."""
+        self._ensure_factorized()
+        points_array = np.atleast_2d(np.asarray(points_array, dtype=np.float64))
+        return self.engine.predict_full(points_array, pred_noise=bool(pred_noise))
+
+    def sample_conditional(self, points_array, size=1, random_seed=None, pred_noise=False):
+        """``size`` joint draws from the conditional at ``points_array`` (standardized space), shape (size, M).
+
+        The O(N^2 M + N M^2) part (solve, covariance) runs on the GPU; the draw itself is mu + chol(cov + 1e-6 I) z on the host
+        (PyMC's ``stabilize`` jitter), O(M^3) for the M requested points only."""
+        mu, cov = self.conditional(points_array, pred_noise=pred_noise)
+        rng = np.random.default_rng(self.seed if random_seed is None else random_seed)
+        Lc = np.linalg.cholesky(cov + JITTER_DEFAULT * np.eye(len(mu)))
+        return mu[None, :] + rng.standard_normal((int(size), len(mu))) @ Lc.T
+
+    def draw_point_samples(self, points, *args, source=None, output=None, var_name="posterior_samples", additive_level="total",
+                           increment_var=True, size=1, random_seed=None, **kwargs):
+        """Mirror of ``PymcGP.draw_point_samples`` (GP.py:861-922) for a MAP source: joint posterior draws at ``points``.
+
+        Needs the ``Regressor`` base class (``_parse_prediction_output``, ``_prepare_points_for_prediction``, ``parray``)."""
+        if additive_level != "total":
+            raise NotImplementedError("Prediction for additive sublevels is not yet supported.")
+        output = self._parse_prediction_output(output)
+        if len(output) > 1:
+            raise NotImplementedError("Drawing correlated samples of multiple outputs is not yet implemented.")
+        points_array, tall_points, param_coords = self._prepare_points_for_prediction(points, output=output)
+        if source is None:
+            if self.MAP is None:
+                raise ValueError('"Source" of predictions must be supplied if GP object has no trace or MAP stored.')
+        elif isinstance(source, dict):
+            self.find_MAP(point=source)
+        else:
+            raise NotImplementedError("The B200 backend draws posterior samples from a MAP point only (no MCMC trace).")
+        samples = self.sample_conditional(points_array, size=size, random_seed=random_seed)
+        self.predictions = self.parray(**{output[0]: samples}, stdzd=True)
+        self.predictions_X = points
+        return self.predictions
+
+    def draw_grid_samples(self, *args, source=None, output=None, categorical_levels=None, var_name="posterior_samples",
+                          additive_level="total", increment_var=True, **kwargs):
+        """Mirror of ``PymcGP.draw_grid_samples`` (GP.py:924-979)."""
+        if self.grid_points is None:
+            raise ValueError("Grid must first be specified with `prepare_grid`")
+        points = self.grid_points
+        if self.categorical_dims:
+            points = self.append_categorical_points(points, categorical_levels=categorical_levels)
+        samples = self.draw_point_samples(*args, points=points, output=output, source=source, var_name=var_name,
+                                          additive_level=additive_level, increment_var=increment_var, **kwargs)
+        self.predictions = samples.reshape(-1, *self.grid_parray.shape)
+        self.predictions_X = self.predictions_X.reshape(self.grid_parray.shape)
+        return self.predictions
+
     def predict_cold(self, points_array, with_noise=True):
         """What ONE reference ``predict`` call costs: rebuild K, re-factorise, solve.  For benchmarking."""
         self._factor_key = None

@@ -343,7 +343,7 @@ int gb2_destroy(gb2_handle* h) {
     p2p_close(h);
     if (h->comm && h->nccl) { h->nccl->CommDestroy(h->comm); h->comm = nullptr; }
     cudaFree(h->dLpack); cudaFree(h->dSend); cudaFree(h->dRecv); cudaFree(h->dFlags); cudaFree(h->dIpcXch);
-    cudaFree(h->dRing); cudaFree(h->dV); cudaFree(h->dPart);
+    cudaFree(h->dRing); cudaFree(h->dV); cudaFree(h->dPart); cudaFree(h->dCov);
     cudaFree(h->dX); cudaFree(h->dy); cudaFree(h->dBtab); cudaFree(h->dF); cudaFree(h->dC); cudaFree(h->dA);
     cudaFree(h->dDinv); cudaFree(h->dInfo); cudaFree(h->dScal); cudaFree(h->dXs); cudaFree(h->dFs); cudaFree(h->dCs);
     cudaFree(h->dAt); cudaFree(h->dMean); cudaFree(h->dVar);
@@ -724,6 +724,55 @@ int gb2_mll_grad(gb2_handle* h, double* mll_out, double* grad_out) {
 int gb2_predict(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_noise, double* mean, double* var) {
     if (!h) return -1;
     return predict_common(h, Xs, M, pred_noise, mean, var, false);
+}
+
+// Posterior mean and FULL covariance: what gp.conditional(name, Xnew) parameterises (GP.py:913-914):
+//   mu = A^T v,  cov = K(X*,X*) - A^T A  (+ noise on the diagonal if pred_noise), A = L^-1 K(X,X*).
+// cov_out is (M, M) row-major, symmetric (both triangles filled).  M is limited by the (M x M) + (M x Np) device buffers.
+int gb2_predict_full(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_noise, double* mean, double* cov_out) {
+    if (!h) return -1;
+    GB2_ARG(h, h->factorized, "gb2_predict_full called before a successful gb2_factorize");
+    GB2_ARG(h, !h->compact, "gb2_predict_full is not available in the storage-sharded mode");
+    GB2_ARG(h, Xs && mean && cov_out, "null pointer");
+    GB2_ARG(h, M >= 1 && M <= 32768, "M must be in [1, 32768] for the full-covariance prediction");
+    GB2_CUDA(h, cudaSetDevice(h->device));
+    const int64_t Np = h->Np, N = h->N, Mp = round_up(M, TILE);
+    const int ncols = (int)((N + TILE - 1) / TILE);
+    cudaStream_t s = h->s_main;
+    int rc;
+    if ((rc = ensure(h, h->dAt, h->At_cap, Mp * Np))) return rc;
+    if ((rc = ensure(h, h->dFs, h->Fs_cap, (int64_t)std::max(1, h->kp.n_feat) * Mp))) return rc;
+    if ((rc = ensure(h, h->dCs, h->Cs_cap, (int64_t)std::max(1, h->kp.n_cat) * Mp))) return rc;
+    if ((rc = ensure(h, h->dXs, h->Xs_cap, M * h->D_in))) return rc;
+    if ((rc = ensure(h, h->dCov, h->cov_cap, Mp * Mp))) return rc;
+    int64_t oc = h->out_cap;
+    if ((rc = ensure(h, h->dMean, oc, M))) return rc;
+    if ((rc = ensure(h, h->dVar, h->out_cap, M))) return rc;
+    GB2_CUDA(h, cudaMemcpyAsync(h->dXs, Xs, (size_t)M * h->D_in * sizeof(double), cudaMemcpyHostToDevice, s));
+    GB2_CUDA(h, cudaMemsetAsync(h->dInfo + 1, 0, sizeof(int), s));
+    int launches = 0;
+    prep_features<<<(unsigned)((Mp + 255) / 256), 256, 0, s>>>(h->dXs, M, Mp, h->pp, h->dFs, h->dCs, h->dInfo + 1);
+    // A^T (rows = prediction points), exactly as gb2_predict
+    dim3 grid((unsigned)(Np / KB_T), (unsigned)(Mp / KB_T));
+    kbuild_dmma_launch<false>(s, grid, kbuild_dmma_smem_bytes(h->kp), h->kp, h->dBtab, h->dFs, h->dCs, Mp, M, h->dF, h->dC, Np, N, nullptr, h->dAt, Np, 1, 0);
+    trsm_rec(s, h->dA, Np, h->dDinv, h->dAt, Np, Mp, 0, ncols, launches);
+    // K(X*, X*) (all tiles) and cov -= At At^T over the training columns only (depth = ncols * 128: the augmented / padding
+    // columns right of N inside the last block are zero in At by construction of K(X*,X) and stay zero through the solve)
+    dim3 g2((unsigned)(Mp / KB_T), (unsigned)(Mp / KB_T));
+    kbuild_dmma_launch<false>(s, g2, kbuild_dmma_smem_bytes(h->kp), h->kp, h->dBtab, h->dFs, h->dCs, Mp, M, h->dFs, h->dCs, Mp, M, nullptr, h->dCov, Mp, 1, 0);
+    mask_columns_kernel<<<(unsigned)((Mp + 255) / 256), 256, 0, s>>>(h->dAt, Np, Mp, N, (int64_t)ncols * TILE);
+    dgemm_nt_launch<128, 64, GM_SUB>(s, h->dAt, Np, h->dAt, Np, h->dCov, Mp, Mp, Mp, ncols * TILE, 0, 0, 0);
+    posterior_reduce_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>(h->kp, h->dBtab, h->dFs, h->dCs, Mp, h->dAt, Np, h->dA + N * Np, N, M, pred_noise,
+                                                                   h->dMean, h->dVar);
+    if (pred_noise) add_noise_diag_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(h->kp, h->dBtab, h->dFs, h->dCs, Mp, M, h->dCov, Mp);
+    GB2_CUDA(h, cudaGetLastError());
+    GB2_CUDA(h, cudaMemcpyAsync(mean, h->dMean, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, s));
+    GB2_CUDA(h, cudaMemcpy2DAsync(cov_out, M * sizeof(double), h->dCov, Mp * sizeof(double), M * sizeof(double), M, cudaMemcpyDeviceToHost, s));
+    int bad = 0;
+    GB2_CUDA(h, cudaMemcpyAsync(&bad, h->dInfo + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
+    GB2_CUDA(h, cudaStreamSynchronize(s));
+    GB2_ARG(h, bad == 0, "a Coregion column of Xs holds a level index outside [0, P)");
+    return 0;
 }
 
 int gb2_predict_dev(gb2_handle* h, const double* dXs, int64_t M, int32_t pred_noise, double* dmean, double* dvar) {

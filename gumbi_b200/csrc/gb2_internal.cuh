@@ -90,6 +90,7 @@ struct gb2_handle {
     double* dFs = nullptr; int* dCs = nullptr; int64_t Fs_cap = 0, Cs_cap = 0;
     double* dAt = nullptr; int64_t At_cap = 0;           // (Mp, Np) rows = test points
     double* dMean = nullptr; double* dVar = nullptr; int64_t out_cap = 0;
+    double* dCov = nullptr; int64_t cov_cap = 0;         // (Mp, Mp) full posterior covariance (gb2_predict_full)
 
     // MLL-gradient scratch: W = L^-T (Np x Np), S = K^-1 (Np x Np), alpha (Np), flat gradient
     double* dW = nullptr; double* dS = nullptr; int64_t G_cap = 0;

@@ -59,6 +59,24 @@ inline void trsm_rec_tf32(gb2_handle* h, cudaStream_t s, int64_t Mp, int c0, int
     trsm_rec_tf32(h, s, Mp, mid, c1, n_total, leaf, launches);
 }
 
+// At[:, n .. width) = 0: the solve leaves garbage in the augmented (y) column and the padding columns of the last block, which
+// the diag reduction skips by its loop bound but a dense At At^T product would pick up.
+__global__ void mask_columns_kernel(double* __restrict__ At, int64_t ldt, int64_t rows, int64_t n, int64_t width) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    for (int64_t c = n; c < width; c++) At[r * ldt + c] = 0.0;
+}
+
+// cov[m][m] += noise.diag(x*_m)   (pred_noise=True, full-covariance prediction)
+__global__ void add_noise_diag_kernel(KParams kp, const double* __restrict__ Btab, const double* __restrict__ Fs, const int* __restrict__ Cs,
+                                      int64_t stride_s, int64_t M, double* __restrict__ cov, int64_t ldc) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    double kss, nz;
+    point_diag(kp, Btab, Fs, Cs, stride_s, m, kss, nz);
+    cov[m * ldc + m] += nz;
+}
+
 // One warp per prediction point: mean = sum_i At[m,i] v[i], var = kss - sum_i At[m,i]^2 (+ noise diag).
 __global__ void __launch_bounds__(256)
 posterior_reduce_kernel(KParams kp, const double* __restrict__ Btab, const double* __restrict__ Fs,

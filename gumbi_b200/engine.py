@@ -176,6 +176,19 @@ class GPEngine:
         self._check(self._lib.gb2_predict(self._h, _lib.as_dp(Xs), M, int(bool(pred_noise)), _lib.as_dp(mean), _lib.as_dp(var)), "predict")
         return mean, var
 
+    def predict_full(self, Xs, pred_noise: bool = False):
+        """Posterior mean (M,) and full covariance (M, M) -- the parameters of ``gp.conditional(name, Xnew)`` (GP.py:913)."""
+        Xs = _c_f64(np.atleast_2d(Xs), 2)
+        if Xs.shape[1] != self.D_in:
+            raise ValueError(f"points_array has {Xs.shape[1]} columns, model has {self.D_in} dims")
+        if not np.all(np.isfinite(Xs)):
+            raise ValueError("points_array must be finite")
+        M = Xs.shape[0]
+        mean = np.empty(M, dtype=np.float64)
+        cov = np.empty((M, M), dtype=np.float64)
+        self._check(self._lib.gb2_predict_full(self._h, _lib.as_dp(Xs), M, int(bool(pred_noise)), _lib.as_dp(mean), _lib.as_dp(cov)), "predict_full")
+        return mean, cov
+
     def predict_device(self, dXs_ptr: int, M: int, pred_noise: bool, dmean_ptr: int, dvar_ptr: int):
         self._check(
             self._lib.gb2_predict_dev(self._h, C.c_void_p(dXs_ptr), int(M), int(bool(pred_noise)), C.c_void_p(dmean_ptr), C.c_void_p(dvar_ptr)),

@@ -123,6 +123,11 @@ int gb2_mll_grad(gb2_handle* h, double* mll_out, double* grad_out);
 int gb2_predict(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_noise, double* mean, double* var);
 int gb2_predict_dev(gb2_handle* h, const double* dXs, int64_t M, int32_t pred_noise, double* dmean, double* dvar);
 
+/* Posterior mean and FULL covariance at Xs:(M,D_in): cov:(M,M) row-major = K(X*,X*) - A^T A (+ noise diag if pred_noise).
+ * Replaces the distribution gp.conditional(var_name, points_array) builds for draw_point_samples / draw_grid_samples
+ * (GP.py:861-979; pm.gp.Marginal.conditional, diag=False).  M <= 32768.                                                */
+int gb2_predict_full(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_noise, double* mean, double* cov);
+
 /* Test hooks: copy the dense objects back (row-major, n x n with n = N).  The strict upper
  * triangle is returned as zero for L and mirrored for K.                                        */
 int gb2_get_K(gb2_handle* h, double* K_out);   /* rebuilds K+Knoise+jitter into scratch; O(N^2)  */

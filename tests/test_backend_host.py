@@ -25,6 +25,9 @@ class OracleEngine:
     def predict(self, Xs, pred_noise=True):
         return orc.conditional(self.spec, self.X, self.L, self.v, Xs, pred_noise)
 
+    def predict_full(self, Xs, pred_noise=False):
+        return orc.conditional_full(self.spec, self.X, self.L, self.v, Xs, pred_noise)
+
     def mll(self):
         return orc.mll(self.spec, self.X, self.y)
 
@@ -209,3 +212,22 @@ def test_fit_runs_end_to_end_on_the_engine_double():
     assert isinstance(gp.MAP, dict)  # tests/test_regression.py:172-182 asserts exactly this of PymcGP
     mu, var = gp.predict(g["points"])
     assert mu.shape == var.shape == (len(g["points"]),) and np.all(var > 0)
+
+
+def test_conditional_and_joint_samples():
+    """conditional(): diag of the full covariance equals predict()'s variance; joint draws have the conditional's moments."""
+    g = load_golden("simple_regression_ExpQuad")
+    gp = gp_from_golden(g)
+    gp.find_MAP(point=g["meta"]["point"])
+    pts = g["points"][:40]
+    mu, cov = gp.conditional(pts)
+    mu1, var1 = gp.predict(pts, with_noise=False)
+    np.testing.assert_allclose(mu, mu1, rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(np.diag(cov), var1, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(cov, cov.T, rtol=0, atol=1e-12)
+    _, cov_n = gp.conditional(pts, pred_noise=True)
+    np.testing.assert_allclose(np.diag(cov_n) - np.diag(cov), g["meta"]["point"]["σ"] ** 2, rtol=1e-9)
+    draws = gp.sample_conditional(pts, size=4000, random_seed=1)
+    assert draws.shape == (4000, 40)
+    np.testing.assert_allclose(draws.mean(0), mu, atol=5 * np.sqrt(np.diag(cov).max() / 4000) + 1e-3)
+    np.testing.assert_allclose(np.cov(draws.T), cov + 1e-6 * np.eye(40), atol=0.1 * np.abs(cov).max())
