@@ -471,8 +471,12 @@ __device__ __forceinline__ double exp_tab_scaled(double x, const double* __restr
     const double p = fma(q, r2, r);
     const double T = tab[n & 63];
     const double res = fma(T, p, T);
-    const double sc = __hiloint2double(__double2hiint(res) + ((n >> 6) << 20), __double2loint(res));
-    return x < -700.0 ? 0.0 : sc;
+    // x < -700 tested on the high word (x <= 0: more negative <=> larger unsigned high word; -700.0 = 0xC085E000'00000000):
+    // integer pipe instead of another fp64-pipe instruction
+    const bool tiny = (unsigned)__double2hiint(x) > 0xC085E000u;
+    const int hi = tiny ? 0 : __double2hiint(res) + ((n >> 6) << 20);
+    const int lo = tiny ? 0 : __double2loint(res);
+    return __hiloint2double(hi, lo);
 }
 
 template <bool TRAIN, int KIND>
@@ -489,6 +493,10 @@ kbuild_strip_kernel(KParams kp, const double* __restrict__ Fi, int64_t stride_i,
     extern __shared__ __align__(16) unsigned char kb_smem[];
     const TermDev& T = kp.t[0];
     const int d = T.d, ka = kb2_ka(d);
+    // d % 4 == 0: the two augmented rows would cost a whole extra DMMA k-step (4 fp64 slots per entry); adding -|u_i|^2/2 and
+    // -|u_j|^2/2 with two DADDs instead is cheaper (d = 8: 10 instead of 12 slots)
+    const bool plain = (d & 3) == 0 && d > 0;
+    const int kdot = plain ? d : ka;
     double* sA = reinterpret_cast<double*>(kb_smem);      // [ka][TS]
     double* sB = sA + ka * KB2_TS;                         // [2][ka][TS]
     double* sTab = sB + 2 * ka * KB2_TS;                   // [64]
@@ -540,7 +548,19 @@ kbuild_strip_kernel(KParams kp, const double* __restrict__ Fi, int64_t stride_i,
         for (int mi = 0; mi < 2; mi++)
 #pragma unroll
             for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-        for (int kk = 0; kk < ka; kk += 4) {
+        if (plain) {   // accumulators start from -|u_i|^2/2 - |u_j|^2/2 (row d of the row side, row d+1 of the column side)
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++) {
+                const double hi_ = sA[d * KB2_TS + r0 + mi * 8 + g];
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) {
+                    const double2 hj = *reinterpret_cast<const double2*>(cB + (d + 1) * KB2_TS + c0 + ni * 8 + 2 * t4);
+                    acc[mi][ni][0] = hi_ + hj.x;
+                    acc[mi][ni][1] = hi_ + hj.y;
+                }
+            }
+        }
+        for (int kk = 0; kk < kdot; kk += 4) {
             const double* pa = sA + (kk + t4) * KB2_TS + r0 + g;
             const double* pb = cB + (kk + t4) * KB2_TS + c0 + g;
             const double a0 = pa[0], a1 = pa[8];

@@ -88,3 +88,24 @@ def test_multioutput_predict_points_reads_W_and_kappa_from_MAP(ref_env):
     gp2.specify_model(continuous_dims="lg10_Z", linear_dims="lg10_Z")
     gp2.build_model(**gp.model_specs)
     assert gp2.model_specs == gp.model_specs
+
+
+def test_draw_point_and_grid_samples_through_the_reference_wrappers(ref_env):
+    """GP.py:861-979: draw_point_samples / draw_grid_samples return a ParameterArray of joint posterior draws."""
+    gmb, GP, pd = ref_env
+    g = load_golden("simple_regression_ExpQuad")
+    df = pd.read_pickle(os.path.join(REF, "gumbi", "data", "Example_DataSet.pkl")).query('Metric=="mean"')
+    ds = gmb.DataSet(df, outputs=["a", "b", "c", "d", "e", "f"], log_vars=["Y", "b", "c", "d", "f"], logit_vars=["X", "e"])
+    ds.tidy = ds.tidy[ds.tidy.Color.isin(["cyan", "magenta"]) & (ds.tidy.Pair == "burrata+barbaresco")]
+    gp = GP(ds, outputs=["d"])
+    gp.specify_model(continuous_dims=["X", "Y", "lg10_Z"], linear_dims=["X", "Y", "lg10_Z"])
+    gp.build_model()
+    gp.find_MAP(point=g["meta"]["point"])
+    gp.prepare_grid(at=gp.parray(lg10_Z=8, X=0.5), resolution=25)
+    samples = gp.draw_grid_samples(size=6, random_seed=3)
+    assert type(samples).__name__ == "ParameterArray" and samples.shape == (6, 25)
+    z = samples.z.values() if hasattr(samples.z, "values") else np.asarray(samples.z["d_z"])
+    assert np.all(np.isfinite(np.asarray(z, dtype=float)))
+    # same seed -> same draws; the draws scatter around the posterior mean of predict()
+    again = gp.draw_grid_samples(size=6, random_seed=3)
+    np.testing.assert_array_equal(np.asarray(again.z.values(), dtype=float), np.asarray(z, dtype=float))

@@ -469,3 +469,27 @@ def test_random_models_against_oracle(engine, seed):
     val0, g0 = orc.mll_grad(spec, X, y)
     np.testing.assert_allclose(val, val0, rtol=1e-8 if rough else 1e-10)
     _tree_close(g, g0, rtol=2e-5 if rough else 2e-6, atol=(1e-5 if rough else 1e-6) * max(1.0, abs(g0["sigma"])))
+
+
+@pytest.mark.parametrize("n,d,P,kind,M", [(300, 2, 1, "ExpQuad", 77), (900, 4, 2, "Matern52", 200), (515, 3, 1, "Matern32", 129)])
+def test_full_covariance_prediction(engine, n, d, P, kind, M):
+    """gb2_predict_full (mean + full M x M covariance, the parameters of gp.conditional) vs the oracle's dense algebra."""
+    spec, X, y, Xs = orc.synthetic_problem(n, d, P=P, M_res=20, kind=kind)
+    if P > 1:
+        spec["noise_coreg"]["kappa"] = [0.7, 1.4]
+    Xs = Xs[:M]
+    engine.set_train(X, y)
+    engine.set_kernel(spec)
+    engine.factorize()
+    L0, v0 = orc.factorize(spec, X, y)
+    for noise in (False, True):
+        mu, cov = engine.predict_full(Xs, noise)
+        mu0, cov0 = orc.conditional_full(spec, X, L0, v0, Xs, noise)
+        np.testing.assert_allclose(mu, mu0, rtol=1e-7, atol=1e-9)
+        np.testing.assert_allclose(cov, cov0, rtol=1e-7, atol=1e-9)
+        assert np.array_equal(cov, cov.T) or np.max(np.abs(cov - cov.T)) < 1e-12
+        mu1, var1 = engine.predict(Xs, noise)
+        np.testing.assert_allclose(np.diag(cov), var1, rtol=1e-9, atol=1e-11)
+    # the factor survives (predict after predict_full)
+    mu2, _ = engine.predict(Xs[:3], True)
+    np.testing.assert_allclose(mu2, mu0[:3], rtol=1e-7, atol=1e-9)
