@@ -491,7 +491,6 @@ kbuild_strip_kernel(KParams kp, const double* __restrict__ Fi, int64_t stride_i,
     const int d = T.d, ka = kb2_ka(d);
     // (Tried and measured slower on B200, 0.117 vs 0.102 ms at C2: for d % 4 == 0, dropping the augmented DMMA k-step in favour of
     // two DADDs per entry and testing the exp range on the integer pipe.  The augmented form stays.)
-    const bool plain = false;
     const int kdot = ka;
     double* sA = reinterpret_cast<double*>(kb_smem);      // [ka][TS]
     double* sB = sA + ka * KB2_TS;                         // [2][ka][TS]
@@ -544,18 +543,6 @@ kbuild_strip_kernel(KParams kp, const double* __restrict__ Fi, int64_t stride_i,
         for (int mi = 0; mi < 2; mi++)
 #pragma unroll
             for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-        if (plain) {   // accumulators start from -|u_i|^2/2 - |u_j|^2/2 (row d of the row side, row d+1 of the column side)
-#pragma unroll
-            for (int mi = 0; mi < 2; mi++) {
-                const double hi_ = sA[d * KB2_TS + r0 + mi * 8 + g];
-#pragma unroll
-                for (int ni = 0; ni < 4; ni++) {
-                    const double2 hj = *reinterpret_cast<const double2*>(cB + (d + 1) * KB2_TS + c0 + ni * 8 + 2 * t4);
-                    acc[mi][ni][0] = hi_ + hj.x;
-                    acc[mi][ni][1] = hi_ + hj.y;
-                }
-            }
-        }
         for (int kk = 0; kk < kdot; kk += 4) {
             const double* pa = sA + (kk + t4) * KB2_TS + r0 + g;
             const double* pb = cB + (kk + t4) * KB2_TS + c0 + g;
