@@ -72,6 +72,14 @@ def main():
         # (tf32 + shard_storage: the sharded solve is fp64 while the single-GPU reference solve is split-TF32)
         ok &= rec["pred_max_abs_diff"] < (1e-8 if not (shard and prec == "tf32") else 2e-2)
         rec["pred_ms"] = eng.timings()["solve_ms"] + eng.timings()["kstar_ms"] + eng.timings()["reduce_ms"]
+        if not shard and prec == "fp64" and len(y) <= 4096:
+            # find_MAP's objective on a sharded factorisation: every rank holds the complete factor, so the gradient is computed
+            # redundantly and must equal the single-GPU one
+            val_s, g_s = eng.mll_grad(spec)
+            val_1, g_1 = ref.mll_grad(spec)
+            rec["mll_grad_max_abs_diff"] = float(max(abs(val_s - val_1), abs(g_s["sigma"] - g_1["sigma"]),
+                                                     np.max(np.abs(np.asarray(g_s["terms"][0]["ls"]) - np.asarray(g_1["terms"][0]["ls"])))))
+            ok &= rec["mll_grad_max_abs_diff"] < 1e-9 * max(1.0, abs(g_1["sigma"]))
         if with_oracle and rank == 0 and len(y) <= 4096:
             from oracle import gp_oracle as orc
 
