@@ -215,8 +215,26 @@ def _time_potrf(orc, spec, X, y):
 # ------------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------------
+def ensure_built():
+    """The CUDA library is built in-tree by __graft_entry__.build(); build it here only if it is missing (nvcc, sm_100a)."""
+    from gumbi_b200 import _lib
+
+    if not os.path.exists(_lib.lib_path()):
+        import __graft_entry__ as ge
+
+        if int(os.environ.get("LOCAL_RANK", 0)) == 0:
+            ge.build()
+        else:   # another rank of the same node is compiling: wait for the file
+            for _ in range(600):
+                if os.path.exists(_lib.lib_path()):
+                    break
+                time.sleep(0.5)
+
+
 def run_ours(args):
     import torch
+
+    ensure_built()
 
     rank, local_rank, world = dist_env()
     if not torch.cuda.is_available():
