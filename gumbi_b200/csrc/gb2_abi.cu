@@ -245,7 +245,7 @@ int predict_common(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_nois
                                                                                      nullptr, h->dAt, Np, 1, 0);
         else
             kbuild_dmma_launch<false>(s, grid, kbuild_dmma_smem_bytes(h->kp), h->kp, h->dBtab, h->dFs, h->dCs, Mp, Mc, h->dF, h->dC, Np, N, nullptr,
-                                      h->dAt, Np, 1, 0);
+                                      h->dAt, Np, 1, 0, 0, h->opt_kbuild_occ);
         GB2_CUDA(h, cudaEventRecord(h->ev[2], s));
         launches += 2;
         if (tf32) trsm_rec_tf32(h, s, Mp, 0, ncols, ncols, h->opt_tf32_leaf, launches);
@@ -623,7 +623,7 @@ static int build_K(gb2_handle* h, int& launches) {
                                                                                 h->dA, Np, h->world, h->rank);
     else
         kbuild_dmma_launch<true>(s, grid, kbuild_dmma_smem_bytes(h->kp), h->kp, h->dBtab, h->dF, h->dC, Np, N, h->dF, h->dC, Np, N, h->dy, h->dA, Np,
-                                 h->world, h->rank, h->compact ? 1 : 0);
+                                 h->world, h->rank, h->compact ? 1 : 0, h->opt_kbuild_occ);
     GB2_CUDA(h, cudaEventRecord(h->ev[2], s));
     launches += 2;
     return 0;
@@ -966,6 +966,11 @@ int gb2_set_option(gb2_handle* h, const char* name, int value) {
         return 0;
     }
     if (!strcmp(name, "fastdiag")) { h->opt_fastdiag = value ? 1 : 0; return 0; }   // ablation: Cholesky critical-path fast path
+    if (!strcmp(name, "kbuild_occ")) {   // register bound of the strip K-build: 3 or 4 resident CTAs per SM
+        GB2_ARG(h, value == 3 || value == 4, "kbuild_occ must be 3 or 4");
+        h->opt_kbuild_occ = value;
+        return 0;
+    }
     if (!strcmp(name, "kbuild_v1")) { h->opt_kbuild_v1 = value ? 1 : 0; h->factorized = false; return 0; }   // ablation: scalar-FMA + libm exp K-build
     if (!strcmp(name, "tf32_nb")) {   // panel width of the GB2_TF32 factorisation / leaf width of its solve, in 128-column blocks
         GB2_ARG(h, value >= 0 && value <= 16, "tf32_nb must be in [0, 16] (0 = auto)");

@@ -475,8 +475,9 @@ __device__ __forceinline__ double exp_tab_scaled(double x, const double* __restr
     return x < -700.0 ? 0.0 : sc;
 }
 
-template <bool TRAIN, int KIND>
-__global__ void __launch_bounds__(KB_THREADS, 3)
+// OCC = resident CTAs per SM the register allocation is bounded for (3: 78 registers, 4: 64 registers, a few bytes of spill)
+template <bool TRAIN, int KIND, int OCC>
+__global__ void __launch_bounds__(KB_THREADS, OCC)
 kbuild_strip_kernel(KParams kp, const double* __restrict__ Fi, int64_t stride_i, int64_t n_i, const double* __restrict__ Fj,
                     int64_t stride_j, int64_t n_j, int n_col_tiles, const double* __restrict__ y, double* __restrict__ out, int64_t ld,
                     int own_stride, int own_rank, int compact) {
@@ -614,19 +615,19 @@ inline size_t kbuild_strip_smem_bytes(const KParams& kp) { return (size_t)(3 * k
 template <bool TRAIN>
 inline void kbuild_dmma_launch(cudaStream_t s, dim3 grid, size_t smem, const KParams& kp, const double* Btab, const double* Fi, const int* Ci,
                                int64_t stride_i, int64_t n_i, const double* Fj, const int* Cj, int64_t stride_j, int64_t n_j, const double* y,
-                               double* out, int64_t ld, int own_stride, int own_rank, int compact = 0) {
+                               double* out, int64_t ld, int own_stride, int own_rank, int compact = 0, int occ = 4) {
     // (the strip kernel's prefetch pipeline walks consecutive column tiles; the column-sharded K* build uses the per-tile kernel)
     const bool simple = kp.n_terms == 1 && kp.t[0].n_lin == 0 && kp.t[0].n_coreg == 0 && kp.noise_cat < 0 && (TRAIN || !compact);
     if (simple && (kp.t[0].kind == GB2_EXPQUAD || kp.t[0].kind == GB2_MATERN52)) {
         // grid: x = strips of KB3_JG column tiles, y = row tiles
         dim3 sgrid((grid.x + KB3_JG - 1) / KB3_JG, grid.y);
         const size_t ssm = kbuild_strip_smem_bytes(kp);
-        if (kp.t[0].kind == GB2_EXPQUAD)
-            kbuild_strip_kernel<TRAIN, GB2_EXPQUAD><<<sgrid, KB_THREADS, ssm, s>>>(kp, Fi, stride_i, n_i, Fj, stride_j, n_j, (int)grid.x, y, out, ld,
-                                                                                  own_stride, own_rank, compact);
-        else
-            kbuild_strip_kernel<TRAIN, GB2_MATERN52><<<sgrid, KB_THREADS, ssm, s>>>(kp, Fi, stride_i, n_i, Fj, stride_j, n_j, (int)grid.x, y, out, ld,
-                                                                                   own_stride, own_rank, compact);
+#define GB2_STRIP(KIND, OCC)                                                                                                          \
+    kbuild_strip_kernel<TRAIN, KIND, OCC><<<sgrid, KB_THREADS, ssm, s>>>(kp, Fi, stride_i, n_i, Fj, stride_j, n_j, (int)grid.x, y, out, ld, \
+                                                                         own_stride, own_rank, compact)
+        if (kp.t[0].kind == GB2_EXPQUAD) { if (occ == 3) GB2_STRIP(GB2_EXPQUAD, 3); else GB2_STRIP(GB2_EXPQUAD, 4); }
+        else { if (occ == 3) GB2_STRIP(GB2_MATERN52, 3); else GB2_STRIP(GB2_MATERN52, 4); }
+#undef GB2_STRIP
         return;
     }
 #define GB2_KB_LAUNCH(KIND, SIMPLE)                                                                                             \
@@ -639,8 +640,10 @@ inline void kbuild_dmma_launch(cudaStream_t s, dim3 grid, size_t smem, const KPa
 template <bool TRAIN>
 inline cudaError_t kbuild_dmma_configure() {
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(kbuild_strip_kernel<TRAIN, GB2_EXPQUAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(kbuild_strip_kernel<TRAIN, GB2_MATERN52>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(kbuild_strip_kernel<TRAIN, GB2_EXPQUAD, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(kbuild_strip_kernel<TRAIN, GB2_MATERN52, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(kbuild_strip_kernel<TRAIN, GB2_EXPQUAD, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(kbuild_strip_kernel<TRAIN, GB2_MATERN52, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(kbuild_dmma_kernel<TRAIN, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
 }
 
