@@ -14,7 +14,9 @@
  *     on the handle's device and are ordered on the handle's stream (they return after the stream
  *     has drained unless documented otherwise).
  *   - the caller owns every buffer it passes; the handle owns all device memory it allocates.
- *   - one handle = one GPU = one pair of CUDA streams; handles share no mutable global state.
+ *   - one handle = one GPU = one pair of CUDA streams; a handle is not re-entrant, different handles may be driven from different
+ *     threads.  Process-wide state is limited to the error text of a failed gb2_create / gb2_nccl_unique_id (handle == NULL in
+ *     gb2_last_error) and the NCCL function table bound by the first multi-GPU call.
  *   - matrices are C-contiguous (row-major) float64, indices int32, exactly as numpy hands them
  *     over from Regressor.get_shaped_data (gumbi/regression/base.py:435-471).
  */
