@@ -100,3 +100,58 @@ def test_sharded_cholesky_matches_single_gpu(mode):
            "--master-port", "29541", os.path.join(ROOT, "tools", "dist_check.py"), "1000", "3000"]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert res.returncode == 0 and "DIST_CHECK OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+BACKEND_WORKER = r"""
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+from conftest import load_golden
+from test_backend_host import HostGP, OracleEngine, gp_from_golden
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+
+class DistDouble(OracleEngine):
+    # engine double that looks like a rank of a replicated-factor job (every rank holds the factor, serves a grid slice)
+    world = {world}
+    rank = rank
+    shard_storage = False
+    calls = []
+    def predict(self, Xs, pred_noise=True):
+        self.calls.append(len(Xs))
+        return super().predict(Xs, pred_noise)
+
+g = load_golden("multioutput_regression")
+gp = gp_from_golden(g)
+gp.engine = DistDouble()
+gp.engine.set_train(gp._X, gp._y)
+gp.find_MAP(point=g["meta"]["point"])
+mu, var = gp.predict(g["points"], with_noise=True)
+# every rank gets the FULL result, computed from its own slice only
+from gumbi_b200 import dist as gdist
+lo, hi = gdist.grid_slice(len(g["points"]), rank, world)
+assert gp.engine.calls == [hi - lo], (gp.engine.calls, lo, hi)
+np.testing.assert_allclose(mu, g["mean"], rtol=1e-9, atol=1e-11)
+np.testing.assert_allclose(var, g["var"], rtol=1e-8, atol=1e-11)
+# storage-sharded engines predict collectively over all points: no slicing, no gather
+gp.engine.shard_storage = True
+gp.engine.calls.clear()
+mu2, _ = gp.predict(g["points"], with_noise=True)
+assert gp.engine.calls == [len(g["points"])]
+np.testing.assert_allclose(mu2, g["mean"], rtol=1e-9, atol=1e-11)
+dist.barrier(); dist.destroy_process_group()
+print("BACKEND_WORKER_OK", rank)
+"""
+
+
+def test_backend_predict_slices_and_gathers_over_gloo(tmp_path):
+    """B200Backend.predict on a 2-rank job: each rank solves its grid slice, the gathered result is the full golden posterior."""
+    script = tmp_path / "bworker.py"
+    script.write_text(BACKEND_WORKER.format(root=ROOT, world=2))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29535", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"BACKEND_WORKER_OK {r}" in o, o[-3000:]
