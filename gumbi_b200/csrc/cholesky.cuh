@@ -592,18 +592,25 @@ inline int factor_steps(gb2_handle* h, int k0, int k1, int col_limit) {
                 panel_pack_kernel<<<dim3(cmax * G, TILE / 8), 256, 0, sp>>>(A, ld, g0, h->dRecv, 1, G, me, nb, k, cmax, -1);
                 launches += 2;
             }
+            // Stream choreography (opt_chain_on_panel, default): the chain  diag -> panel solve -> next-column update -> next diag
+            // stays on the panel stream in program order; only the bulk update goes to the main stream.  Two event edges per
+            // step remain (panel complete -> main; bulk update k-1 done -> next-column update k, normally long satisfied), and
+            // neither sits between two kernels of the chain.  (The older schedule, next-column update on the main stream, put two
+            // cross-stream hops of ~10 us each on the chain of every block step.)
+            const bool chain = two && h->opt_chain_on_panel;
             if (two) {
                 cudaEvent_t e = pool_event(h, 2 * k);
                 cudaEventRecord(e, sp);
                 cudaStreamWaitEvent(sm, e, 0);
             }
+            if (chain && k > k0) cudaStreamWaitEvent(sp, pool_event(h, 2 * (k - 1) + 1), 0);   // bulk update k-1 touched column k+1
             // next panel column first: A[i, k+1] -= L[i,k] L[k+1,k]^T for owned i >= k+1
             if (c1 > 0 && k + 1 < col_limit) {
-                dgemm_nt_launch<128, 64, GM_SUB>(sm, colk, ld, A + (g0 + TILE) * ld + g0, ld, A + g0 + TILE, ld, (int64_t)c1 * TILE, TILE,
-                                                 TILE, 1, 0, g0 + TILE, f1, G);
+                dgemm_nt_launch<128, 64, GM_SUB>(chain ? sp : sm, colk, ld, A + (g0 + TILE) * ld + g0, ld, A + g0 + TILE, ld, (int64_t)c1 * TILE,
+                                                 TILE, TILE, 1, 0, g0 + TILE, f1, G);
                 launches++;
             }
-            if (two) {
+            if (two && !chain) {
                 cudaEvent_t e = pool_event(h, 2 * k + 1);
                 cudaEventRecord(e, sm);
                 cudaStreamWaitEvent(sp, e, 0);
@@ -618,6 +625,7 @@ inline int factor_steps(gb2_handle* h, int k0, int k1, int col_limit) {
                     launches++;
                 }
             }
+            if (chain) cudaEventRecord(pool_event(h, 2 * k + 1), sm);   // bulk update k done (or nothing to do)
         }
     }
     if (two) {  // join
@@ -744,17 +752,21 @@ inline int factor_steps_compact(gb2_handle* h, int k0, int k1, int col_limit, in
                 h->dPlo + (int64_t)col_limit * TILE * pld + (int64_t)(k - split_c0) * TILE, pld);
             launches++;
         }
+        const bool chain = h->opt_chain_on_panel != 0;   // see factor_steps: the next-column update stays on the panel stream
         cudaEvent_t e0 = pool_event(h, 2 * k);
         cudaEventRecord(e0, sp);
         cudaStreamWaitEvent(sm, e0, 0);
+        if (chain && k > k0) cudaStreamWaitEvent(sp, pool_event(h, 2 * (k - 1) + 1), 0);
         if (c1 > 0 && k + 1 < col_limit) {   // next column first
-            dgemm_nt_launch<128, 64, GM_SUB>(sm, colk, ld, Pk + (g0 + TILE) * TILE, TILE, A + g0 + TILE, ld, (int64_t)c1 * TILE, TILE, TILE, 1, 0,
-                                             g0 + TILE, f1, G, nullptr, l1);
+            dgemm_nt_launch<128, 64, GM_SUB>(chain ? sp : sm, colk, ld, Pk + (g0 + TILE) * TILE, TILE, A + g0 + TILE, ld, (int64_t)c1 * TILE, TILE,
+                                             TILE, 1, 0, g0 + TILE, f1, G, nullptr, l1);
             launches++;
         }
-        cudaEvent_t e1 = pool_event(h, 2 * k + 1);
-        cudaEventRecord(e1, sm);
-        cudaStreamWaitEvent(sp, e1, 0);
+        if (!chain) {
+            cudaEvent_t e1 = pool_event(h, 2 * k + 1);
+            cudaEventRecord(e1, sm);
+            cudaStreamWaitEvent(sp, e1, 0);
+        }
         if (k + 2 < col_limit) {
             const int f2 = first_owned_after(k + 1, me), c2 = count_from(f2);
             if (c2 > 0) {
@@ -763,6 +775,7 @@ inline int factor_steps_compact(gb2_handle* h, int k0, int k1, int col_limit, in
                 launches++;
             }
         }
+        if (chain) cudaEventRecord(pool_event(h, 2 * k + 1), sm);   // bulk update k done
     }
     cudaEvent_t e = pool_event(h, 3 * nb + 3);
     cudaEventRecord(e, sp);

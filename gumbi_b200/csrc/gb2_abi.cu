@@ -966,6 +966,7 @@ int gb2_set_option(gb2_handle* h, const char* name, int value) {
         return 0;
     }
     if (!strcmp(name, "fastdiag")) { h->opt_fastdiag = value ? 1 : 0; return 0; }   // ablation: Cholesky critical-path fast path
+    if (!strcmp(name, "chain_on_panel")) { h->opt_chain_on_panel = value ? 1 : 0; return 0; }   // ablation: Cholesky stream choreography
     if (!strcmp(name, "kbuild_occ")) {   // register bound of the strip K-build: 3 or 4 resident CTAs per SM
         GB2_ARG(h, value == 3 || value == 4, "kbuild_occ must be 3 or 4");
         h->opt_kbuild_occ = value;
