@@ -99,11 +99,31 @@ class ClockSampler:
 
 
 def measured_peaks():
+    """Roofline denominators: MEASURED_PEAKS.json (driver-written) when present, else the B200_PROFILING.md fallback; says which."""
+    fb = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        d = json.load(open(p))
-        return {"hbm_gbs": d.get("hbm_gbs"), "bf16_tflops": d.get("bf16_tflops"), "source": "MEASURED_PEAKS.json (measured)"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "B200_PROFILING.md fallback"}
+        try:
+            d = json.load(open(p))
+        except Exception:
+            d = {}
+
+        def find(keys):
+            for k in keys:
+                v = d.get(k)
+                if isinstance(v, dict):
+                    v = v.get("value", v.get("burst"))
+                if isinstance(v, (int, float)) and v > 0:
+                    return float(v)
+            return None
+
+        hbm = find(["hbm_gbs", "hbm_gb_s", "hbm_copy_gbs"])
+        bf16 = find(["bf16_tflops", "bf16_tflops_burst", "bf16_tf"])
+        if hbm and bf16:
+            return {"hbm_gbs": hbm, "bf16_tflops": bf16, "source": "MEASURED_PEAKS.json (measured)"}
+        return {"hbm_gbs": hbm or fb["hbm_gbs"], "bf16_tflops": bf16 or fb["bf16_tflops"],
+                "source": "MEASURED_PEAKS.json where it has the entry, B200_PROFILING.md fallback otherwise"}
+    return {**fb, "source": "B200_PROFILING.md fallback"}
 
 
 def measured_traffic(key):
