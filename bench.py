@@ -152,6 +152,27 @@ def cublas_dgemm_peak(torch, dev):
     return 2 * n ** 3 / best / 1e9
 
 
+def live_copy_bandwidth(torch, dev):
+    """STREAM-style device copy (read + write bytes / time), 2 GiB, best of 5 -- context for the HBM roofline when
+    MEASURED_PEAKS.json is absent; never replaces the contract's denominator."""
+    try:
+        n = (1 << 31) // 8
+        a = torch.empty(n, dtype=torch.float64, device=dev).normal_()
+        b = torch.empty_like(a)
+        b.copy_(a)
+        torch.cuda.synchronize(dev)
+        best = 1e30
+        for _ in range(5):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); b.copy_(a); e1.record(); torch.cuda.synchronize(dev)
+            best = min(best, e0.elapsed_time(e1))
+        del a, b
+        torch.cuda.empty_cache()
+        return 2.0 * n * 8 / (best * 1e-3) / 1e9
+    except Exception:
+        return None
+
+
 def make_workload(name):
     from gumbi_b200.synthetic import synthetic_problem
 
@@ -423,6 +444,7 @@ def run_ours(args):
     # ---- rooflines ---------------------------------------------------------------------------------------------------
     peaks = measured_peaks()
     dgemm_peak = cublas_dgemm_peak(torch, dev)
+    copy_gbs = live_copy_bandwidth(torch, dev)
     Ml = hi - lo
     kb_bytes = 8.0 * N * (N + 1) / 2 + 8.0 * N * D_in
     kb_gbs = kb_bytes / world / (phase["kbuild_ms"] * 1e-3) / 1e9
@@ -455,7 +477,9 @@ def run_ours(args):
                      "frac": chol_tflops / dgemm_peak, "algorithmic_flop_per_step": N ** 3 / 3,
                      "peak_source": "cuBLAS DGEMM 8192^3 burst measured live in this run"}
     roofline_kb = {"kernel": "kbuild_kernel<train>", "bound": "hbm", "achieved": kb_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                   "frac": kb_gbs / peaks["hbm_gbs"], "peak_source": peaks["source"], "algorithmic_bytes_per_launch": kb_bytes / world, "traffic": None}
+                   "frac": kb_gbs / peaks["hbm_gbs"], "peak_source": peaks["source"], "algorithmic_bytes_per_launch": kb_bytes / world, "traffic": None,
+                   "device_copy_gbs_measured_live": copy_gbs, "frac_of_live_copy": (kb_gbs / copy_gbs) if copy_gbs else None,
+                   "note": "fp64-pipe bound on B200 (DESIGN.md section 3): DMMA Gram + table-driven exp need ~24 fp64 issue slots per entry"}
 
     # ---- CPU baseline on the host cores (bounded: one full cold call) ---------------------------------------------
     cpu = None
