@@ -476,7 +476,7 @@ def run_ours(args):
                      "bound": "tensor", "achieved": chol_tflops, "peak": dgemm_peak, "unit": "TFLOP/s (fp64-equivalent N^3/3)",
                      "frac": chol_tflops / dgemm_peak, "algorithmic_flop_per_step": N ** 3 / 3,
                      "peak_source": "cuBLAS DGEMM 8192^3 burst measured live in this run"}
-    roofline_kb = {"kernel": "kbuild_kernel<train>", "bound": "hbm", "achieved": kb_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+    roofline_kb = {"kernel": "kbuild_strip_kernel<TRAIN> (single stationary term) / kbuild_dmma_kernel (Linear, Coregion, additive models)", "bound": "hbm", "achieved": kb_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                    "frac": kb_gbs / peaks["hbm_gbs"], "peak_source": peaks["source"], "algorithmic_bytes_per_launch": kb_bytes / world, "traffic": None,
                    "device_copy_gbs_measured_live": copy_gbs, "frac_of_live_copy": (kb_gbs / copy_gbs) if copy_gbs else None,
                    "note": "fp64-pipe bound on B200 (DESIGN.md section 3): DMMA Gram + table-driven exp need ~24 fp64 issue slots per entry"}
