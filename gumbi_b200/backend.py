@@ -257,7 +257,8 @@ class B200Backend:
     def _ensure_factorized(self):
         if self.MAP is None:
             raise RuntimeError("predict called before find_MAP/fit")
-        key = id(self.MAP)
+        # fingerprint of the hyper-parameter VALUES (a MAP dict edited in place must trigger a new factorisation)
+        key = hash(tuple((k, np.asarray(v, dtype=np.float64).tobytes()) for k, v in sorted(self.MAP.items()) if not k.endswith("_log__")))
         if self._factor_key != key:
             self.engine.set_kernel(self.spec_from_point(self.MAP))
             self.engine.factorize()

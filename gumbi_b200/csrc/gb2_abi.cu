@@ -648,6 +648,16 @@ int gb2_factorize(gb2_handle* h) {
     h->timings[1] = ms_between(h->ev[1], h->ev[2]);
     h->timings[2] = ms_between(h->ev[2], h->ev[3]);
     h->timings[6] = launches;
+    if (h->world > 1) {
+        // the first failing pivot is only known to the rank that owns its diagonal block: agree on one verdict, otherwise some ranks
+        // would raise while the others walk into the next collective.  Encoded so that "smallest positive pivot" is a minimum.
+        // one integer per rank: 1 = bad level index, pivot + 1 = first failing pivot, INT_MAX = fine
+        const int mine = info[1] != 0 ? 1 : (info[0] > 0 ? info[0] + 1 : 0x7fffffff);
+        int agreed = 0, rcq;
+        if ((rcq = dist_min_int(h, mine, &agreed))) return rcq;
+        info[1] = agreed == 1 ? 1 : 0;
+        info[0] = (agreed > 1 && agreed != 0x7fffffff) ? agreed - 1 : 0;
+    }
     GB2_ARG(h, info[1] == 0, "a Coregion column of X holds a level index outside [0, P)");
     if (info[0] != 0) {
         h->err = "matrix is not positive definite: leading minor of order " + std::to_string(info[0]);

@@ -89,6 +89,24 @@ def main():
         out.append(rec)
         if rank == 0:
             print(json.dumps(rec), flush=True)
+    # a non-positive-definite matrix: every rank must raise, and report the SAME pivot (the owner of the failing block knows it,
+    # the verdict is agreed collectively inside gb2_factorize)
+    spec, X, y, Xs = synthetic_problem(600, 2)
+    spec["sigma"] = 0.0
+    spec["jitter"] = 0.0
+    X[450] = X[140]
+    eng.set_train(X, y); eng.set_kernel(spec)
+    try:
+        eng.factorize()
+        msg = "no error"
+    except np.linalg.LinAlgError as e:
+        msg = str(e)
+    msgs = [None] * world
+    dist.all_gather_object(msgs, msg)
+    same = all(m == msgs[0] for m in msgs) and "not positive definite" in msgs[0]
+    if rank == 0:
+        print(json.dumps({"non_pd_verdict_identical_on_all_ranks": same, "message": msgs[0]}), flush=True)
+    ok &= same
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
