@@ -77,17 +77,30 @@ def parse_ls_limits(X, ARD=True, lower=None, upper=None):
     return lowers, uppers
 
 
-def find_constrained_invgamma(lower, upper, mass=0.98):
+def find_constrained_invgamma(lower, upper, mass=0.98, exact=False):
     """``pm.find_constrained_prior(pm.InverseGamma, lower, upper, init_guess={alpha: lower, beta: upper}, mass)``.
 
-    PyMC poses: minimise (CDF(lower) - (1-mass)/2)^2 subject to CDF(upper) - CDF(lower) = mass, and hands it to SciPy's
-    SLSQP.  Both conditions can be met exactly, so the optimum is the root of a two-equation system; because beta is a
-    pure scale parameter it reduces to one monotone equation in alpha (the quantile ratio q_hi/q_lo of InvGamma(alpha, 1)
-    must equal upper/lower), solved here by bracketing.  Raises ValueError('Optimization of parameters failed') like
-    PyMC when no solution exists."""
+    PyMC poses: minimise (CDF(lower) - (1-mass)/2)^2 subject to CDF(upper) - CDF(lower) = mass, and hands it to
+    ``scipy.optimize.minimize`` with a ``NonlinearConstraint`` (-> SLSQP) started at [lower, upper].  What the reference actually
+    gets is NOT the exact optimum: the objective is at most 1e-4 in magnitude, so SLSQP meets the mass constraint in a few
+    steps and declares convergence with CDF(lower) ~ 0 (e.g. lower=0.01, upper=3.5: alpha=4.07, beta=3.68, whereas the exact
+    solution of both conditions is alpha=1.06, beta=0.047 -- a prior with its mode 30x lower).  Parity with the reference means
+    reproducing that, so the same SciPy call is made here (``exact=True`` solves both conditions instead: beta is a pure scale,
+    which leaves one monotone equation in alpha).  Raises ValueError('Optimization of parameters failed') like PyMC."""
     if not (0 < lower < upper) or not (0 < mass < 1):
         raise ValueError("Optimization of parameters failed.")
     tail = (1.0 - mass) / 2.0
+    if not exact:
+        def cdf(p, x):
+            return stats.invgamma.cdf(x, p[0], scale=p[1]) if p[0] > 0 and p[1] > 0 else np.nan
+
+        cons = optimize.NonlinearConstraint(lambda p: cdf(p, upper) - cdf(p, lower), lb=mass, ub=mass)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            opt = optimize.minimize(lambda p: (cdf(p, lower) - tail) ** 2, x0=[lower, upper], constraints=cons)
+        if not opt.success or not np.all(np.isfinite(opt.x)) or np.any(opt.x <= 0):
+            raise ValueError("Optimization of parameters failed.")
+        return {"alpha": float(opt.x[0]), "beta": float(opt.x[1])}
     target = np.log(upper / lower)
 
     def ratio(log_a):

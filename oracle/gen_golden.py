@@ -215,5 +215,50 @@ def main():
     dump("test_dataset_filtered", gp, point, points_array, {})
 
 
+def notebook_fixture():
+    """tests/golden/notebook_simple_regression.npz: everything needed to replay docs/source/notebooks/examples/Simple_Regression
+    (script Simple_Regression.pct.py:33-63) WITHOUT gumbi: the shaped training arrays, the standardized prediction points and the
+    constants of the output transform -- plus the numbers the reference's own executed notebook shows (PyMC run by the author):
+    Simple_Regression.ipynb:192 (point prediction) and :230-234 (first 10 grid predictions)."""
+    sys.path.insert(0, ROOT)
+    gmb = import_reference()
+    import pandas as pd
+    from gumbi.regression.base import Regressor
+
+    from gumbi_b200.backend import B200Backend
+
+    class ShapeOnly(B200Backend, Regressor):
+        def __init__(self, dataset, outputs=None, seed=2021):
+            Regressor.__init__(self, dataset, outputs, seed)
+            self._init_backend()
+
+    df = pd.read_pickle(os.path.join(REF, "gumbi", "data", "Example_DataSet.pkl")).query('Metric=="mean"')
+    ds = gmb.DataSet(df, outputs=["a", "b", "c", "d", "e", "f"], log_vars=["Y", "b", "c", "d", "f"], logit_vars=["X", "e"])
+    ds.tidy = ds.tidy[ds.tidy.Color.isin(["cyan", "magenta"]) & (ds.tidy.Pair == "burrata+barbaresco")]
+    gp = ShapeOnly(ds, outputs=["d"])
+    gp.specify_model(continuous_dims=["X", "Y", "lg10_Z"], linear_dims=["X", "Y", "lg10_Z"])
+    X, y = gp.get_shaped_data("mean")
+    out = gp._parse_prediction_output(None)
+    pt, _, _ = gp._prepare_points_for_prediction(gp.parray(lg10_Z=8, X=0.5, Y=88), output=out)
+    gp.prepare_grid(at=gp.parray(lg10_Z=8, X=0.5))
+    grid, _, _ = gp._prepare_points_for_prediction(gp.grid_points, output=out)
+    mu_d, s2_d = float(gp.stdzr["d"]["μ"]), float(gp.stdzr["d"]["σ2"])
+    expected_point = np.array([0.7526282, 0.00204789])                                      # Simple_Regression.ipynb:192
+    expected_grid = np.array([[0.95353955, 0.02777067], [0.94923129, 0.02648205], [0.94544874, 0.02492182], [0.94220088, 0.02307904],
+                              [0.93948256, 0.02096868], [0.93727268, 0.01863859], [0.93553307, 0.01617249], [0.93420812, 0.01368664],
+                              [0.93322533, 0.01131927], [0.93249681, 0.009213]])           # Simple_Regression.ipynb:230-234
+    meta = {"continuous_dims": ["X", "Y", "lg10_Z"], "linear_dims": ["X", "Y", "lg10_Z"], "output": "d", "output_transform": "log",
+            "stdzr_mu": mu_d, "stdzr_sigma2": s2_d, "seed": 2021,
+            "source": "docs/source/notebooks/examples/Simple_Regression.ipynb:192,230-234 (reference commit 27bdbee)",
+            "post_processing": "mu_natural = exp(mu_z*sqrt(sigma2) + mu); sigma2_reported = var_z*sigma2  (base.py:580, aggregation.py:469-485)"}
+    np.savez_compressed(os.path.join(OUT, "notebook_simple_regression.npz"), X=X, y=y, point=pt, grid=grid[:10], expected_point=expected_point,
+                        expected_grid=expected_grid, meta=np.asarray(json.dumps(meta, ensure_ascii=False)))
+    print("notebook_simple_regression: X", X.shape, "stdzr d", mu_d, s2_d)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "notebook":
+        notebook_fixture()
+    else:
+        main()
+        notebook_fixture()
