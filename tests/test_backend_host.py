@@ -164,10 +164,16 @@ def test_ls_prior_matches_pdist_definition_and_mass():
     d = pdist(X)
     d = d[d != 0]
     assert lo1 == [pytest.approx(max(d.min(), 0.01))] and hi1 == [pytest.approx(d.max())]
+    # default = what the reference gets from PyMC: SciPy's SLSQP meets the mass constraint and stops (objective <= 1e-4), so the
+    # lower tail is NOT 1 %; exact=True solves both conditions
     p = find_constrained_invgamma(0.1, 5.0, mass=0.98)
     cdf = lambda x: stats.invgamma.cdf(x, p["alpha"], scale=p["beta"])
     assert cdf(5.0) - cdf(0.1) == pytest.approx(0.98, abs=1e-4)
-    assert cdf(0.1) == pytest.approx(0.01, abs=2e-3)
+    assert cdf(0.1) < 1e-6 and p["alpha"] == pytest.approx(3.8958, rel=1e-3) and p["beta"] == pytest.approx(4.8302, rel=1e-3)
+    p = find_constrained_invgamma(0.1, 5.0, mass=0.98, exact=True)
+    cdf = lambda x: stats.invgamma.cdf(x, p["alpha"], scale=p["beta"])
+    assert cdf(5.0) - cdf(0.1) == pytest.approx(0.98, abs=1e-6)
+    assert cdf(0.1) == pytest.approx(0.01, abs=1e-6)
 
 
 def test_find_map_objective_gradient_and_improvement():
