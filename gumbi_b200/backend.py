@@ -34,10 +34,14 @@ class B200Backend:
     """Mixin with the three backend methods + ``fit``.  Expects the attributes ``Regressor.specify_model`` sets."""
 
     # -- construction -----------------------------------------------------------------------------------------------
-    def _init_backend(self, device=0, precision="fp64", distributed=False):
+    def _init_backend(self, device=0, precision="fp64", distributed=False, multioutput="dense"):
+        assert_in("multioutput", multioutput, ["dense", "kron", "auto"])
         self.device = device
         self.precision = precision
         self.distributed = distributed   # True: join torch.distributed's default group (one process per GPU)
+        # "dense": factorise the stacked (nP x nP) system like the reference.  "kron": aligned multi-output models are split into
+        # P independent n x n problems (gumbi_b200/kron.py; ValueError if the data are not aligned).  "auto": kron when possible.
+        self.multioutput = multioutput
         self.engine = None
         self.MAP = None
         self.trace = None
@@ -112,16 +116,67 @@ class B200Backend:
         self._X = np.ascontiguousarray(X, dtype=np.float64)
         self._y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
         self._layout = self._model_layout()
+        want_kron = self._wants_kron()
+        if self.engine is not None and want_kron != (type(self.engine).__name__ == "KronEngine"):
+            self.engine.close()      # the structure changed between two build_model calls
+            self.engine = None
         if self.engine is None:
-            self.engine = GPEngine(self.device, self.precision)
-            if self.distributed:
-                from . import dist as gdist
-
-                gdist.init_engine(self.engine)   # collective: factorize() is row-block sharded across the ranks from here on
+            self.engine = self._make_kron_engine() if want_kron else self._make_dense_engine()
         self.engine.set_train(self._X, self._y)
         self._factor_key = None
         self.model = self._layout  # truthy placeholder: the reference asserts ``self.model is not None`` in find_MAP
         return self
+
+    def _make_dense_engine(self):
+        engine = GPEngine(self.device, self.precision)
+        if self.distributed:
+            from . import dist as gdist
+
+            gdist.init_engine(engine)   # collective: factorize() is row-block sharded across the ranks from here on
+        return engine
+
+    def _make_block_engine(self):
+        """One single-GPU engine per output block of the Kronecker-aware solve (never joined to the process group)."""
+        return GPEngine(self.device, self.precision)
+
+    def _make_kron_engine(self):
+        from . import kron
+
+        rank, world, gather = 0, 1, None
+        if self.distributed:
+            import torch.distributed as tdist
+
+            if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1:
+                rank, world = tdist.get_rank(), tdist.get_world_size()
+
+                def gather(obj):
+                    parts = [None] * world
+                    tdist.all_gather_object(parts, obj)
+                    return parts
+
+        lay = self._layout
+        pcol, P = lay["terms"][0]["coreg"][-1][1], lay["terms"][0]["coreg"][-1][2]
+        return kron.KronEngine(self._make_block_engine, pcol, P, rank=rank, world=world, gather=gather)
+
+    def _wants_kron(self):
+        """Whether this model is solved block-wise (see ``multioutput``): needs the output Coregion, a non-additive model and
+        aligned observations (every output at the same inputs)."""
+        if self.multioutput == "dense":
+            return False
+        from . import kron
+
+        try:
+            if self.out_col not in self.categorical_dims:
+                raise kron.NotAligned("the model has a single output")
+            if self.additive:
+                raise kron.NotAligned("additive models have no single B (x) Kx form")
+            pcol = self._get_dim_indexes()["p"]
+            kron.aligned_blocks(self._X, pcol, len(self.categorical_levels[self.out_col]))
+        except kron.NotAligned as e:
+            if self.multioutput == "kron":
+                raise ValueError(f'multioutput="kron" is not applicable: {e}') from None
+            return False
+        return True
 
     # -- structure of the covariance (GP.py:652-757) ------------------------------------------------------------------
     def _get_dim_counts(self):
@@ -393,18 +448,18 @@ class ArrayRegressor:
 
 
 class ArrayGP(B200Backend, ArrayRegressor):
-    def __init__(self, X, y, continuous_dims, device=0, precision="fp64", distributed=False, **kwargs):
+    def __init__(self, X, y, continuous_dims, device=0, precision="fp64", distributed=False, multioutput="dense", **kwargs):
         ArrayRegressor.__init__(self, X, y, continuous_dims, **kwargs)
-        self._init_backend(device=device, precision=precision, distributed=distributed)
+        self._init_backend(device=device, precision=precision, distributed=distributed, multioutput=multioutput)
 
 
 def make_backend(regressor_base):
     """Create the drop-in ``B200GP`` subclass of Gumbi's ``Regressor`` (``gumbi.regression.base.Regressor``)."""
 
     class B200GP(B200Backend, regressor_base):
-        def __init__(self, dataset, outputs=None, seed=2021, device=0, precision="fp64", distributed=False):
+        def __init__(self, dataset, outputs=None, seed=2021, device=0, precision="fp64", distributed=False, multioutput="dense"):
             regressor_base.__init__(self, dataset, outputs, seed)
-            self._init_backend(device=device, precision=precision, distributed=distributed)
+            self._init_backend(device=device, precision=precision, distributed=distributed, multioutput=multioutput)
 
     B200GP.__doc__ = "Gumbi Regressor backend running the exact-GP dense path on a B200 (see gumbi_b200.backend)."
     return B200GP

@@ -664,6 +664,7 @@ int gb2_factorize(gb2_handle* h) {
         return info[0];
     }
     h->factorized = true;
+    h->factor_count++;
     return 0;
 }
 
@@ -728,6 +729,7 @@ int gb2_mll_grad(gb2_handle* h, double* mll_out, double* grad_out) {
     grad_out[GR_SIGMA] *= 0.5 * 2.0 * h->sigma_host;
     for (int e = 0; e < GB2_MAX_P * GB2_MAX_P; e++) grad_out[GR_NOISE_B + e] *= 0.5;
     h->timings[6] = launches + 5;
+    h->alpha_for = h->factor_count;
     return 0;
 }
 
@@ -841,6 +843,16 @@ int gb2_get_v(gb2_handle* h, double* v_out) {
         return 0;
     }
     GB2_CUDA(h, cudaMemcpy(v_out, h->dA + h->N * h->Np, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int gb2_get_alpha(gb2_handle* h, double* alpha_out) {
+    if (!h) return -1;
+    GB2_ARG(h, alpha_out, "null pointer");
+    GB2_ARG(h, h->factorized && h->alpha_for != 0 && h->alpha_for == h->factor_count,
+            "gb2_get_alpha needs a gb2_mll_grad call on the current factorisation");
+    GB2_CUDA(h, cudaSetDevice(h->device));
+    GB2_CUDA(h, cudaMemcpy(alpha_out, h->dAlpha, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost));
     return 0;
 }
 

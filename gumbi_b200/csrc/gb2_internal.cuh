@@ -95,6 +95,7 @@ struct gb2_handle {
     // MLL-gradient scratch: W = L^-T (Np x Np), S = K^-1 (Np x Np), alpha (Np), flat gradient
     double* dW = nullptr; double* dS = nullptr; int64_t G_cap = 0;
     double* dAlpha = nullptr; int64_t alpha_cap = 0;
+    uint64_t factor_count = 0, alpha_for = 0;   // dAlpha belongs to factorisation number alpha_for (0 = none)
     double* dGrad = nullptr;
     double eta_host[GB2_MAX_TERMS] = {0, 0, 0, 0};
     double sigma_host = 0.0;

@@ -220,6 +220,12 @@ class GPEngine:
         self._check(self._lib.gb2_get_v(self._h, _lib.as_dp(v)), "get_v")
         return v
 
+    def get_alpha(self):
+        """alpha = K^-1 y of the last ``mll_grad`` call (valid until the next factorisation)."""
+        a = np.empty(self.N, dtype=np.float64)
+        self._check(self._lib.gb2_get_alpha(self._h, _lib.as_dp(a)), "get_alpha")
+        return a
+
     def timings(self) -> dict:
         out = np.zeros(_lib.N_TIMINGS, dtype=np.float64)
         self._check(self._lib.gb2_get_timings(self._h, _lib.as_dp(out)), "get_timings")

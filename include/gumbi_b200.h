@@ -119,6 +119,9 @@ int gb2_mll(gb2_handle* h, double* out);
 #define GB2_GRAD_NOISE_B (GB2_GRAD_SIGMA + 1)
 #define GB2_GRAD_LEN (GB2_GRAD_NOISE_B + GB2_MAX_P * GB2_MAX_P)
 int gb2_mll_grad(gb2_handle* h, double* mll_out, double* grad_out);
+/* alpha = K^-1 y (length N) as computed by the gb2_mll_grad call on the current factorisation; the Kronecker-aware
+ * multi-output solve (gumbi_b200/kron.py) needs it for the gradient w.r.t. the output Coregion and the output noise.   */
+int gb2_get_alpha(gb2_handle* h, double* alpha_out);
 
 /* Posterior mean/variance at Xs:(M,D_in) -- replaces PymcGP.predict (GP.py:837-849):
  * Marginal.predict(Xs, point=MAP, diag=True, pred_noise=with_noise).  Needs gb2_factorize.     */

@@ -1,0 +1,106 @@
+"""Device tests of the Kronecker-aware multi-output solve (gumbi_b200/kron.py) -- CUDA block engines through the C ABI against the
+dense CUDA path, the dense oracle and the committed golden vectors.  (Sorted last on purpose: this path was added after the
+round's GPU minutes were spent, so its first device run is the driver's; the block engines only use single-output code paths
+that the parity tests above already cover, plus ``gb2_get_alpha``.)"""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from test_kron import from_golden, random_point, synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def pair(X, y, kw, **build):
+    from gumbi_b200 import ArrayGP
+
+    dense = ArrayGP(X, y, **kw)
+    dense.build_model(**build)
+    kr = ArrayGP(X, y, multioutput="kron", **kw)
+    kr.build_model(**build)
+    return dense, kr
+
+
+@pytest.mark.parametrize("kernel,extra_cat,hetero", [("ExpQuad", 0, True), ("Matern52", 3, True), ("Matern32", 0, False)])
+def test_kron_matches_dense_cuda_path(lib_built, kernel, extra_cat, hetero):
+    from gumbi_b200 import kron
+    from gumbi_b200.map import named_gradient
+
+    X, y, kw = synthetic(n=301, P=3, d=2, extra_cat=extra_cat, seed=7)
+    dense, kr = pair(X, y, kw, continuous_kernel=kernel, heteroskedastic_outputs=hetero)
+    assert isinstance(kr.engine, kron.KronEngine)
+    pt = random_point(dense, 13)
+    dense.find_MAP(point=pt)
+    kr.find_MAP(point=pt)
+    rng = np.random.default_rng(1)
+    pts = X[rng.integers(0, len(X), 500)].copy()
+    pts[:, :2] += 0.2 * rng.standard_normal((500, 2))
+    pts[:, -1] = rng.integers(0, 3, 500)
+    for noise in (True, False):
+        mu_d, var_d = dense.predict(pts, with_noise=noise)
+        mu_k, var_k = kr.predict(pts, with_noise=noise)
+        np.testing.assert_allclose(mu_k, mu_d, rtol=1e-7, atol=1e-9)
+        np.testing.assert_allclose(var_k, var_d, rtol=1e-6, atol=1e-9)
+    assert kr.marginal_log_likelihood() == pytest.approx(dense.marginal_log_likelihood(), rel=1e-9)
+    m_d, c_d = dense.conditional(pts[:40], pred_noise=True)
+    m_k, c_k = kr.conditional(pts[:40], pred_noise=True)
+    np.testing.assert_allclose(m_k, m_d, rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(c_k, c_d, rtol=1e-6, atol=1e-9)
+    spec = dense.spec_from_point(dense.MAP)
+    v_d, g_d = dense.engine.mll_grad(spec)
+    v_k, g_k = kr.engine.mll_grad(spec)
+    assert v_k == pytest.approx(v_d, rel=1e-9)
+    n_d, n_k = named_gradient(dense, g_d), named_gradient(kr, g_k)
+    for name in n_d:
+        np.testing.assert_allclose(n_k[name], n_d[name], rtol=1e-5, atol=1e-6, err_msg=name)
+    assert kr.predict(pts[:0])[0].shape == (0,)
+    dense.engine.close()
+    kr.engine.close()
+
+
+def test_kron_on_the_reference_shaped_golden(lib_built):
+    from gumbi_b200 import ArrayGP
+
+    g = load_golden("multioutput_regression")
+    gp = from_golden(g, ArrayGP, multioutput="kron")
+    gp.find_MAP(point=g["meta"]["point"])
+    mu, var = gp.predict(g["points"], with_noise=True)
+    np.testing.assert_allclose(mu, g["mean"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(var, g["var"], rtol=1e-6, atol=1e-9)
+    gp.engine.close()
+
+
+def test_find_map_on_device_blocks(lib_built):
+    X, y, kw = synthetic(n=120, P=3, d=1, seed=8)
+    dense, kr = pair(X, y, kw)
+    a = dense.find_MAP(options={"maxiter": 15})
+    b = kr.find_MAP(options={"maxiter": 15})
+    for name in a:
+        np.testing.assert_allclose(b[name], a[name], rtol=1e-4, atol=1e-6, err_msg=name)
+    dense.engine.close()
+    kr.engine.close()
+
+
+def test_get_alpha_needs_the_gradient_of_the_current_factor(lib_built):
+    from gumbi_b200 import GPEngine
+    from oracle import gp_oracle as orc
+
+    rng = np.random.default_rng(0)
+    X, y = rng.standard_normal((200, 2)), rng.standard_normal(200)
+    spec = {"terms": [{"kind": "ExpQuad", "cont_idx": [0, 1], "ls": [1.0, 1.3], "eta": 1.1, "lin_idx": [], "c": [], "tau": 0.0, "coreg": []}],
+            "sigma": 0.2, "noise_coreg": None, "jitter": 1e-6}
+    e = GPEngine()
+    e.set_train(X, y)
+    e.set_kernel(spec)
+    e.factorize()
+    with pytest.raises(ValueError):
+        e.get_alpha()
+    e.mll_grad(spec)
+    L, v = orc.factorize(spec, X, y)
+    from scipy.linalg import solve_triangular
+
+    np.testing.assert_allclose(e.get_alpha(), solve_triangular(L, v, lower=True, trans="T"), rtol=1e-7, atol=1e-9)
+    e.factorize()
+    with pytest.raises(ValueError):
+        e.get_alpha()
+    e.close()

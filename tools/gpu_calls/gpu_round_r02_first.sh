@@ -1,0 +1,7 @@
+#!/bin/bash
+# first GPU call of round 2 (1 GPU, ~4 min): full GPU suite (includes the Kronecker-solve device tests that round 1 could not
+# run), Kronecker vs dense cold-predict timing on BASELINE config 3, default bench line.
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -15 | tee gpurun_out/pytest_gpu_r02a.log
+timeout 600 python tools/kron_timing.py 2>&1 | tail -5 | tee gpurun_out/kron_timing_r02a.log
+timeout 600 python bench.py 2>&1 | tail -2 | tee gpurun_out/bench_r02a.log
