@@ -109,3 +109,42 @@ def test_draw_point_and_grid_samples_through_the_reference_wrappers(ref_env):
     # same seed -> same draws; the draws scatter around the posterior mean of predict()
     again = gp.draw_grid_samples(size=6, random_seed=3)
     np.testing.assert_array_equal(np.asarray(again.z.values(), dtype=float), np.asarray(z, dtype=float))
+
+
+def test_kron_solver_behind_the_reference_wrappers(ref_env):
+    """multioutput="kron" (gumbi_b200/kron.py) under the real DataSet / get_shaped_data / predict_grid: the stacked arrays the
+    reference builds for the multi-output notebook are aligned, and the block-wise solve returns the dense golden posterior."""
+    gmb, GP, pd = ref_env
+    from gumbi_b200 import kron
+    from test_backend_host import OracleEngine
+
+    class KronGP(GP):
+        def build_model(self, *a, **k):
+            self.engine = None
+            return super(GP, self).build_model(*a, **k)      # skip the dense double injected by HostB200GP
+
+        def _make_block_engine(self):
+            return OracleEngine()
+
+    g = load_golden("multioutput_regression")
+    df = pd.read_pickle(os.path.join(REF, "gumbi", "data", "Example_DataSet.pkl"))
+    df = df[(df.Name == "binary-pollen") & (df.Color == "cyan") & (df.Metric == "mean")]
+    ds = gmb.DataSet(df, outputs=["a", "b", "c", "d", "e", "f"], log_vars=["Y", "b", "c", "d", "f"], logit_vars=["X", "e"])
+    gp = KronGP(ds, outputs=["a", "b", "c", "d", "e"], multioutput="kron")
+    gp.specify_model(continuous_dims="lg10_Z", linear_dims="lg10_Z")
+    gp.build_model()
+    assert isinstance(gp.engine, kron.KronEngine) and gp.engine.n == 14 and gp.engine.P == 5
+    gp.find_MAP(point=g["meta"]["point"])
+    gp.prepare_grid(limits=gp.parray(lg10_Z=[1, 9]), resolution=17)
+    mv = gp.predict_grid()
+    assert type(mv).__name__ == "MVUncertainParameterArray" and mv.shape == (17,)
+    pts, _, _ = gp._prepare_points_for_prediction(gp.grid_points, output=gp._parse_prediction_output(None))
+    mu, var = gp.predict(pts)
+    np.testing.assert_allclose(mu, g["mean"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(var, g["var"], rtol=1e-8, atol=1e-11)
+    # one output only (predict_grid(output="c")): still every block, one solve per distinct grid point
+    up = gp.predict_grid(output="c")
+    assert type(up).__name__ == "UncertainParameterArray" and up.shape == (17,)
+    # fit() end to end through the block objective
+    gp.find_MAP(options={"maxiter": 10})
+    assert np.isfinite(gp.marginal_log_likelihood())
