@@ -248,8 +248,36 @@ int predict_common(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_nois
                                       h->dAt, Np, 1, 0, 0, h->opt_kbuild_occ);
         GB2_CUDA(h, cudaEventRecord(h->ev[2], s));
         launches += 2;
+        const int n_str = (int)std::min<int64_t>(h->opt_solve_streams, Mp / TILE);
         if (tf32) trsm_rec_tf32(h, s, Mp, 0, ncols, ncols, h->opt_tf32_leaf, launches);
-        else trsm_rec(s, h->dA, Np, h->dDinv, h->dAt, Np, Mp, 0, ncols, launches);
+        else if (n_str <= 1) trsm_rec(s, h->dA, Np, h->dDinv, h->dAt, Np, Mp, 0, ncols, launches);
+        else {
+            // The rows of At (prediction points) are independent: run the recursion on n_str row slabs in concurrent streams, so
+            // that the partial last wave of one slab's GEMM is filled by CTAs of another slab's (79 row tiles x 4 column tiles
+            // on 296 CTA slots leaves the second wave 7 % full when the slabs run one after the other).
+            if (!h->ev_fork) GB2_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+            GB2_CUDA(h, cudaEventRecord(h->ev_fork, s));
+            const int64_t nt = Mp / TILE;
+            for (int r = 0; r < n_str; r++) {
+                const int64_t t0 = nt * r / n_str, t1 = nt * (r + 1) / n_str;
+                cudaStream_t sr = s;
+                if (r > 0) {
+                    if (!h->s_aux[r - 1]) {
+                        int lo_p, hi_p;
+                        GB2_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+                        GB2_CUDA(h, cudaStreamCreateWithPriority(&h->s_aux[r - 1], cudaStreamNonBlocking, lo_p));
+                        GB2_CUDA(h, cudaEventCreateWithFlags(&h->ev_join[r - 1], cudaEventDisableTiming));
+                    }
+                    sr = h->s_aux[r - 1];
+                    GB2_CUDA(h, cudaStreamWaitEvent(sr, h->ev_fork, 0));
+                }
+                trsm_rec(sr, h->dA, Np, h->dDinv, h->dAt + t0 * TILE * Np, Np, (t1 - t0) * TILE, 0, ncols, launches);
+                if (r > 0) {
+                    GB2_CUDA(h, cudaEventRecord(h->ev_join[r - 1], sr));
+                    GB2_CUDA(h, cudaStreamWaitEvent(s, h->ev_join[r - 1], 0));
+                }
+            }
+        }
         GB2_CUDA(h, cudaEventRecord(h->ev[3], s));
         posterior_reduce_kernel<<<(unsigned)((Mc + 7) / 8), 256, 0, s>>>(h->kp, h->dBtab, h->dFs, h->dCs, Mp, h->dAt, Np, h->dA + N * Np, N, Mc,
                                                                         pred_noise, dmean_all + m0, dvar_all + m0);
@@ -352,6 +380,9 @@ int gb2_destroy(gb2_handle* h) {
     for (auto ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto ev : h->ev_pool) cudaEventDestroy(ev);
     for (auto ev : h->ev_mark) if (ev) cudaEventDestroy(ev);
+    for (auto st : h->s_aux) if (st) cudaStreamDestroy(st);
+    for (auto ev : h->ev_join) if (ev) cudaEventDestroy(ev);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->s_main) cudaStreamDestroy(h->s_main);
     if (h->s_panel) cudaStreamDestroy(h->s_panel);
     delete h;
@@ -985,6 +1016,11 @@ int gb2_set_option(gb2_handle* h, const char* name, int value) {
     if (!strcmp(name, "p2p")) {   // 1: panel exchange through NVLink peer mappings (default), 0: NCCL broadcast + all-gather
         GB2_ARG(h, !h->p2p_ready || value, "p2p cannot be switched off once the peer mappings are in use");
         h->opt_p2p = value ? 1 : 0;
+        return 0;
+    }
+    if (!strcmp(name, "solve_streams")) {   // fp64 predict solve: row slabs of the prediction points in concurrent streams
+        GB2_ARG(h, value >= 1 && value <= 4, "solve_streams must be in [1, 4]");
+        h->opt_solve_streams = value;
         return 0;
     }
     if (!strcmp(name, "fastdiag")) { h->opt_fastdiag = value ? 1 : 0; return 0; }   // ablation: Cholesky critical-path fast path

@@ -104,3 +104,28 @@ def test_get_alpha_needs_the_gradient_of_the_current_factor(lib_built):
     with pytest.raises(ValueError):
         e.get_alpha()
     e.close()
+
+
+@pytest.mark.parametrize("streams", [2, 4])
+def test_solve_streams_gives_identical_posterior(lib_built, streams):
+    """"solve_streams": the prediction rows are solved as independent slabs on concurrent streams -- same arithmetic per row, so
+    the posterior is bit-identical to the single-stream solve (also with fewer row tiles than streams)."""
+    from gumbi_b200 import GPEngine
+    from oracle import gp_oracle as orc
+
+    spec, X, y, Xs = orc.synthetic_problem(900, 3, M_res=25)      # M = 625 -> 5 row tiles
+    e = GPEngine()
+    e.set_train(X, y)
+    e.set_kernel(spec)
+    e.factorize()
+    ref = e.predict(Xs)
+    small = e.predict(Xs[:100])
+    e.set_option("solve_streams", streams)
+    got = e.predict(Xs)
+    got_small = e.predict(Xs[:100])                               # one row tile: falls back to a single stream
+    e.set_option("solve_streams", 1)
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
+    assert np.array_equal(got_small[0], small[0]) and np.array_equal(got_small[1], small[1])
+    with pytest.raises(ValueError):
+        e.set_option("solve_streams", 9)
+    e.close()
