@@ -7,3 +7,5 @@ timeout 600 python tools/kron_timing.py 2>&1 | tail -5 | tee gpurun_out/kron_tim
 timeout 600 python bench.py 2>&1 | tail -2 | tee gpurun_out/bench_r02a.log
 # wave-tail filling of the predict solve: prediction rows as 2 / 4 concurrent slabs (default 1)
 for s in 2 4; do timeout 300 python bench.py --no-cpu --opt solve_streams=$s 2>&1 | tail -1 | tee gpurun_out/bench_r02a_streams$s.log; done
+# kernel-only rates of the DMMA GEMM per launch shape (full waves vs the recursion's partial waves)
+timeout 300 ./tools/micro_dgemm 2>&1 | tee gpurun_out/micro_dgemm_r02a.log
