@@ -40,7 +40,10 @@ int main() {
         {8192, 8192, 8192}, {16384, 16384, 4096},                      // full-wave references
         {9472, 4096, 4096}, {10112, 4096, 4096},                      // 74 vs 79 row tiles (74 * 4 = 296 = one exact wave per 256 columns)
         {10112, 2048, 2048}, {10112, 1024, 1024}, {10112, 512, 512}, {10112, 256, 256}, {10112, 128, 128},
-        {9472, 256, 256}, {5120, 256, 256}, {2560, 256, 256}};
+        {9472, 256, 256}, {5120, 256, 256}, {2560, 256, 256},
+        // right-looking update of prediction rows appended below the factor (k = one 128-column panel per launch): the rate that
+        // decides whether fusing the predict solve into the factorisation's trailing updates would pay
+        {10112, 8192, 128}, {10112, 4096, 128}, {10112, 1024, 128}, {10112, 8192, 256}};
     for (auto s : shapes) {
         const double ms = run<128, 64, GM_SUB>(A, B, C, ld, s.r, s.c, s.k, 0, 10);
         const double ctas = (double)(s.r / 128) * (s.c / 64);
