@@ -313,11 +313,18 @@ class B200Backend:
         if self.MAP is None:
             raise RuntimeError("predict called before find_MAP/fit")
         # fingerprint of the hyper-parameter VALUES (a MAP dict edited in place must trigger a new factorisation)
-        key = hash(tuple((k, np.asarray(v, dtype=np.float64).tobytes()) for k, v in sorted(self.MAP.items()) if not k.endswith("_log__")))
+        key = self._map_key()
         if self._factor_key != key:
             self.engine.set_kernel(self.spec_from_point(self.MAP))
             self.engine.factorize()
             self._factor_key = key
+
+    def _map_key(self):
+        return hash(tuple((k, np.asarray(v, dtype=np.float64).tobytes()) for k, v in sorted(self.MAP.items()) if not k.endswith("_log__")))
+
+    def _ensure_factorized_key(self):
+        """Record that the engine now holds the factor of the current MAP (after a fused factorise+predict)."""
+        self._factor_key = self._map_key()
 
     def predict(self, points_array, with_noise=True, additive_level="total", **kwargs):
         if additive_level != "total":
@@ -389,10 +396,23 @@ class B200Backend:
         self.predictions_X = self.predictions_X.reshape(self.grid_parray.shape)
         return self.predictions
 
-    def predict_cold(self, points_array, with_noise=True):
-        """What ONE reference ``predict`` call costs: rebuild K, re-factorise, solve.  For benchmarking."""
+    def predict_cold(self, points_array, with_noise=True, fused=False):
+        """What ONE reference ``predict`` call costs: rebuild K, re-factorise, solve.  For benchmarking.
+
+        ``fused=True``: one pass through ``gb2_factorize_predict`` (prediction points carried through the factorisation as extra
+        rows of the factor) instead of factorise-then-solve; single GPU, fp64, dense solver only."""
         self._factor_key = None
-        return self.predict(points_array, with_noise=with_noise)
+        if not fused:
+            return self.predict(points_array, with_noise=with_noise)
+        if self.MAP is None:
+            raise RuntimeError("predict called before find_MAP/fit")
+        if not hasattr(self.engine, "factorize_predict") or getattr(self.engine, "world", 1) > 1:
+            raise NotImplementedError("fused cold predict needs the dense single-GPU engine")
+        points_array = np.atleast_2d(np.asarray(points_array, dtype=np.float64))
+        self.engine.set_kernel(self.spec_from_point(self.MAP))
+        out = self.engine.factorize_predict(points_array, pred_noise=bool(with_noise))
+        self._ensure_factorized_key()
+        return out
 
     def marginal_log_likelihood(self, point=None):
         """log p(y | X, theta) of ``gp.marginal_likelihood("ml", ...)`` (GP.py:580) at ``point`` (default: MAP)."""

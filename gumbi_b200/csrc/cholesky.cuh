@@ -627,6 +627,26 @@ inline int factor_steps(gb2_handle* h, int k0, int k1, int col_limit) {
             }
             if (chain) cudaEventRecord(pool_event(h, 2 * k + 1), sm);   // bulk update k done (or nothing to do)
         }
+        if (h->ext_rows > 0 && k < h->ext_ncols) {
+            // Fused cold predict: the prediction points are extra rows E (ext_rows x Np, = K(X*,X) on entry) below the factor.  Step k
+            // gives them what it gives every row below the diagonal -- E[:,k] <- E[:,k] inv(L_kk)^T, then E[:,j] -= E[:,k] L[j,k]^T for
+            // the column blocks j > k -- so that E ends as K(X*,X) L^-T, the A^T of the posterior.  These launches sit on the main
+            // stream behind the bulk update (never on the diag -> panel -> next-column chain) and fill the SM slots that the
+            // shrinking trailing matrix leaves idle.
+            if (below <= 0 && two) {   // last block step: nothing else made the main stream wait for this diagonal block
+                cudaEvent_t e = pool_event(h, 2 * k);
+                cudaEventRecord(e, sp);
+                cudaStreamWaitEvent(sm, e, 0);
+            }
+            double* Ek = h->ext_At + g0;
+            dgemm_nt_launch<64, 128, GM_SET>(sm, Ek, h->ext_ld, Dk, TILE, Ek, h->ext_ld, h->ext_rows, TILE, TILE, 0, 0, 0);
+            launches++;
+            if (k + 1 < h->ext_ncols) {
+                dgemm_nt_launch<128, 64, GM_SUB>(sm, Ek, h->ext_ld, A + (g0 + TILE) * ld + g0, ld, Ek + TILE, h->ext_ld, h->ext_rows,
+                                                 (int64_t)(h->ext_ncols - (k + 1)) * TILE, TILE, 0, 0, 0);
+                launches++;
+            }
+        }
     }
     if (two) {  // join
         cudaEvent_t e = pool_event(h, 3 * nb + 3);

@@ -660,8 +660,10 @@ static int build_K(gb2_handle* h, int& launches) {
     return 0;
 }
 
-int gb2_factorize(gb2_handle* h) {
-    if (!h) return -1;
+// Prediction points of a fused cold predict (gb2_factorize_predict); M == 0: plain factorisation.
+struct ExtPredict { const double* Xs = nullptr; int64_t M = 0; int32_t pred_noise = 0; double* mean = nullptr; double* var = nullptr; };
+
+static int factorize_impl(gb2_handle* h, const ExtPredict& x) {
     GB2_ARG(h, h->have_train, "gb2_factorize: no training data (call gb2_set_train)");
     GB2_ARG(h, h->have_kernel, "gb2_factorize: no kernel (call gb2_set_kernel)");
     GB2_CUDA(h, cudaSetDevice(h->device));
@@ -669,16 +671,50 @@ int gb2_factorize(gb2_handle* h) {
     h->L_split_valid = false;
     int launches = 0, rc;
     if ((rc = build_K(h, launches))) return rc;
+    const int64_t Np = h->Np, N = h->N, Mp = round_up(x.M, TILE);
+    cudaStream_t s = h->s_main;
+    if (x.M > 0) {
+        GB2_ARG(h, !h->compact, "gb2_factorize_predict is not available in the storage-sharded mode");
+        GB2_ARG(h, h->precision == GB2_FP64, "gb2_factorize_predict is fp64 only");
+        GB2_ARG(h, !h->opt_fastdiag, "gb2_factorize_predict is not available with the fastdiag ablation");
+        GB2_ARG(h, Mp * Np * (int64_t)sizeof(double) <= ((int64_t)8 << 30), "too many prediction points for one fused pass (use gb2_factorize + gb2_predict)");
+        if ((rc = ensure(h, h->dAt, h->At_cap, Mp * Np))) return rc;
+        if ((rc = ensure(h, h->dFs, h->Fs_cap, (int64_t)std::max(1, h->kp.n_feat) * Mp))) return rc;
+        if ((rc = ensure(h, h->dCs, h->Cs_cap, (int64_t)std::max(1, h->kp.n_cat) * Mp))) return rc;
+        if ((rc = ensure(h, h->dXs, h->Xs_cap, x.M * h->D_in))) return rc;
+        int64_t oc = h->out_cap;
+        if ((rc = ensure(h, h->dMean, oc, x.M))) return rc;
+        if ((rc = ensure(h, h->dVar, h->out_cap, x.M))) return rc;
+        // K(X*, X) as rows below the factor, exactly as gb2_predict builds it
+        GB2_CUDA(h, cudaMemcpyAsync(h->dXs, x.Xs, (size_t)x.M * h->D_in * sizeof(double), cudaMemcpyHostToDevice, s));
+        prep_features<<<(unsigned)((Mp + 255) / 256), 256, 0, s>>>(h->dXs, x.M, Mp, h->pp, h->dFs, h->dCs, h->dInfo + 1);
+        dim3 grid((unsigned)(Np / KB_T), (unsigned)(Mp / KB_T));
+        kbuild_dmma_launch<false>(s, grid, kbuild_dmma_smem_bytes(h->kp), h->kp, h->dBtab, h->dFs, h->dCs, Mp, x.M, h->dF, h->dC, Np, N, nullptr,
+                                  h->dAt, Np, 1, 0, 0, h->opt_kbuild_occ);
+        GB2_CUDA(h, cudaEventRecord(h->ev[2], s));   // "K build" now covers K and K*
+        launches += 2;
+        h->ext_At = h->dAt; h->ext_rows = Mp; h->ext_ld = Np; h->ext_ncols = (int)((N + TILE - 1) / TILE);
+    }
     launches += cholesky_enqueue(h);
-    GB2_CUDA(h, cudaEventRecord(h->ev[3], h->s_main));
+    h->ext_At = nullptr; h->ext_rows = 0;
+    GB2_CUDA(h, cudaEventRecord(h->ev[3], s));
+    if (x.M > 0) {
+        posterior_reduce_kernel<<<(unsigned)((x.M + 7) / 8), 256, 0, s>>>(h->kp, h->dBtab, h->dFs, h->dCs, Mp, h->dAt, Np, h->dA + N * Np, N, x.M,
+                                                                         x.pred_noise, h->dMean, h->dVar);
+        launches++;
+        GB2_CUDA(h, cudaEventRecord(h->ev[4], s));
+        GB2_CUDA(h, cudaMemcpyAsync(x.mean, h->dMean, (size_t)x.M * sizeof(double), cudaMemcpyDeviceToHost, s));
+        GB2_CUDA(h, cudaMemcpyAsync(x.var, h->dVar, (size_t)x.M * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
     int info[2] = {0, 0};
-    GB2_CUDA(h, cudaMemcpyAsync(info, h->dInfo, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->s_main));
+    GB2_CUDA(h, cudaMemcpyAsync(info, h->dInfo, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
     GB2_CUDA(h, cudaGetLastError());
-    GB2_CUDA(h, cudaStreamSynchronize(h->s_main));
+    GB2_CUDA(h, cudaStreamSynchronize(s));
     h->timings[0] = ms_between(h->ev[0], h->ev[1]);
     h->timings[1] = ms_between(h->ev[1], h->ev[2]);
     h->timings[2] = ms_between(h->ev[2], h->ev[3]);
     h->timings[6] = launches;
+    if (x.M > 0) { h->timings[3] = 0; h->timings[4] = 0; h->timings[5] = ms_between(h->ev[3], h->ev[4]); h->timings[7] = 0; }
     if (h->world > 1) {
         // the first failing pivot is only known to the rank that owns its diagonal block: agree on one verdict, otherwise some ranks
         // would raise while the others walk into the next collective.  Encoded so that "smallest positive pivot" is a minimum.
@@ -689,7 +725,7 @@ int gb2_factorize(gb2_handle* h) {
         info[1] = agreed == 1 ? 1 : 0;
         info[0] = (agreed > 1 && agreed != 0x7fffffff) ? agreed - 1 : 0;
     }
-    GB2_ARG(h, info[1] == 0, "a Coregion column of X holds a level index outside [0, P)");
+    GB2_ARG(h, info[1] == 0, "a Coregion column of X (or Xs) holds a level index outside [0, P)");
     if (info[0] != 0) {
         h->err = "matrix is not positive definite: leading minor of order " + std::to_string(info[0]);
         return info[0];
@@ -697,6 +733,25 @@ int gb2_factorize(gb2_handle* h) {
     h->factorized = true;
     h->factor_count++;
     return 0;
+}
+
+int gb2_factorize(gb2_handle* h) {
+    if (!h) return -1;
+    return factorize_impl(h, ExtPredict{});
+}
+
+// One reference predict call in one pass (PymcGP.predict rebuilds K, re-factorises and solves on every call,
+// gumbi/regression/pymc/GP.py:845-847): the prediction points are appended as extra rows of the factor, so the solve
+// A^T = K(X*,X) L^-T is carried by the factorisation's own panel solves and right-looking updates (cholesky.cuh, factor_steps).
+// Leaves the handle factorised exactly as gb2_factorize does.  Multi-GPU (replicated storage): collective, every rank passes its
+// own points.
+int gb2_factorize_predict(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_noise, double* mean, double* var) {
+    if (!h) return -1;
+    GB2_ARG(h, Xs && mean && var, "null pointer");
+    GB2_ARG(h, M >= 1, "M must be >= 1");
+    ExtPredict x;
+    x.Xs = Xs; x.M = M; x.pred_noise = pred_noise; x.mean = mean; x.var = var;
+    return factorize_impl(h, x);
 }
 
 int gb2_mll(gb2_handle* h, double* out) {

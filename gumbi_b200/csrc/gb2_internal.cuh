@@ -143,6 +143,8 @@ struct gb2_handle {
     int opt_chain_on_panel = 1;   // Cholesky: keep the next-column update on the panel stream (no cross-stream hop on the chain)
     int opt_fastdiag = 0;    // single GPU: "row-fix" schedule for the next diagonal block (cholesky.cuh); measured slower, kept as ablation
     int opt_lookahead = 1;
+    // fused cold predict (gb2_factorize_predict): prediction points ride along as ext_rows extra rows of the factor (row-major, ld ext_ld)
+    double* ext_At = nullptr; int64_t ext_rows = 0, ext_ld = 0; int ext_ncols = 0;
     int opt_solve_streams = 1;   // fp64 predict solve: split the prediction rows over this many concurrent streams (wave-tail filling)
     cudaStream_t s_aux[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};

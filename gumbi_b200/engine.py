@@ -176,6 +176,21 @@ class GPEngine:
         self._check(self._lib.gb2_predict(self._h, _lib.as_dp(Xs), M, int(bool(pred_noise)), _lib.as_dp(mean), _lib.as_dp(var)), "predict")
         return mean, var
 
+    def factorize_predict(self, Xs, pred_noise: bool = True):
+        """``factorize()`` + ``predict()`` in one pass (one cold reference ``predict`` call): the prediction points ride through the
+        factorisation as extra rows of the factor.  fp64, replicated storage; leaves the handle factorised."""
+        Xs = _c_f64(np.atleast_2d(Xs), 2)
+        if Xs.shape[1] != self.D_in:
+            raise ValueError(f"points_array has {Xs.shape[1]} columns, model has {self.D_in} dims")
+        if not np.all(np.isfinite(Xs)):
+            raise ValueError("points_array must be finite")
+        M = Xs.shape[0]
+        mean = np.empty(M, dtype=np.float64)
+        var = np.empty(M, dtype=np.float64)
+        self._check(self._lib.gb2_factorize_predict(self._h, _lib.as_dp(Xs), M, int(bool(pred_noise)), _lib.as_dp(mean), _lib.as_dp(var)),
+                    "factorize_predict")
+        return mean, var
+
     def predict_full(self, Xs, pred_noise: bool = False):
         """Posterior mean (M,) and full covariance (M, M) -- the parameters of ``gp.conditional(name, Xnew)`` (GP.py:913)."""
         Xs = _c_f64(np.atleast_2d(Xs), 2)

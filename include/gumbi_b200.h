@@ -128,6 +128,13 @@ int gb2_get_alpha(gb2_handle* h, double* alpha_out);
 int gb2_predict(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_noise, double* mean, double* var);
 int gb2_predict_dev(gb2_handle* h, const double* dXs, int64_t M, int32_t pred_noise, double* dmean, double* dvar);
 
+/* gb2_factorize + gb2_predict in ONE pass -- what a single PymcGP.predict call costs in the reference, which rebuilds K,
+ * re-factorises and solves every time (GP.py:845-847).  The prediction points are appended as extra rows of the
+ * factor: their solve K(X*,X) L^-T is carried by the factorisation's own panel solves and trailing updates instead of a
+ * separate triangular solve afterwards.  Same results as the two calls up to summation order; leaves the handle factorised.
+ * fp64, replicated storage, M * round_up(N+1,128) * 8 bytes <= 8 GiB.  Multi-GPU: collective, each rank passes its own points. */
+int gb2_factorize_predict(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_noise, double* mean, double* var);
+
 /* Posterior mean and FULL covariance at Xs:(M,D_in): cov:(M,M) row-major = K(X*,X*) - A^T A (+ noise diag if pred_noise).
  * Replaces the distribution gp.conditional(var_name, points_array) builds for draw_point_samples / draw_grid_samples
  * (GP.py:861-979; pm.gp.Marginal.conditional, diag=False).  M <= 32768.                                                */

@@ -248,3 +248,25 @@ def test_conditional_and_joint_samples():
     assert draws.shape == (4000, 40)
     np.testing.assert_allclose(draws.mean(0), mu, atol=5 * np.sqrt(np.diag(cov).max() / 4000) + 1e-3)
     np.testing.assert_allclose(np.cov(draws.T), cov + 1e-6 * np.eye(40), atol=0.1 * np.abs(cov).max())
+
+
+def test_predict_cold_fused_uses_the_one_pass_entry_point():
+    """predict_cold(fused=True) -> engine.factorize_predict (gb2_factorize_predict); afterwards the factor counts as current."""
+    g = load_golden("simple_regression_ExpQuad")
+    gp = gp_from_golden(g)
+    gp.find_MAP(point=g["meta"]["point"])
+    with pytest.raises(NotImplementedError):                   # the plain double has no one-pass entry point
+        gp.predict_cold(g["points"], fused=True)
+
+    class Fused(OracleEngine):
+        def factorize_predict(self, Xs, pred_noise=True):
+            self.factorize()
+            return self.predict(Xs, pred_noise)
+
+    gp.engine = Fused()
+    gp.engine.set_train(gp._X, gp._y)
+    mu, var = gp.predict_cold(g["points"], with_noise=True, fused=True)
+    np.testing.assert_allclose(mu, g["mean"], rtol=1e-9, atol=1e-11)
+    n = gp.engine.n_fact
+    gp.predict(g["points"])                                     # no second factorisation: the fused pass left the factor behind
+    assert gp.engine.n_fact == n

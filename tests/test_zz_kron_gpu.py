@@ -129,3 +129,41 @@ def test_solve_streams_gives_identical_posterior(lib_built, streams):
     with pytest.raises(ValueError):
         e.set_option("solve_streams", 9)
     e.close()
+
+
+@pytest.mark.parametrize("n,d,P,kind", [(900, 3, 1, "ExpQuad"), (1000, 2, 1, "Matern52"), (127, 1, 1, "ExpQuad"), (300, 2, 2, "ExpQuad")])
+def test_fused_cold_predict_matches_factorize_then_predict(lib_built, n, d, P, kind):
+    """gb2_factorize_predict: prediction points carried through the factorisation as extra rows of the factor -- same posterior as
+    gb2_factorize + gb2_predict (different summation order only), same factor left behind, same oracle numbers."""
+    from gumbi_b200 import GPEngine
+    from oracle import gp_oracle as orc
+
+    spec, X, y, Xs = orc.synthetic_problem(n, d, P=P, M_res=21 if d >= 2 else 77, kind=kind)
+    e = GPEngine()
+    e.set_train(X, y)
+    e.set_kernel(spec)
+    e.factorize()
+    L_ref = e.get_L()
+    ref = {noise: e.predict(Xs, noise) for noise in (True, False)}
+    for noise in (True, False):
+        mu, var = e.factorize_predict(Xs, noise)
+        np.testing.assert_allclose(mu, ref[noise][0], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(var, ref[noise][1], rtol=1e-7, atol=1e-10)
+    assert np.array_equal(e.get_L(), L_ref)                       # the factorisation itself is untouched by the extra rows
+    mu2, var2 = e.predict(Xs[:50], True)                          # and the handle is left factorised
+    np.testing.assert_allclose(mu2, ref[True][0][:50], rtol=1e-12, atol=1e-13)
+    L, v = orc.factorize(spec, X, y)
+    mu_o, var_o = orc.conditional(spec, X, L, v, Xs, True)
+    mu, var = e.factorize_predict(Xs, True)
+    np.testing.assert_allclose(mu, mu_o, rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(var, var_o, rtol=1e-5, atol=1e-8)
+    mu1, var1 = e.factorize_predict(Xs[:1], True)                 # a single point
+    np.testing.assert_allclose(mu1, mu_o[:1], rtol=1e-6, atol=1e-8)
+    bad = dict(spec, sigma=0.0, jitter=0.0)
+    Xd = X.copy()
+    Xd[n // 2] = Xd[n // 4]                                       # duplicated row, no noise: singular K
+    e.set_train(Xd, y)
+    e.set_kernel(bad)
+    with pytest.raises(np.linalg.LinAlgError):
+        e.factorize_predict(Xs, True)
+    e.close()

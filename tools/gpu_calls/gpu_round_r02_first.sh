@@ -9,3 +9,5 @@ timeout 600 python bench.py 2>&1 | tail -2 | tee gpurun_out/bench_r02a.log
 for s in 2 4; do timeout 300 python bench.py --no-cpu --opt solve_streams=$s 2>&1 | tail -1 | tee gpurun_out/bench_r02a_streams$s.log; done
 # kernel-only rates of the DMMA GEMM per launch shape (full waves vs the recursion's partial waves)
 timeout 300 ./tools/micro_dgemm 2>&1 | tee gpurun_out/micro_dgemm_r02a.log
+# cold predict: factorise-then-solve (1/2/4 solve streams) against the fused one-pass entry point
+timeout 300 python tools/fused_timing.py 2>&1 | tail -6 | tee gpurun_out/fused_timing_r02a.log
