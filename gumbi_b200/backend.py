@@ -473,13 +473,20 @@ class ArrayGP(B200Backend, ArrayRegressor):
         self._init_backend(device=device, precision=precision, distributed=distributed, multioutput=multioutput)
 
 
-def make_backend(regressor_base):
-    """Create the drop-in ``B200GP`` subclass of Gumbi's ``Regressor`` (``gumbi.regression.base.Regressor``)."""
+def make_backend(regressor_base, device=0, precision="fp64", distributed=False, multioutput="dense"):
+    """Create the drop-in ``B200GP`` subclass of Gumbi's ``Regressor`` (``gumbi.regression.base.Regressor``).
+
+    The keyword arguments become the class's constructor defaults, so that objects Gumbi re-creates itself with
+    ``self.__class__(dataset, outputs=..., seed=...)`` (``cross_validate``, base.py:1060) keep the device / precision / solver."""
+    defaults = dict(device=device, precision=precision, distributed=distributed, multioutput=multioutput)
 
     class B200GP(B200Backend, regressor_base):
-        def __init__(self, dataset, outputs=None, seed=2021, device=0, precision="fp64", distributed=False, multioutput="dense"):
+        def __init__(self, dataset, outputs=None, seed=2021, **options):
+            unknown = set(options) - set(defaults)
+            if unknown:
+                raise TypeError(f"unexpected keyword arguments {sorted(unknown)} (options: {sorted(defaults)})")
             regressor_base.__init__(self, dataset, outputs, seed)
-            self._init_backend(device=device, precision=precision, distributed=distributed, multioutput=multioutput)
+            self._init_backend(**{**defaults, **options})
 
     B200GP.__doc__ = "Gumbi Regressor backend running the exact-GP dense path on a B200 (see gumbi_b200.backend)."
     return B200GP

@@ -148,3 +148,22 @@ def test_kron_solver_behind_the_reference_wrappers(ref_env):
     # fit() end to end through the block objective
     gp.find_MAP(options={"maxiter": 10})
     assert np.isfinite(gp.marginal_log_likelihood())
+
+
+def test_class_defaults_survive_reconstruction(ref_env):
+    """cross_validate re-creates the regressor with ``self.__class__(train_ds, outputs=..., seed=...)`` (base.py:1060): options given
+    to make_backend are class defaults and therefore survive; unknown options are rejected like any unexpected keyword."""
+    gmb, GP, pd = ref_env
+    from gumbi.regression.base import Regressor
+
+    from gumbi_b200 import make_backend
+
+    Cls = make_backend(Regressor, device=3, precision="tf32", multioutput="auto")
+    df = pd.read_pickle(os.path.join(REF, "gumbi", "data", "Example_DataSet.pkl")).query('Metric=="mean"')
+    ds = gmb.DataSet(df, outputs=["a", "b", "c", "d", "e", "f"], log_vars=["Y", "b", "c", "d", "f"], logit_vars=["X", "e"])
+    gp = Cls(ds, outputs=["d"])
+    again = gp.__class__(ds, outputs=gp.outputs, seed=7)
+    assert (again.device, again.precision, again.multioutput, again.seed) == (3, "tf32", "auto", 7)
+    assert Cls(ds, outputs=["d"], device=1).device == 1
+    with pytest.raises(TypeError):
+        Cls(ds, outputs=["d"], gpu=1)
