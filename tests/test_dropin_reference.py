@@ -167,3 +167,18 @@ def test_class_defaults_survive_reconstruction(ref_env):
     assert Cls(ds, outputs=["d"], device=1).device == 1
     with pytest.raises(TypeError):
         Cls(ds, outputs=["d"], gpu=1)
+
+
+def test_cross_validate_runs_unmodified_on_the_backend(ref_env):
+    """Regressor.cross_validate (base.py:844-1109) re-creates the class on a training subset, calls build_model(**model_specs),
+    find_MAP(**MAP_kws), predict_points on train and test rows, and scores them -- all inherited, nothing backend-specific."""
+    gmb, GP, pd = ref_env
+    df = pd.read_pickle(os.path.join(REF, "gumbi", "data", "Example_DataSet.pkl")).query('Metric=="mean"')
+    ds = gmb.DataSet(df, outputs=["a", "b", "c", "d", "e", "f"], log_vars=["Y", "b", "c", "d", "f"], logit_vars=["X", "e"])
+    ds.tidy = ds.tidy[ds.tidy.Color.isin(["cyan", "magenta"]) & (ds.tidy.Pair == "burrata+barbaresco")]
+    gp = GP(ds, outputs=["d"])
+    gp.fit(continuous_dims=["X", "Y", "lg10_Z"], linear_dims=["X", "Y", "lg10_Z"], MAP_kwargs={"options": {"maxiter": 10}})
+    cv = gp.cross_validate(n_train=50, seed=1, options={"maxiter": 10})
+    assert set(cv) == {"train", "test"}
+    for part in cv.values():
+        assert np.all(np.isfinite(np.asarray(part["NLPDs"], dtype=float))) and np.all(np.isfinite(np.asarray(part["errors"], dtype=float)))
