@@ -16,10 +16,10 @@
 
 namespace gb2 {
 
-constexpr int GM_BK = 16;
-constexpr int GM_LDS = 20;  // padded shared row, doubles
-constexpr int GM_STAGES = 3;
+constexpr int GM_BK = 16;      // product configuration; the kernel is also parametrised over BK / stages / warp tile so that
+constexpr int GM_STAGES = 3;   // tools/micro_dgemm.cu can time variants (BK=32 x 2 stages, 32x64 warp tiles) without touching it
 constexpr int GM_THREADS = 256;
+__host__ __device__ constexpr int gm_lds(int bk) { return bk + 4; }   // padded shared row, doubles: row stride = 8 banks mod 32 for BK = 16, 32
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -48,8 +48,8 @@ struct PushArgs {
     int64_t ld;                          // row stride of the targets (0: same as the local C)
 };
 
-template <int BM, int BN>
-constexpr size_t dgemm_smem_bytes() { return (size_t)GM_STAGES * (BM + BN) * GM_LDS * sizeof(double); }
+template <int BM, int BN, int BK = GM_BK, int STAGES = GM_STAGES>
+constexpr size_t dgemm_smem_bytes() { return (size_t)STAGES * (BM + BN) * gm_lds(BK) * sizeof(double); }
 
 // C[bi*BM.., bj*BN..] (MODE==GM_SUB: -=, GM_SET: =) sum_k A[bi*BM + r, k] * B[bj*BN + c, k],  k < kdepth.
 // lower_only: skip tiles lying strictly above the diagonal of the global matrix, where tile (0,0) sits at
@@ -60,12 +60,13 @@ constexpr size_t dgemm_smem_bytes() { return (size_t)GM_STAGES * (BM + BN) * GM_
 // block starting at block `rb_first` (block-cyclic ownership); row tile bi then sits at row
 //   ((rb_first + (bi / (128/BM)) * rb_stride) * 128 + (bi % (128/BM)) * BM   relative to the A / C base pointers.
 // rb_first = 0, rb_stride = 1 is the dense case.
-template <int BM, int BN, int MODE>
-__global__ void __launch_bounds__(GM_THREADS, 2)
+template <int BM, int BN, int MODE, int BK = GM_BK, int STAGES = GM_STAGES, int WM = 32, int WN = 32, int MINB = 2>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB)
 dgemm_nt_kernel(const double* A, int64_t lda, const double* __restrict__ B, int64_t ldb, double* C, int64_t ldc,
                 int kdepth, int lower_only, int64_t row_off, int64_t col_off, int rb_first, int rb_stride, PushArgs push,
                 int rb_local_first) {
-    static_assert((BM / 32) * (BN / 32) == GM_THREADS / 32, "8 warps of 32x32");
+    constexpr int THREADS = (BM / WM) * (BN / WN) * 32, LDS = gm_lds(BK), MI = WM / 8, NI = WN / 8, CH = BK / 2;
+    static_assert(BM % WM == 0 && BN % WN == 0 && WM % 8 == 0 && WN % 8 == 0 && BK % 4 == 0, "warp tiles of 8x8x4 DMMA fragments");
     static_assert(TILE % BM == 0, "row tiles must not straddle 128-row blocks");
     const int bi = blockIdx.x, bj = blockIdx.y;
     constexpr int TPB = TILE / BM;
@@ -77,75 +78,75 @@ dgemm_nt_kernel(const double* A, int64_t lda, const double* __restrict__ B, int6
 
     extern __shared__ __align__(16) unsigned char gm_smem[];
     double* sA = reinterpret_cast<double*>(gm_smem);
-    double* sB = sA + GM_STAGES * BM * GM_LDS;
+    double* sB = sA + STAGES * BM * LDS;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp % (BM / 32), wn = warp / (BM / 32);
+    const int wm = warp % (BM / WM), wn = warp / (BM / WM);
     const int g = lane >> 2, t = lane & 3;
 
     const double* Ag = A + lrow * lda;
     const double* Bg = B + (int64_t)bj * BN * ldb;
 
     auto load_stage = [&](int stage, int kt) {
-        const int k0 = kt * GM_BK;
-        double* dA = sA + stage * BM * GM_LDS;
-        double* dB = sB + stage * BN * GM_LDS;
+        const int k0 = kt * BK;
+        double* dA = sA + stage * BM * LDS;
+        double* dB = sB + stage * BN * LDS;
 #pragma unroll
-        for (int c = tid; c < BM * 8; c += GM_THREADS) {
-            const int r = c >> 3, ch = c & 7;
-            cp_async16(dA + r * GM_LDS + ch * 2, Ag + (int64_t)r * lda + k0 + ch * 2);
+        for (int c = tid; c < BM * CH; c += THREADS) {
+            const int r = c / CH, ch = c % CH;
+            cp_async16(dA + r * LDS + ch * 2, Ag + (int64_t)r * lda + k0 + ch * 2);
         }
 #pragma unroll
-        for (int c = tid; c < BN * 8; c += GM_THREADS) {
-            const int r = c >> 3, ch = c & 7;
-            cp_async16(dB + r * GM_LDS + ch * 2, Bg + (int64_t)r * ldb + k0 + ch * 2);
+        for (int c = tid; c < BN * CH; c += THREADS) {
+            const int r = c / CH, ch = c % CH;
+            cp_async16(dB + r * LDS + ch * 2, Bg + (int64_t)r * ldb + k0 + ch * 2);
         }
     };
 
-    double acc[4][4][2];
+    double acc[MI][NI][2];
 #pragma unroll
-    for (int mi = 0; mi < 4; mi++)
+    for (int mi = 0; mi < MI; mi++)
 #pragma unroll
-        for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        for (int ni = 0; ni < NI; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
-    const int nk = kdepth / GM_BK;
+    const int nk = kdepth / BK;
     // lower_only == 2: both operands are rows of an upper-triangular matrix (W = L^-T: W[r][k] = 0 for k < r), so the product
     // of this tile only has terms from k >= max(first row of the A tile, first row of the B tile)
-    const int kt0 = lower_only == 2 ? (int)(((grow > (int64_t)bj * BN) ? grow : (int64_t)bj * BN) / GM_BK) : 0;
+    const int kt0 = lower_only == 2 ? (int)(((grow > (int64_t)bj * BN) ? grow : (int64_t)bj * BN) / BK) : 0;
 #pragma unroll
-    for (int s = 0; s < GM_STAGES - 1; s++) {
+    for (int s = 0; s < STAGES - 1; s++) {
         if (kt0 + s < nk) load_stage(s, kt0 + s);
         cp_async_commit();
     }
     for (int kt = kt0; kt < nk; kt++) {
-        cp_async_wait<GM_STAGES - 2>();
+        cp_async_wait<STAGES - 2>();
         __syncthreads();
-        const int nxt = kt + GM_STAGES - 1;
-        if (nxt < nk) load_stage((nxt - kt0) % GM_STAGES, nxt);
+        const int nxt = kt + STAGES - 1;
+        if (nxt < nk) load_stage((nxt - kt0) % STAGES, nxt);
         cp_async_commit();
-        const int st = (kt - kt0) % GM_STAGES;
-        const double* cA = sA + st * BM * GM_LDS + (wm * 32 + g) * GM_LDS + t;
-        const double* cB = sB + st * BN * GM_LDS + (wn * 32 + g) * GM_LDS + t;
+        const int st = (kt - kt0) % STAGES;
+        const double* cA = sA + st * BM * LDS + (wm * WM + g) * LDS + t;
+        const double* cB = sB + st * BN * LDS + (wn * WN + g) * LDS + t;
 #pragma unroll
-        for (int kk = 0; kk < GM_BK / 4; kk++) {
-            double a[4], b[4];
+        for (int kk = 0; kk < BK / 4; kk++) {
+            double a[MI], b[NI];
 #pragma unroll
-            for (int mi = 0; mi < 4; mi++) a[mi] = cA[mi * 8 * GM_LDS + kk * 4];
+            for (int mi = 0; mi < MI; mi++) a[mi] = cA[mi * 8 * LDS + kk * 4];
 #pragma unroll
-            for (int ni = 0; ni < 4; ni++) b[ni] = cB[ni * 8 * GM_LDS + kk * 4];
+            for (int ni = 0; ni < NI; ni++) b[ni] = cB[ni * 8 * LDS + kk * 4];
 #pragma unroll
-            for (int mi = 0; mi < 4; mi++)
+            for (int mi = 0; mi < MI; mi++)
 #pragma unroll
-                for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                for (int ni = 0; ni < NI; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
         }
     }
     cp_async_wait<0>();
 
-    double* Cg = C + (lrow + wm * 32 + g) * ldc + (int64_t)bj * BN + wn * 32 + 2 * t;
+    double* Cg = C + (lrow + wm * WM + g) * ldc + (int64_t)bj * BN + wn * WN + 2 * t;
 #pragma unroll
-    for (int mi = 0; mi < 4; mi++)
+    for (int mi = 0; mi < MI; mi++)
 #pragma unroll
-        for (int ni = 0; ni < 4; ni++) {
+        for (int ni = 0; ni < NI; ni++) {
             double2* p = reinterpret_cast<double2*>(Cg + (int64_t)mi * 8 * ldc + ni * 8);
             if (MODE == GM_SUB) {
                 double2 c = *p;
@@ -158,13 +159,13 @@ dgemm_nt_kernel(const double* A, int64_t lda, const double* __restrict__ B, int6
         }
     if (MODE == GM_SET_PUSH) {
         const int64_t pld = push.ld ? push.ld : ldc;
-        const int64_t off = (grow + wm * 32 + g) * pld + (int64_t)bj * BN + wn * 32 + 2 * t;
+        const int64_t off = (grow + wm * WM + g) * pld + (int64_t)bj * BN + wn * WN + 2 * t;
         for (int pr = 0; pr < push.n_peers; pr++) {
             double* Pg = push.peerC[pr] + off;
 #pragma unroll
-            for (int mi = 0; mi < 4; mi++)
+            for (int mi = 0; mi < MI; mi++)
 #pragma unroll
-                for (int ni = 0; ni < 4; ni++)
+                for (int ni = 0; ni < NI; ni++)
                     *reinterpret_cast<double2*>(Pg + (int64_t)mi * 8 * pld + ni * 8) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
         }
         __threadfence_system();          // this thread's peer stores are performed system-wide ...
@@ -175,14 +176,14 @@ dgemm_nt_kernel(const double* A, int64_t lda, const double* __restrict__ B, int6
     }
 }
 
-template <int BM, int BN, int MODE>
+template <int BM, int BN, int MODE, int BK = GM_BK, int STAGES = GM_STAGES, int WM = 32, int WN = 32, int MINB = 2>
 inline cudaError_t dgemm_nt_configure() {
-    return cudaFuncSetAttribute(dgemm_nt_kernel<BM, BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)dgemm_smem_bytes<BM, BN>());
+    return cudaFuncSetAttribute(dgemm_nt_kernel<BM, BN, MODE, BK, STAGES, WM, WN, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)dgemm_smem_bytes<BM, BN, BK, STAGES>());
 }
 
 // rows x cols output, both multiples of the tile.
-template <int BM, int BN, int MODE>
+template <int BM, int BN, int MODE, int BK = GM_BK, int STAGES = GM_STAGES, int WM = 32, int WN = 32, int MINB = 2>
 inline void dgemm_nt_launch(cudaStream_t s, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                             int64_t ldc, int64_t rows, int64_t cols, int kdepth, int lower_only, int64_t row_off,
                             int64_t col_off, int rb_first = 0, int rb_stride = 1, const PushArgs* push = nullptr,
@@ -191,9 +192,8 @@ inline void dgemm_nt_launch(cudaStream_t s, const double* A, int64_t lda, const 
     dim3 grid((unsigned)(rows / BM), (unsigned)(cols / BN));
     PushArgs pa{};
     if (push) pa = *push;
-    dgemm_nt_kernel<BM, BN, MODE><<<grid, GM_THREADS, dgemm_smem_bytes<BM, BN>(), s>>>(A, lda, B, ldb, C, ldc, kdepth,
-                                                                                      lower_only, row_off, col_off, rb_first, rb_stride, pa,
-                                                                                      rb_local_first);
+    dgemm_nt_kernel<BM, BN, MODE, BK, STAGES, WM, WN, MINB><<<grid, (BM / WM) * (BN / WN) * 32, dgemm_smem_bytes<BM, BN, BK, STAGES>(), s>>>(
+        A, lda, B, ldb, C, ldc, kdepth, lower_only, row_off, col_off, rb_first, rb_stride, pa, rb_local_first);
 }
 
 }  // namespace gb2

@@ -7,13 +7,14 @@
 #include <vector>
 using namespace gb2;
 
-template <int BM, int BN, int MODE>
+template <int BM, int BN, int MODE, int BK = GM_BK, int STAGES = GM_STAGES, int WM = 32, int WN = 32, int MINB = 2>
 static double run(const double* A, const double* B, double* C, int64_t ld, int64_t rows, int64_t cols, int k, int lower, int reps) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int i = 0; i < 2; i++) dgemm_nt_launch<BM, BN, MODE>(0, A, ld, B, ld, C, ld, rows, cols, k, lower, 0, 0);
+    if (dgemm_nt_configure<BM, BN, MODE, BK, STAGES, WM, WN, MINB>() != cudaSuccess) { printf("configure failed\n"); exit(1); }
+    for (int i = 0; i < 2; i++) dgemm_nt_launch<BM, BN, MODE, BK, STAGES, WM, WN, MINB>(0, A, ld, B, ld, C, ld, rows, cols, k, lower, 0, 0);
     cudaEventRecord(e0);
-    for (int i = 0; i < reps; i++) dgemm_nt_launch<BM, BN, MODE>(0, A, ld, B, ld, C, ld, rows, cols, k, lower, 0, 0);
+    for (int i = 0; i < reps; i++) dgemm_nt_launch<BM, BN, MODE, BK, STAGES, WM, WN, MINB>(0, A, ld, B, ld, C, ld, rows, cols, k, lower, 0, 0);
     cudaEventRecord(e1);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); exit(1); }
@@ -31,7 +32,6 @@ int main() {
     cudaMemcpy(A, h.data(), h.size() * 8, cudaMemcpyHostToDevice);
     cudaMemcpy(B, h.data(), h.size() * 8, cudaMemcpyHostToDevice);
     cudaMemset(C, 0, h.size() * 8);
-    dgemm_nt_configure<128, 64, GM_SUB>(); dgemm_nt_configure<64, 128, GM_SET>();
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     const int slots = 2 * sms;
@@ -64,6 +64,28 @@ int main() {
         char name[64];
         snprintf(name, sizeof name, "SYRK lower  %d blocks, k=128", m);
         printf("%-34s %9.3f %9.2f %8.0f %8.2f\n", name, ms, (double)m * (m + 1) / 2 * 2.0 * 128 * 128 * 128 / ms / 1e9, ctas, ctas / slots);
+    }
+    // kernel variants on a full-wave shape and on the k = 128 update shape (same arithmetic, different staging / warp tiling):
+    //   BK=32 x 2 stages: half the barriers per flop;  32x64 warp tiles, 4 warps per 64x128 CTA: 0.375 instead of 0.5 LDS per DMMA
+    //   (what the cuBLAS kernel of the same tile, cutlass_80_tensorop_d884gemm_64x128_16x3, uses);  128x128 CTA, 1 per SM
+    struct V { const char* name; double (*fn)(const double*, const double*, double*, int64_t, int64_t, int64_t, int, int, int); int bm, bn; };
+    V variants[] = {
+        {"128x64 BK16x3 w32x32 (product)", run<128, 64, GM_SUB>, 128, 64},
+        {"128x64 BK32x2 w32x32", run<128, 64, GM_SUB, 32, 2>, 128, 64},
+        {"64x128 BK16x3 w32x64 (4 warps)", run<64, 128, GM_SUB, 16, 3, 32, 64>, 64, 128},
+        {"128x128 BK16x3 w64x32 (1 CTA/SM)", run<128, 128, GM_SUB, 16, 3, 64, 32, 1>, 128, 128},
+        {"128x128 BK16x4 w32x64 (1 CTA/SM)", run<128, 128, GM_SUB, 16, 4, 32, 64, 1>, 128, 128}};
+    struct S2 { int64_t r, c; int k; } vs[] = {{8192, 8192, 8192}, {10112, 4096, 4096}, {10112, 8192, 128}, {10112, 256, 256}};
+    printf("\n%-36s", "variant \\ TFLOP/s at shape");
+    for (auto s : vs) printf(" %6lldx%lldx%d", (long long)s.r, (long long)s.c, s.k);
+    printf("\n");
+    for (auto& v : variants) {
+        printf("%-36s", v.name);
+        for (auto s : vs) {
+            const double ms = v.fn(A, B, C, ld, s.r, s.c, s.k, 0, 6);
+            printf(" %18.2f", 2.0 * s.r * s.c * s.k / ms / 1e9);
+        }
+        printf("\n");
     }
     return 0;
 }
