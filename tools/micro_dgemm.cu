@@ -75,6 +75,21 @@ int main() {
         {"64x128 BK16x3 w32x64 (4 warps)", run<64, 128, GM_SUB, 16, 3, 32, 64>, 64, 128},
         {"128x128 BK16x3 w64x32 (1 CTA/SM)", run<128, 128, GM_SUB, 16, 3, 64, 32, 1>, 128, 128},
         {"128x128 BK16x4 w32x64 (1 CTA/SM)", run<128, 128, GM_SUB, 16, 4, 32, 64, 1>, 128, 128}};
+    {   // every variant accumulates k in the same order: results must be bit-identical to the product configuration
+        const int64_t r = 1024, c = 1024; const int k = 512;
+        std::vector<double> ref((size_t)r * ld), got((size_t)r * ld);
+        for (auto& v : variants) {
+            cudaMemset(C, 0, (size_t)r * ld * 8);
+            v.fn(A, B, C, ld, r, c, k, 0, 0);   // reps = 0: the two warm-up launches only (C = -2 A B^T)
+            cudaMemcpy(got.data(), C, (size_t)r * ld * 8, cudaMemcpyDeviceToHost);
+            if (&v == &variants[0]) ref = got;
+            size_t bad = 0;
+            for (int64_t i = 0; i < r; i++)
+                for (int64_t j = 0; j < c; j++) bad += got[i * ld + j] != ref[i * ld + j];
+            printf("check %-36s mismatching entries vs product: %zu  (C[0,0] = %.6f)\n", v.name, bad, got[0]);
+        }
+        cudaMemset(C, 0, (size_t)R * ld * 8);
+    }
     struct S2 { int64_t r, c; int k; } vs[] = {{8192, 8192, 8192}, {10112, 4096, 4096}, {10112, 8192, 128}, {10112, 256, 256}};
     printf("\n%-36s", "variant \\ TFLOP/s at shape");
     for (auto s : vs) printf(" %6lldx%lldx%d", (long long)s.r, (long long)s.c, s.k);
