@@ -170,14 +170,35 @@ def _exponential(lam):
     return (lambda x: np.sum(np.log(lam) - lam * x), lambda x: np.full(np.shape(x), -lam), lambda shape: np.full(shape, 1.0 / lam))
 
 
+def ls_bounds_z(gp):
+    """(lower, upper) standardized lengthscale bounds from ``gp.ls_bounds`` -- ``PymcGP._prepare_lengthscales`` (GP.py:630-646).
+
+    ``ls_bounds`` is a ParameterArray with one layer per bounded continuous dimension holding [lower, upper] in natural units
+    (NaN = unbounded); on plain arrays (``ArrayGP``) a dict {dim: (lower_z, upper_z)} already in standardized units.  Only the
+    dimensions named in ``ls_bounds`` contribute, in ``continuous_dims`` order, and the reference's check
+    ``not ARD and len(lower) != 1 or len(upper) != 1`` is kept as written (it rejects more than one bounded dimension)."""
+    lb = getattr(gp, "ls_bounds", None)
+    if lb is None:
+        return None, None
+    is_parray = hasattr(lb, "names")
+    names = list(lb.names) if is_parray else list(lb)
+    zbounds = []
+    for dim in gp.continuous_dims:
+        if dim in names:
+            vals = np.asarray(lb[dim].z.values() if is_parray else lb[dim], dtype=np.float64).squeeze()
+            zbounds.append([None if np.isnan(b) else float(b) for b in vals])
+    lower, upper = list(zip(*zbounds))
+    if not gp.ARD and len(lower) != 1 or len(upper) != 1:
+        raise ValueError("Bounds must be specified for only a single dimension if ARD is False")
+    return lower, upper
+
+
 def build_priors(gp):
     """name -> (logp, dlogp, init) for every free hyper-parameter of ``gp`` (a built B200Backend)."""
     lay = gp._layout
     X = gp._X
     Xs = X[:, lay["idx_s"]]
-    lower = upper = None
-    if getattr(gp, "ls_bounds", None) is not None:
-        raise NotImplementedError("ls_bounds is not supported by the B200 backend yet")
+    lower, upper = ls_bounds_z(gp)
     ls_params = get_ls_prior(Xs, ARD=gp.ARD, lower=lower, upper=upper, mass=gp.mass)
     pri = {}
     for name, shape in gp.param_shapes().items():

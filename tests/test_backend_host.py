@@ -270,3 +270,34 @@ def test_predict_cold_fused_uses_the_one_pass_entry_point():
     n = gp.engine.n_fact
     gp.predict(g["points"])                                     # no second factorisation: the fused pass left the factor behind
     assert gp.engine.n_fact == n
+
+
+def test_ls_bounds_follow_prepare_lengthscales():
+    """fit(ls_bounds=...) (GP.py:630-646): bounds of the named dimension replace the pdist defaults (lower never below the smallest
+    distance / 0.01), NaN = unbounded, and the reference's single-dimension check is kept as written."""
+    from gumbi_b200.map import build_priors, find_constrained_invgamma, get_ls_prior, ls_bounds_z
+
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((40, 1))
+    y = np.sin(X[:, 0])
+    gp = HostGP(X, y, ["x0"])
+    gp.build_model(ls_bounds={"x0": (0.5, 2.0)})
+    assert ls_bounds_z(gp) == ((0.5,), (2.0,))
+    want = find_constrained_invgamma(0.5, 2.0, mass=0.98)
+    pri = build_priors(gp)["ls_total"]
+    x = np.array([0.9])
+    a, b = want["alpha"], want["beta"]
+    assert pri[1](x)[0] == pytest.approx(-(a + 1) / x[0] + b / x[0] ** 2, rel=1e-12)
+    gp.build_model(ls_bounds={"x0": (np.nan, 2.0)})             # NaN lower bound -> the pdist default
+    free = get_ls_prior(X, ARD=True, lower=None, upper=(2.0,), mass=0.98)
+    assert build_priors(gp)["ls_total"][1](x)[0] == pytest.approx(-(free["alpha"][0] + 1) / x[0] + free["beta"][0] / x[0] ** 2, rel=1e-12)
+    gp.build_model(ls_bounds=None)
+    assert ls_bounds_z(gp) == (None, None)
+    X2 = rng.standard_normal((40, 2))
+    gp2 = HostGP(X2, y, ["x0", "x1"])
+    gp2.build_model(ls_bounds={"x0": (0.5, 2.0), "x1": (0.5, 2.0)})
+    with pytest.raises(ValueError, match="single dimension"):   # `... or len(upper) != 1` as written in the reference
+        build_priors(gp2)
+    gp2.build_model(ls_bounds={"x1": (0.5, 2.0)})               # one bounded dimension is broadcast to all (parse_ls_limits)
+    p2 = build_priors(gp2)["ls_total"]
+    assert np.all(np.isfinite(p2[1](np.array([0.9, 1.1]))))

@@ -182,3 +182,21 @@ def test_cross_validate_runs_unmodified_on_the_backend(ref_env):
     assert set(cv) == {"train", "test"}
     for part in cv.values():
         assert np.all(np.isfinite(np.asarray(part["NLPDs"], dtype=float))) and np.all(np.isfinite(np.asarray(part["errors"], dtype=float)))
+
+
+def test_ls_bounds_as_a_parameter_array(ref_env):
+    """fit(ls_bounds=parray) (GP.py:630-646): the bounds are read through ``ls_bounds[dim].z.values()`` exactly as the reference does."""
+    gmb, GP, pd = ref_env
+    from gumbi_b200.map import ls_bounds_z
+
+    df = pd.read_pickle(os.path.join(REF, "gumbi", "data", "Example_DataSet.pkl"))
+    df = df[(df.Name == "binary-pollen") & (df.Color == "cyan") & (df.Metric == "mean")]
+    ds = gmb.DataSet(df, outputs=["a", "b", "c", "d", "e", "f"], log_vars=["Y", "b", "c", "d", "f"], logit_vars=["X", "e"])
+    gp = GP(ds, outputs=["d"])
+    gp.specify_model(continuous_dims="lg10_Z")
+    bounds = gp.parray(lg10_Z=[4.0, 9.0])
+    gp.build_model(ls_bounds=bounds)
+    lower, upper = ls_bounds_z(gp)
+    np.testing.assert_allclose([lower[0], upper[0]], np.asarray(bounds["lg10_Z"].z.values()).squeeze())
+    gp.find_MAP(options={"maxiter": 5})
+    assert np.isfinite(gp.MAP["ls_total"]).all()
