@@ -86,9 +86,11 @@ class B200Backend:
             raise NotImplementedError("Heteroskedasticity over inputs is not yet implemented.")
         if sparse:
             raise NotImplementedError("The B200 backend implements the exact (dense) GP only; sparse=True is out of scope.")
-        if period is not None or str(continuous_kernel).endswith("Periodic"):
-            raise NotImplementedError("Periodic kernels are not implemented in the B200 backend.")
-        assert_in("Continuous kernel", continuous_kernel, CONTINUOUS_KERNELS)
+        kernels = CONTINUOUS_KERNELS + ["Periodic"]
+        kernels += [k + "+Periodic" for k in kernels if k != "Periodic"]          # GP.py:664-674
+        assert_in("Continuous kernel", continuous_kernel, kernels)
+        if "Periodic" in continuous_kernel and period is None:
+            raise ValueError("Period must be specified for periodic kernel")     # GP.py:678-679
 
         X, y = self.get_shaped_data("mean")
         D_in = len(self.dims)
@@ -105,6 +107,7 @@ class B200Backend:
         self.ARD = ARD
         self.ls_bounds = ls_bounds
         self.mass = mass
+        self.period = period
         self.model_specs = {
             "seed": seed,
             "continuous_kernel": continuous_kernel,
@@ -116,16 +119,77 @@ class B200Backend:
         self._X = np.ascontiguousarray(X, dtype=np.float64)
         self._y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
         self._layout = self._model_layout()
+        self._layout["warp"] = self._periodic_warp(continuous_kernel, period)
         want_kron = self._wants_kron()
         if self.engine is not None and want_kron != (type(self.engine).__name__ == "KronEngine"):
             self.engine.close()      # the structure changed between two build_model calls
             self.engine = None
         if self.engine is None:
             self.engine = self._make_kron_engine() if want_kron else self._make_dense_engine()
-        self.engine.set_train(self._X, self._y)
+        self.engine.set_train(self._engine_points(self._X), self._y)
         self._factor_key = None
         self.model = self._layout  # truthy placeholder: the reference asserts ``self.model is not None`` in find_MAP
         return self
+
+    # -- periodic kernels (GP.py:389-447) ---------------------------------------------------------------------------
+    def _periodic_warp(self, continuous_kernel, period):
+        """How ``continuous_kernel="Periodic"`` / ``"<K>+Periodic"`` are lowered onto the stationary kernels of the CUDA core.
+
+        Both are stationary kernels of the warped coordinates u(x) = [sin(2 pi x / T), cos(2 pi x / T)] (the reference's own
+        ``mapping`` for ``WarpedInput``, GP.py:432-435), because |u(x) - u(x')|^2 = 2 - 2 cos(2 pi (x - x') / T) = 4 sin^2(pi (x - x') / T):
+          * ``pm.gp.cov.Periodic``: exp(-1/2 sum_j sin^2(pi (x_j - x'_j) / T_j) / ls_j^2) = ExpQuad on u with lengthscale 2 ls_j;
+          * ``"<K>+Periodic"``: ``WarpedInput(cov_func=K(input_dim=2, ls), warp_func=mapping)`` = K on u with lengthscale ls.
+        The warped columns are appended to every array handed to the engine (O(N) host work); the Linear kernel and the Coregion
+        factors keep reading the original columns.  Returns None for the plain kernels."""
+        if "Periodic" not in continuous_kernel:
+            return None
+        lay = self._layout
+        if hasattr(period, "z"):   # ParameterArray: the reference reads period.z[dim + "_z"] (GP.py:403, :429)
+            zp = [np.asarray(period.z[dim + "_z"].values(), dtype=np.float64).reshape(-1)[0] for dim in self.continuous_dims]
+        else:                      # plain arrays (ArrayGP): {dim: standardized period}
+            zp = [float(period[dim]) for dim in self.continuous_dims]
+        zp = np.asarray(zp, dtype=np.float64)
+        if not np.all(np.isfinite(zp)) or np.any(zp == 0):
+            raise ValueError("periods must be finite and non-zero")
+        base = continuous_kernel.removesuffix("+Periodic")
+        if continuous_kernel != "Periodic" and lay["n_s"] != 1:
+            # the inner kernel is built with input_dim=2 (GP.py:424-426): with several continuous dims it would only see the first
+            # two warped columns -- not a model anybody means
+            raise NotImplementedError('"<kernel>+Periodic" is defined for exactly one continuous dimension')
+        D = len(self.dims)
+        return {"mode": "periodic" if continuous_kernel == "Periodic" else "warped", "kind": "ExpQuad" if continuous_kernel == "Periodic" else base,
+                "c": 2.0 * np.pi / zp, "src": list(lay["idx_s"]), "cols": [D + j for j in range(2 * lay["n_s"])]}
+
+    def _engine_points(self, points):
+        """Columns the engine sees: the model dims, plus the warped coordinates of a periodic kernel."""
+        w = self._layout.get("warp")
+        if not w:
+            return points
+        x = points[:, w["src"]] * w["c"][None, :]
+        return np.ascontiguousarray(np.hstack([points, np.sin(x), np.cos(x)]))
+
+    def _engine_ls(self, ls):
+        """Lengthscales of the engine's stationary kernel for the model's ``ls`` (see ``_periodic_warp``)."""
+        w = self._layout.get("warp")
+        ls = np.atleast_1d(np.asarray(ls, dtype=np.float64))
+        if not w:
+            return ls
+        if w["mode"] == "warped":
+            return ls.reshape(-1)[:1]                                   # one lengthscale shared by sin and cos
+        return 2.0 * (np.concatenate([ls, ls]) if ls.size == self._layout["n_s"] and ls.size > 1 else ls.reshape(-1)[:1])
+
+    def _fold_ls_gradient(self, g):
+        """Gradient w.r.t. the engine's lengthscales -> gradient w.r.t. the model's ``ls``."""
+        w = self._layout.get("warp")
+        g = np.atleast_1d(np.asarray(g, dtype=np.float64))
+        if not w:
+            return g
+        if w["mode"] == "warped":
+            return np.array([g.sum()])
+        n_s = self._layout["n_s"]
+        if g.size == 2 * n_s and n_s > 1 and self.ARD:
+            return 2.0 * (g[:n_s] + g[n_s:])
+        return np.array([2.0 * g.sum()])
 
     def _make_dense_engine(self):
         engine = GPEngine(self.device, self.precision)
@@ -254,8 +318,9 @@ class B200Backend:
         terms = []
         for t in lay["terms"]:
             sfx = t["suffix"]
-            ls = np.atleast_1d(np.asarray(point[f"ls_{sfx}"], dtype=np.float64))
-            term = {"kind": self.continuous_kernel, "cont_idx": list(lay["idx_s"]), "ls": ls.tolist(),
+            warp = lay.get("warp")
+            ls = self._engine_ls(point[f"ls_{sfx}"])
+            term = {"kind": warp["kind"] if warp else self.continuous_kernel, "cont_idx": list(warp["cols"] if warp else lay["idx_s"]), "ls": ls.tolist(),
                     "eta": float(point[f"η_{sfx}"]), "lin_idx": [], "c": [], "tau": 0.0, "coreg": []}
             if lay["n_l"] > 0:
                 term["lin_idx"] = list(lay["idx_l"])
@@ -338,16 +403,16 @@ class B200Backend:
             from . import dist as gdist
 
             lo, hi = gdist.grid_slice(len(points_array), self.engine.rank, self.engine.world)
-            mu, var = self.engine.predict(points_array[lo:hi], pred_noise=bool(with_noise))
+            mu, var = self.engine.predict(self._engine_points(points_array[lo:hi]), pred_noise=bool(with_noise))
             return gdist.gather_grid(mu, var, len(points_array))
-        return self.engine.predict(points_array, pred_noise=bool(with_noise))
+        return self.engine.predict(self._engine_points(points_array), pred_noise=bool(with_noise))
 
     # -- conditional / posterior samples (GP.py:861-979) ------------------------------------------------------------
     def conditional(self, points_array, pred_noise=False):
         """Mean and full covariance of ``gp_dict["total"].conditional(var_name, points_array)`` (GP.py:913-914), on device."""
         self._ensure_factorized()
         points_array = np.atleast_2d(np.asarray(points_array, dtype=np.float64))
-        return self.engine.predict_full(points_array, pred_noise=bool(pred_noise))
+        return self.engine.predict_full(self._engine_points(points_array), pred_noise=bool(pred_noise))
 
     def sample_conditional(self, points_array, size=1, random_seed=None, pred_noise=False):
         """``size`` joint draws from the conditional at ``points_array`` (standardized space), shape (size, M).
@@ -410,7 +475,7 @@ class B200Backend:
             raise NotImplementedError("fused cold predict needs the dense single-GPU engine")
         points_array = np.atleast_2d(np.asarray(points_array, dtype=np.float64))
         self.engine.set_kernel(self.spec_from_point(self.MAP))
-        out = self.engine.factorize_predict(points_array, pred_noise=bool(with_noise))
+        out = self.engine.factorize_predict(self._engine_points(points_array), pred_noise=bool(with_noise))
         self._ensure_factorized_key()
         return out
 

@@ -236,7 +236,7 @@ def named_gradient(gp, gspec):
 
     for t, tg in zip(lay["terms"], gspec["terms"]):
         sfx = t["suffix"]
-        add(f"ls_{sfx}", tg["ls"])
+        add(f"ls_{sfx}", gp._fold_ls_gradient(tg["ls"]))
         add(f"η_{sfx}", tg["eta"])
         if lay["n_l"] > 0:
             add(f"c_{sfx}", tg["c"])

@@ -301,3 +301,76 @@ def test_ls_bounds_follow_prepare_lengthscales():
     gp2.build_model(ls_bounds={"x1": (0.5, 2.0)})               # one bounded dimension is broadcast to all (parse_ls_limits)
     p2 = build_priors(gp2)["ls_total"]
     assert np.all(np.isfinite(p2[1](np.array([0.9, 1.1]))))
+
+
+def reference_form(gp, spec, mode, zp):
+    """The spec the reference would build for a periodic model: original columns, pm.gp.cov.Periodic / WarpedInput semantics."""
+    import copy
+
+    ref = copy.deepcopy(spec)
+    t = ref["terms"][0]
+    t["cont_idx"] = list(gp._layout["idx_s"])
+    t["ls"] = np.atleast_1d(np.asarray(gp.MAP["ls_total"], dtype=np.float64)).tolist()
+    if mode == "Periodic":
+        t["kind"], t["period"] = "Periodic", list(zp)
+    else:
+        t["warp_period"] = list(zp)
+    return ref
+
+
+@pytest.mark.parametrize("kernel,d,ARD", [("Periodic", 1, True), ("Periodic", 3, True), ("Periodic", 2, False), ("Matern52+Periodic", 1, True),
+                                          ("ExpQuad+Periodic", 1, True)])
+def test_periodic_kernels_are_lowered_onto_the_stationary_path(kernel, d, ARD):
+    """continuous_kernel="Periodic" / "<K>+Periodic" (GP.py:389-447, :664-689): the engine sees a stationary kernel on the warped
+    coordinates [sin(2 pi x/T), cos(2 pi x/T)]; posterior, likelihood and ls-gradient equal the reference formulation
+    (pm.gp.cov.Periodic / WarpedInput, restated in oracle/gp_oracle.py) on the original columns."""
+    from gumbi_b200.map import make_objective
+
+    rng = np.random.default_rng(4)
+    X = rng.standard_normal((60, d))
+    y = np.sin(3 * X[:, 0]) + 0.1 * rng.standard_normal(60)
+    dims = [f"x{j}" for j in range(d)]
+    zp = [1.7 + 0.4 * j for j in range(d)]
+    gp = HostGP(X, y, dims, linear_dims=dims[:1])
+    gp.build_model(continuous_kernel=kernel, period=dict(zip(dims, zp)), ARD=ARD)
+    assert gp.engine.X.shape[1] == 3 * d                        # original columns + sin + cos
+    pt = {"ls_total": rng.uniform(0.5, 1.5, size=d if ARD else 1), "η_total": 1.3, "σ": 0.2, "c_total": [0.1], "τ_total": 0.3}
+    gp.find_MAP(point=pt)
+    spec = gp.spec_from_point(gp.MAP)
+    assert spec["terms"][0]["kind"] == ("ExpQuad" if kernel == "Periodic" else kernel.split("+")[0])
+    ref = reference_form(gp, spec, "Periodic" if kernel == "Periodic" else "warped", zp)
+    Xs = rng.standard_normal((25, d))
+    mu, var = gp.predict(Xs, with_noise=True)
+    mu0, var0 = orc.predict(ref, X, y, Xs, True)
+    np.testing.assert_allclose(mu, mu0, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(var, var0, rtol=1e-8, atol=1e-11)
+    assert gp.marginal_log_likelihood() == pytest.approx(orc.mll(ref, X, y), rel=1e-11)
+    # the objective's gradient w.r.t. log(ls) against central differences of the reference-form likelihood + prior
+    fun, x0, unpack, names, positive = make_objective(gp)
+    x = x0.copy()
+    f0, g0 = fun(x)
+    i0 = 0
+    for n in names:
+        size = int(np.prod(gp.param_shapes()[n])) if gp.param_shapes()[n] != () else 1
+        if n == "ls_total":
+            for k in range(size):
+                e = np.zeros_like(x); e[i0 + k] = 1e-6
+                num = (fun(x + e)[0] - fun(x - e)[0]) / 2e-6
+                assert g0[i0 + k] == pytest.approx(num, rel=2e-5, abs=1e-7)
+        i0 += size
+
+
+def test_periodic_argument_errors():
+    X = np.random.default_rng(0).standard_normal((20, 2))
+    y = X[:, 0]
+    gp = HostGP(X, y, ["x0", "x1"])
+    with pytest.raises(ValueError, match="Period must be specified"):
+        gp.build_model(continuous_kernel="ExpQuad+Periodic")
+    with pytest.raises(ValueError, match="Period must be specified"):
+        gp.build_model(continuous_kernel="Periodic")
+    with pytest.raises(NotImplementedError, match="one continuous dimension"):
+        gp.build_model(continuous_kernel="ExpQuad+Periodic", period={"x0": 1.0, "x1": 2.0})
+    with pytest.raises(ValueError, match="Continuous kernel"):
+        gp.build_model(continuous_kernel="Periodic+Periodic", period={"x0": 1.0, "x1": 2.0})
+    with pytest.raises(ValueError, match="non-zero"):
+        gp.build_model(continuous_kernel="Periodic", period={"x0": 0.0, "x1": 2.0})

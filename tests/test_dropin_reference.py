@@ -200,3 +200,23 @@ def test_ls_bounds_as_a_parameter_array(ref_env):
     np.testing.assert_allclose([lower[0], upper[0]], np.asarray(bounds["lg10_Z"].z.values()).squeeze())
     gp.find_MAP(options={"maxiter": 5})
     assert np.isfinite(gp.MAP["ls_total"]).all()
+
+
+def test_periodic_kernel_with_a_parameter_array_period(ref_env):
+    """build_model(continuous_kernel="ExpQuad+Periodic", period=parray) (GP.py:403, :429): the period is read as
+    ``period.z[dim + "_z"]`` like the reference does, and predict_grid runs through the warped-coordinate lowering."""
+    gmb, GP, pd = ref_env
+    df = pd.read_pickle(os.path.join(REF, "gumbi", "data", "Example_DataSet.pkl"))
+    df = df[(df.Name == "binary-pollen") & (df.Color == "cyan") & (df.Metric == "mean")]
+    ds = gmb.DataSet(df, outputs=["a", "b", "c", "d", "e", "f"], log_vars=["Y", "b", "c", "d", "f"], logit_vars=["X", "e"])
+    for kernel in ("ExpQuad+Periodic", "Periodic"):
+        gp = GP(ds, outputs=["d"])
+        gp.specify_model(continuous_dims="lg10_Z")
+        period = gp.parray(lg10_Z=12.0)
+        gp.build_model(continuous_kernel=kernel, period=period)
+        zp = float(np.asarray(period.z["lg10_Z_z"].values()).reshape(-1)[0])
+        np.testing.assert_allclose(gp._layout["warp"]["c"], [2 * np.pi / zp])
+        gp.find_MAP(options={"maxiter": 8})
+        gp.prepare_grid(resolution=11)
+        up = gp.predict_grid()
+        assert up.shape == (11,) and np.all(np.isfinite(up.μ)) and np.all(up.σ2 > 0)
