@@ -373,6 +373,13 @@ class B200Backend:
                 out[name + "_log__"] = np.log(val)  # pm.find_MAP also returns the transformed values
         return out
 
+    # -- inference modes that stay with PyMC (GP.py:759-797, :815-835) -------------------------------------------------
+    def build_latent(self, *args, **kwargs):
+        raise NotImplementedError("Latent GPs (pm.gp.Latent) are out of scope of the B200 backend; use PymcGP.build_latent.")
+
+    def sample(self, *args, **kwargs):
+        raise NotImplementedError("MCMC over the hyper-parameters is out of scope of the B200 backend (MAP inference only); use PymcGP.sample.")
+
     # -- predict (GP.py:837-849) --------------------------------------------------------------------------------------
     def _ensure_factorized(self):
         if self.MAP is None:

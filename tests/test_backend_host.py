@@ -374,3 +374,16 @@ def test_periodic_argument_errors():
         gp.build_model(continuous_kernel="Periodic+Periodic", period={"x0": 1.0, "x1": 2.0})
     with pytest.raises(ValueError, match="non-zero"):
         gp.build_model(continuous_kernel="Periodic", period={"x0": 0.0, "x1": 2.0})
+
+
+def test_inference_modes_left_to_pymc_raise():
+    g = load_golden("simple_regression_ExpQuad")
+    gp = gp_from_golden(g)
+    with pytest.raises(NotImplementedError):
+        gp.build_latent()
+    with pytest.raises(NotImplementedError):
+        gp.sample(100)
+    with pytest.raises(NotImplementedError):
+        gp.build_model(sparse=True)
+    with pytest.raises(NotImplementedError):
+        gp.build_model(heteroskedastic_inputs=True)
