@@ -1,7 +1,8 @@
-"""Device tests of the Kronecker-aware multi-output solve (gumbi_b200/kron.py) -- CUDA block engines through the C ABI against the
-dense CUDA path, the dense oracle and the committed golden vectors.  (Sorted last on purpose: this path was added after the
-round's GPU minutes were spent, so its first device run is the driver's; the block engines only use single-output code paths
-that the parity tests above already cover, plus ``gb2_get_alpha``.)"""
+"""Device tests of what was built after round 1's GPU minutes were spent: the Kronecker-aware multi-output solve
+(gumbi_b200/kron.py), ``gb2_get_alpha``, the ``solve_streams`` option, the fused cold predict (``gb2_factorize_predict``) and the
+periodic-kernel lowering -- CUDA engines through the C ABI against the dense CUDA path, the oracle and the committed golden vectors.
+Sorted last on purpose: their first device run is the driver's round-end run, and a failure here must not hide the suite above.
+(The Kronecker blocks and the periodic kernels only use device code paths the parity tests above already cover.)"""
 import numpy as np
 import pytest
 
