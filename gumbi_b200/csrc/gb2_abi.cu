@@ -661,7 +661,7 @@ static int build_K(gb2_handle* h, int& launches) {
 }
 
 // Prediction points of a fused cold predict (gb2_factorize_predict); M == 0: plain factorisation.
-struct ExtPredict { const double* Xs = nullptr; int64_t M = 0; int32_t pred_noise = 0; double* mean = nullptr; double* var = nullptr; };
+struct ExtPredict { const double* Xs = nullptr; int64_t M = 0; int32_t pred_noise = 0; double* mean = nullptr; double* var = nullptr; bool dev = false; };
 
 static int factorize_impl(gb2_handle* h, const ExtPredict& x) {
     GB2_ARG(h, h->have_train, "gb2_factorize: no training data (call gb2_set_train)");
@@ -681,13 +681,17 @@ static int factorize_impl(gb2_handle* h, const ExtPredict& x) {
         if ((rc = ensure(h, h->dAt, h->At_cap, Mp * Np))) return rc;
         if ((rc = ensure(h, h->dFs, h->Fs_cap, (int64_t)std::max(1, h->kp.n_feat) * Mp))) return rc;
         if ((rc = ensure(h, h->dCs, h->Cs_cap, (int64_t)std::max(1, h->kp.n_cat) * Mp))) return rc;
-        if ((rc = ensure(h, h->dXs, h->Xs_cap, x.M * h->D_in))) return rc;
-        int64_t oc = h->out_cap;
-        if ((rc = ensure(h, h->dMean, oc, x.M))) return rc;
-        if ((rc = ensure(h, h->dVar, h->out_cap, x.M))) return rc;
+        const double* dXs = x.Xs;
+        if (!x.dev) {
+            if ((rc = ensure(h, h->dXs, h->Xs_cap, x.M * h->D_in))) return rc;
+            int64_t oc = h->out_cap;
+            if ((rc = ensure(h, h->dMean, oc, x.M))) return rc;
+            if ((rc = ensure(h, h->dVar, h->out_cap, x.M))) return rc;
+            GB2_CUDA(h, cudaMemcpyAsync(h->dXs, x.Xs, (size_t)x.M * h->D_in * sizeof(double), cudaMemcpyHostToDevice, s));
+            dXs = h->dXs;
+        }
         // K(X*, X) as rows below the factor, exactly as gb2_predict builds it
-        GB2_CUDA(h, cudaMemcpyAsync(h->dXs, x.Xs, (size_t)x.M * h->D_in * sizeof(double), cudaMemcpyHostToDevice, s));
-        prep_features<<<(unsigned)((Mp + 255) / 256), 256, 0, s>>>(h->dXs, x.M, Mp, h->pp, h->dFs, h->dCs, h->dInfo + 1);
+        prep_features<<<(unsigned)((Mp + 255) / 256), 256, 0, s>>>(dXs, x.M, Mp, h->pp, h->dFs, h->dCs, h->dInfo + 1);
         dim3 grid((unsigned)(Np / KB_T), (unsigned)(Mp / KB_T));
         kbuild_dmma_launch<false>(s, grid, kbuild_dmma_smem_bytes(h->kp), h->kp, h->dBtab, h->dFs, h->dCs, Mp, x.M, h->dF, h->dC, Np, N, nullptr,
                                   h->dAt, Np, 1, 0, 0, h->opt_kbuild_occ);
@@ -700,11 +704,13 @@ static int factorize_impl(gb2_handle* h, const ExtPredict& x) {
     GB2_CUDA(h, cudaEventRecord(h->ev[3], s));
     if (x.M > 0) {
         posterior_reduce_kernel<<<(unsigned)((x.M + 7) / 8), 256, 0, s>>>(h->kp, h->dBtab, h->dFs, h->dCs, Mp, h->dAt, Np, h->dA + N * Np, N, x.M,
-                                                                         x.pred_noise, h->dMean, h->dVar);
+                                                                         x.pred_noise, x.dev ? x.mean : h->dMean, x.dev ? x.var : h->dVar);
         launches++;
         GB2_CUDA(h, cudaEventRecord(h->ev[4], s));
-        GB2_CUDA(h, cudaMemcpyAsync(x.mean, h->dMean, (size_t)x.M * sizeof(double), cudaMemcpyDeviceToHost, s));
-        GB2_CUDA(h, cudaMemcpyAsync(x.var, h->dVar, (size_t)x.M * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (!x.dev) {
+            GB2_CUDA(h, cudaMemcpyAsync(x.mean, h->dMean, (size_t)x.M * sizeof(double), cudaMemcpyDeviceToHost, s));
+            GB2_CUDA(h, cudaMemcpyAsync(x.var, h->dVar, (size_t)x.M * sizeof(double), cudaMemcpyDeviceToHost, s));
+        }
     }
     int info[2] = {0, 0};
     GB2_CUDA(h, cudaMemcpyAsync(info, h->dInfo, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -751,6 +757,15 @@ int gb2_factorize_predict(gb2_handle* h, const double* Xs, int64_t M, int32_t pr
     GB2_ARG(h, M >= 1, "M must be >= 1");
     ExtPredict x;
     x.Xs = Xs; x.M = M; x.pred_noise = pred_noise; x.mean = mean; x.var = var;
+    return factorize_impl(h, x);
+}
+
+int gb2_factorize_predict_dev(gb2_handle* h, const double* dXs, int64_t M, int32_t pred_noise, double* dmean, double* dvar) {
+    if (!h) return -1;
+    GB2_ARG(h, dXs && dmean && dvar, "null pointer");
+    GB2_ARG(h, M >= 1, "M must be >= 1");
+    ExtPredict x;
+    x.Xs = dXs; x.M = M; x.pred_noise = pred_noise; x.mean = dmean; x.var = dvar; x.dev = true;
     return factorize_impl(h, x);
 }
 

@@ -210,6 +210,14 @@ class GPEngine:
             "predict_dev",
         )
 
+    def factorize_predict_device(self, dXs_ptr: int, M: int, pred_noise: bool, dmean_ptr: int, dvar_ptr: int):
+        """``factorize_predict`` on device pointers (no host copies)."""
+        self._check(
+            self._lib.gb2_factorize_predict_dev(self._h, C.c_void_p(dXs_ptr), int(M), int(bool(pred_noise)), C.c_void_p(dmean_ptr),
+                                                C.c_void_p(dvar_ptr)),
+            "factorize_predict_dev",
+        )
+
     def mark(self, slot: int):
         """Record a timing mark on the handle's stream (device-side timing for benchmarks)."""
         self._check(self._lib.gb2_mark(self._h, int(slot)), "mark")

@@ -134,6 +134,7 @@ int gb2_predict_dev(gb2_handle* h, const double* dXs, int64_t M, int32_t pred_no
  * separate triangular solve afterwards.  Same results as the two calls up to summation order; leaves the handle factorised.
  * fp64, replicated storage, M * round_up(N+1,128) * 8 bytes <= 8 GiB.  Multi-GPU: collective, each rank passes its own points. */
 int gb2_factorize_predict(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_noise, double* mean, double* var);
+int gb2_factorize_predict_dev(gb2_handle* h, const double* dXs, int64_t M, int32_t pred_noise, double* dmean, double* dvar);
 
 /* Posterior mean and FULL covariance at Xs:(M,D_in): cov:(M,M) row-major = K(X*,X*) - A^T A (+ noise diag if pred_noise).
  * Replaces the distribution gp.conditional(var_name, points_array) builds for draw_point_samples / draw_grid_samples

@@ -158,6 +158,13 @@ def test_fused_cold_predict_matches_factorize_then_predict(lib_built, n, d, P, k
     mu, var = e.factorize_predict(Xs, True)
     np.testing.assert_allclose(mu, mu_o, rtol=1e-6, atol=1e-8)
     np.testing.assert_allclose(var, var_o, rtol=1e-5, atol=1e-8)
+    import torch
+
+    dXs = torch.from_numpy(np.ascontiguousarray(Xs)).cuda()        # device-pointer twin: no host copies
+    dout = torch.zeros(2 * len(Xs), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    e.factorize_predict_device(dXs.data_ptr(), len(Xs), True, dout.data_ptr(), dout.data_ptr() + 8 * len(Xs))
+    assert np.array_equal(dout[:len(Xs)].cpu().numpy(), mu) and np.array_equal(dout[len(Xs):].cpu().numpy(), var)
     mu1, var1 = e.factorize_predict(Xs[:1], True)                 # a single point
     np.testing.assert_allclose(mu1, mu_o[:1], rtol=1e-6, atol=1e-8)
     bad = dict(spec, sigma=0.0, jitter=0.0)
