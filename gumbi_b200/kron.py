@@ -116,9 +116,13 @@ class KronEngine:
     ``gather(obj) -> [obj_rank0, ...]`` (``torch.distributed.all_gather_object``), the only communication of this path.
     """
 
-    def __init__(self, make_engine, pcol: int, P: int, rank: int = 0, world: int = 1, gather=None):
+    def __init__(self, make_engine, pcol: int, P: int, rank: int = 0, world: int = 1, gather=None, threads: int = 1):
         if world > 1 and gather is None:
             raise ValueError("world > 1 needs a gather callable")
+        # threads > 1: this rank's blocks are driven from that many host threads at once (every block engine owns its handle and
+        # streams, the C ABI keeps no shared mutable state and ctypes drops the GIL), so that on one GPU the factorisation of one
+        # block fills the SM slots another block's critical chain leaves idle.  Same arithmetic per block: identical results.
+        self.threads = int(threads)
         self.make_engine = make_engine
         self.pcol, self.P = int(pcol), int(P)
         self.kron_rank, self.kron_world, self.gather = int(rank), int(world), gather
@@ -162,11 +166,24 @@ class KronEngine:
                 self.blocks[q] = self.make_engine()
                 for k, v in self.options.items():
                     self.blocks[q].set_option(k, v)
+
+        def one(q):
             e = self.blocks[q]
             e.set_train(self.Xb, self.Yt[q])
             e.set_kernel(self.block_spec(q))
             e.factorize()
+
+        self._each(one)
         self.factorized = True
+
+    def _each(self, fn):
+        """{q: fn(q)} over this rank's blocks, on ``self.threads`` host threads when asked to."""
+        if self.threads > 1 and len(self.mine) > 1:
+            from concurrent.futures import ThreadPoolExecutor
+
+            with ThreadPoolExecutor(max_workers=min(self.threads, len(self.mine))) as pool:
+                return dict(zip(self.mine, pool.map(fn, self.mine)))
+        return {q: fn(q) for q in self.mine}
 
     def _collect(self, local: dict):
         """{q: value} from every rank -> list indexed by q."""
@@ -178,13 +195,13 @@ class KronEngine:
 
     def mll(self):
         self._need_factor()
-        vals = self._collect({q: float(self.blocks[q].mll()) for q in self.mine})
+        vals = self._collect(self._each(lambda q: float(self.blocks[q].mll())))
         return float(np.sum(vals) - 0.5 * self.n * np.log(self.D).sum())
 
     def predict(self, Xs, pred_noise: bool = True):
         self._need_factor()
         rest, pstar, uniq, inv = self._split_points(Xs)
-        res = self._collect({q: self.blocks[q].predict(uniq, pred_noise=False) for q in self.mine})
+        res = self._collect(self._each(lambda q: self.blocks[q].predict(uniq, pred_noise=False)))
         A = self.Tinv[:, pstar]                                                   # (P, M')
         mean = np.zeros(len(pstar))
         var = np.zeros(len(pstar))
@@ -198,7 +215,7 @@ class KronEngine:
     def predict_full(self, Xs, pred_noise: bool = False):
         self._need_factor()
         rest, pstar, uniq, inv = self._split_points(Xs)
-        res = self._collect({q: self.blocks[q].predict_full(uniq, pred_noise=False) for q in self.mine})
+        res = self._collect(self._each(lambda q: self.blocks[q].predict_full(uniq, pred_noise=False)))
         A = self.Tinv[:, pstar]
         mean = np.zeros(len(pstar))
         cov = np.zeros((len(pstar), len(pstar)))
@@ -218,11 +235,11 @@ class KronEngine:
           dD[p]    = sum G o (E_pp  (x) I ) = 1/2 [T (Aa - diag(tr K_q^-1)) T^T]_pp,                 Aa[q,q'] = alpha~_q^T alpha~_q'
         with Kx alpha~_q = (y~_q - alpha~_q)/lam_q and tr K_q^-1 = alpha~_q^T alpha~_q - d mll_q/d sigma_q (sigma_q = 1)."""
         self._need_factor()
-        local = {}
-        for q in self.mine:
+        def one(q):
             val, g = self.blocks[q].mll_grad(self.block_spec(q))
-            local[q] = (float(val), g, np.asarray(self.blocks[q].get_alpha(), dtype=np.float64))
-        res = self._collect(local)
+            return float(val), g, np.asarray(self.blocks[q].get_alpha(), dtype=np.float64)
+
+        res = self._collect(self._each(one))
         P, n, lam, T = self.P, self.n, self.lam, self.T
         val = float(sum(r[0] for r in res) - 0.5 * n * np.log(self.D).sum())
         alpha = np.stack([r[2] for r in res])                                     # (P, n) alpha~_q

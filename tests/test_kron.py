@@ -242,3 +242,22 @@ def test_blocks_dealt_over_two_ranks_gloo(tmp_path):
     outs = [p.communicate(timeout=300)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"WORKER_OK {r}" in o, o
+
+
+def test_blocks_driven_from_several_host_threads_give_identical_results():
+    X, y, kw = synthetic(n=35, P=4, d=2, seed=9)
+    a = HostKronGP(X, y, **kw)
+    a.build_model()
+    b = HostKronGP(X, y, **kw)
+    b.build_model()
+    b.engine.threads = 3
+    pt = random_point(a, 6)
+    a.find_MAP(point=pt)
+    b.find_MAP(point=pt)
+    ra, rb = a.predict(X[::2]), b.predict(X[::2])
+    assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1])
+    assert a.marginal_log_likelihood() == b.marginal_log_likelihood()
+    spec = a.spec_from_point(a.MAP)
+    ga, gb = a.engine.mll_grad(spec), b.engine.mll_grad(spec)
+    assert ga[0] == gb[0]
+    np.testing.assert_array_equal(ga[1]["terms"][0]["coreg"][0]["W"], gb[1]["terms"][0]["coreg"][0]["W"])

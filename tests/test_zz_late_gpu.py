@@ -55,6 +55,10 @@ def test_kron_matches_dense_cuda_path(lib_built, kernel, extra_cat, hetero):
     for name in n_d:
         np.testing.assert_allclose(n_k[name], n_d[name], rtol=1e-5, atol=1e-6, err_msg=name)
     assert kr.predict(pts[:0])[0].shape == (0,)
+    seq = kr.predict_cold(pts)
+    kr.engine.threads = 3                                         # all blocks in flight at once: same arithmetic per block
+    par = kr.predict_cold(pts)
+    assert np.array_equal(seq[0], par[0]) and np.array_equal(seq[1], par[1])
     dense.engine.close()
     kr.engine.close()
 
