@@ -261,3 +261,27 @@ def test_blocks_driven_from_several_host_threads_give_identical_results():
     ga, gb = a.engine.mll_grad(spec), b.engine.mll_grad(spec)
     assert ga[0] == gb[0]
     np.testing.assert_array_equal(ga[1]["terms"][0]["coreg"][0]["W"], gb[1]["terms"][0]["coreg"][0]["W"])
+
+
+def test_kron_with_a_periodic_kernel_shifts_the_warped_columns():
+    """Periodic lowering appends warped columns AFTER the output column; the block problems drop the output column, so every
+    column index above it moves down by one (kron.split_spec)."""
+    X, y, kw = synthetic(n=29, P=3, d=2, seed=12, linear=True)
+    period = {"x0": 1.9, "x1": 2.4}
+    dense = HostGP(X, y, **kw)
+    dense.build_model(continuous_kernel="Periodic", period=period)
+    kr = HostKronGP(X, y, **kw)
+    kr.build_model(continuous_kernel="Periodic", period=period)
+    pt = random_point(dense, 3)
+    dense.find_MAP(point=pt)
+    kr.find_MAP(point=pt)
+    pts = X[::3].copy()
+    pts[:, 0] += 0.1
+    mu_d, var_d = dense.predict(pts)
+    mu_k, var_k = kr.predict(pts)
+    np.testing.assert_allclose(mu_k, mu_d, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(var_k, var_d, rtol=1e-8, atol=1e-12)
+    spec = dense.spec_from_point(dense.MAP)
+    n_d, n_k = named_gradient(dense, dense.engine.mll_grad(spec)[1]), named_gradient(kr, kr.engine.mll_grad(spec)[1])
+    for name in n_d:
+        np.testing.assert_allclose(n_k[name], n_d[name], rtol=1e-7, atol=1e-8, err_msg=name)
