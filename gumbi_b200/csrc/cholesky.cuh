@@ -638,12 +638,22 @@ inline int factor_steps(gb2_handle* h, int k0, int k1, int col_limit) {
                 cudaEventRecord(e, sp);
                 cudaStreamWaitEvent(sm, e, 0);
             }
+            // Column blocks are grouped w at a time (opt_fused_group): inside a group the next column receives a narrow left-looking
+            // update from the group's earlier columns, and the bulk right-looking update of everything right of the group is ONE
+            // GEMM of depth w*128 when the group closes -- w times fewer read-modify-write passes over E, w times the depth per launch.
+            const int w = h->opt_fused_group, gw = (k / w) * w, pcol = k - gw;   // group start, position inside the group
+            double* Eg = h->ext_At + (int64_t)gw * TILE;
             double* Ek = h->ext_At + g0;
+            if (pcol > 0) {
+                dgemm_nt_launch<128, 64, GM_SUB>(sm, Eg, h->ext_ld, A + g0 * ld + (int64_t)gw * TILE, ld, Ek, h->ext_ld, h->ext_rows, TILE,
+                                                 pcol * TILE, 0, 0, 0);
+                launches++;
+            }
             dgemm_nt_launch<64, 128, GM_SET>(sm, Ek, h->ext_ld, Dk, TILE, Ek, h->ext_ld, h->ext_rows, TILE, TILE, 0, 0, 0);
             launches++;
-            if (k + 1 < h->ext_ncols) {
-                dgemm_nt_launch<128, 64, GM_SUB>(sm, Ek, h->ext_ld, A + (g0 + TILE) * ld + g0, ld, Ek + TILE, h->ext_ld, h->ext_rows,
-                                                 (int64_t)(h->ext_ncols - (k + 1)) * TILE, TILE, 0, 0, 0);
+            if ((pcol == w - 1 || k == h->ext_ncols - 1) && k + 1 < h->ext_ncols) {
+                dgemm_nt_launch<128, 64, GM_SUB>(sm, Eg, h->ext_ld, A + (g0 + TILE) * ld + (int64_t)gw * TILE, ld, Ek + TILE, h->ext_ld, h->ext_rows,
+                                                 (int64_t)(h->ext_ncols - (k + 1)) * TILE, (pcol + 1) * TILE, 0, 0, 0);
                 launches++;
             }
         }

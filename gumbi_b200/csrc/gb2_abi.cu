@@ -1093,6 +1093,11 @@ int gb2_set_option(gb2_handle* h, const char* name, int value) {
         h->opt_solve_streams = value;
         return 0;
     }
+    if (!strcmp(name, "fused_group")) {   // gb2_factorize_predict: column blocks per bulk update of the prediction rows
+        GB2_ARG(h, value == 1 || value == 2 || value == 4 || value == 8, "fused_group must be 1, 2, 4 or 8");
+        h->opt_fused_group = value;
+        return 0;
+    }
     if (!strcmp(name, "fastdiag")) { h->opt_fastdiag = value ? 1 : 0; return 0; }   // ablation: Cholesky critical-path fast path
     if (!strcmp(name, "chain_on_panel")) { h->opt_chain_on_panel = value ? 1 : 0; return 0; }   // ablation: Cholesky stream choreography
     if (!strcmp(name, "kbuild_occ")) {   // register bound of the strip K-build: 3 or 4 resident CTAs per SM

@@ -179,7 +179,8 @@ int gb2_dist_allgather_dev(gb2_handle* h, const double* dsend, double* drecv, in
  *   "p2p"           1|0  multi-GPU panel exchange through NVLink peer mappings (default) or NCCL broadcast + all-gather
  *   "tf32_nb"       0..16  GB2_TF32 factor-panel width in 128-column blocks (0 = auto); "tf32_leaf" 1..16 fp64 leaf width of the solve
  *   "lookahead"     1|0  panel look-ahead on a second stream;  "fastdiag", "kbuild_v1": ablations
- *   "solve_streams" 1..4 fp64 predict solve: row slabs of the prediction points on this many concurrent streams (default 1)    */
+ *   "solve_streams" 1..4 fp64 predict solve: row slabs of the prediction points on this many concurrent streams (default 1)
+ *   "fused_group"   1|2|4|8  gb2_factorize_predict: column blocks per bulk update of the prediction rows (default 4)            */
 int gb2_set_option(gb2_handle* h, const char* name, int value);
 
 #ifdef __cplusplus

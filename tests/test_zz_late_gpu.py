@@ -154,6 +154,12 @@ def test_fused_cold_predict_matches_factorize_then_predict(lib_built, n, d, P, k
         mu, var = e.factorize_predict(Xs, noise)
         np.testing.assert_allclose(mu, ref[noise][0], rtol=1e-9, atol=1e-10)
         np.testing.assert_allclose(var, ref[noise][1], rtol=1e-7, atol=1e-10)
+    for group in (1, 2, 8):                                       # column blocks per bulk update of the prediction rows (default 4)
+        e.set_option("fused_group", group)
+        mu, var = e.factorize_predict(Xs, True)
+        np.testing.assert_allclose(mu, ref[True][0], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(var, ref[True][1], rtol=1e-7, atol=1e-10)
+    e.set_option("fused_group", 4)
     assert np.array_equal(e.get_L(), L_ref)                       # the factorisation itself is untouched by the extra rows
     mu2, var2 = e.predict(Xs[:50], True)                          # and the handle is left factorised
     np.testing.assert_allclose(mu2, ref[True][0][:50], rtol=1e-12, atol=1e-13)

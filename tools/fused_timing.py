@@ -33,9 +33,12 @@ def one_call():
 
 
 ref = None
-for name, fn, streams in (("factorize+predict", two_calls, 1), ("factorize+predict solve_streams=2", two_calls, 2),
-                          ("factorize+predict solve_streams=4", two_calls, 4), ("factorize_predict (fused)", one_call, 1)):
+for name, fn, streams, group in (("factorize+predict", two_calls, 1, 4), ("factorize+predict solve_streams=2", two_calls, 2, 4),
+                                 ("factorize+predict solve_streams=4", two_calls, 4, 4), ("factorize_predict fused_group=1", one_call, 1, 1),
+                                 ("factorize_predict fused_group=2", one_call, 1, 2), ("factorize_predict fused_group=4", one_call, 1, 4),
+                                 ("factorize_predict fused_group=8", one_call, 1, 8)):
     e.set_option("solve_streams", streams)
+    e.set_option("fused_group", group)
     for _ in range(3):
         out = fn()
     t0 = time.perf_counter()

@@ -10,6 +10,6 @@ for s in 2 4; do timeout 300 python bench.py --no-cpu --opt solve_streams=$s 2>&
 # kernel-only rates of the DMMA GEMM per launch shape (full waves vs the recursion's partial waves)
 timeout 300 ./tools/micro_dgemm 2>&1 | tee gpurun_out/micro_dgemm_r02a.log
 # cold predict: factorise-then-solve (1/2/4 solve streams) against the fused one-pass entry point
-timeout 300 python tools/fused_timing.py 2>&1 | tail -6 | tee gpurun_out/fused_timing_r02a.log
+timeout 300 python tools/fused_timing.py 2>&1 | tail -8 | tee gpurun_out/fused_timing_r02a.log
 # (2+ GPUs, separate call)  python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/replicate_timing.py
 #                           python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 tools/c5_kron_demo.py
