@@ -156,7 +156,7 @@ class KronEngine:
         t["tau"] = self.block_term["tau"] * self.lam[q]
         return {"terms": [t], "sigma": 1.0, "noise_coreg": None, "jitter": 0.0}
 
-    def factorize(self):
+    def factorize(self, _predict_points=None):
         if self.spec is None:
             raise RuntimeError("factorize called before set_kernel")
         self.lam, self.T, self.Tinv = rotation(self.B, self.D)
@@ -171,10 +171,21 @@ class KronEngine:
             e = self.blocks[q]
             e.set_train(self.Xb, self.Yt[q])
             e.set_kernel(self.block_spec(q))
-            e.factorize()
+            if _predict_points is None:
+                e.factorize()
+                return None
+            return e.factorize_predict(_predict_points, pred_noise=False)
 
-        self._each(one)
+        self._block_posteriors = self._each(one)
         self.factorized = True
+
+    def factorize_predict(self, Xs, pred_noise: bool = True):
+        """``factorize()`` + ``predict()`` with every block going through its engine's one-pass entry point (gb2_factorize_predict)."""
+        if self.spec is None:
+            raise RuntimeError("factorize_predict called before set_kernel")
+        rest, pstar, uniq, inv = self._split_points(Xs)
+        self.factorize(_predict_points=uniq)
+        return self._combine(self._collect(self._block_posteriors), pstar, inv, pred_noise)
 
     def _each(self, fn):
         """{q: fn(q)} over this rank's blocks, on ``self.threads`` host threads when asked to."""
@@ -202,6 +213,10 @@ class KronEngine:
         self._need_factor()
         rest, pstar, uniq, inv = self._split_points(Xs)
         res = self._collect(self._each(lambda q: self.blocks[q].predict(uniq, pred_noise=False)))
+        return self._combine(res, pstar, inv, pred_noise)
+
+    def _combine(self, res, pstar, inv, pred_noise):
+        """Block posteriors (mu_q, var_q at the distinct inputs) -> posterior at the requested (input, output) pairs."""
         A = self.Tinv[:, pstar]                                                   # (P, M')
         mean = np.zeros(len(pstar))
         var = np.zeros(len(pstar))

@@ -285,3 +285,35 @@ def test_kron_with_a_periodic_kernel_shifts_the_warped_columns():
     n_d, n_k = named_gradient(dense, dense.engine.mll_grad(spec)[1]), named_gradient(kr, kr.engine.mll_grad(spec)[1])
     for name in n_d:
         np.testing.assert_allclose(n_k[name], n_d[name], rtol=1e-7, atol=1e-8, err_msg=name)
+
+
+def test_fused_cold_predict_through_the_blocks():
+    """predict_cold(fused=True) on the Kronecker solver: every block uses its engine's one-pass entry point."""
+    class Fused(OracleEngine):
+        n_fused = 0
+
+        def factorize_predict(self, Xs, pred_noise=True):
+            Fused.n_fused += 1
+            self.factorize()
+            return self.predict(Xs, pred_noise)
+
+    class G(HostKronGP):
+        def _make_block_engine(self):
+            return Fused()
+
+    X, y, kw = synthetic(n=31, P=3, d=2, seed=2)
+    gp = G(X, y, **kw)
+    gp.build_model()
+    ref = HostKronGP(X, y, **kw)
+    ref.build_model()
+    pt = random_point(gp, 4)
+    gp.find_MAP(point=pt)
+    ref.find_MAP(point=pt)
+    pts = X[::2]
+    for noise in (True, False):
+        a = gp.predict_cold(pts, with_noise=noise, fused=True)
+        b = ref.predict(pts, with_noise=noise)
+        np.testing.assert_allclose(a[0], b[0], rtol=1e-12)
+        np.testing.assert_allclose(a[1], b[1], rtol=1e-12)
+    assert Fused.n_fused == 6
+    np.testing.assert_allclose(gp.predict(pts)[0], ref.predict(pts)[0], rtol=1e-12)   # the factors stay resident

@@ -3,7 +3,7 @@
 # run), Kronecker vs dense cold-predict timing on BASELINE config 3, default bench line.
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -15 | tee gpurun_out/pytest_gpu_r02a.log
-timeout 600 python tools/kron_timing.py 2>&1 | tail -5 | tee gpurun_out/kron_timing_r02a.log
+timeout 600 python tools/kron_timing.py 2>&1 | tail -8 | tee gpurun_out/kron_timing_r02a.log
 timeout 600 python bench.py 2>&1 | tail -2 | tee gpurun_out/bench_r02a.log
 # wave-tail filling of the predict solve: prediction rows as 2 / 4 concurrent slabs (default 1)
 for s in 2 4; do timeout 300 python bench.py --no-cpu --opt solve_streams=$s 2>&1 | tail -1 | tee gpurun_out/bench_r02a_streams$s.log; done

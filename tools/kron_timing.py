@@ -26,16 +26,17 @@ def main():
              "W_Output_noise": spec["noise_coreg"]["W"], "κ_Output_noise": spec["noise_coreg"]["kappa"]}
     kw = dict(categorical_dims=["Variable"], categorical_levels={"Variable": [f"y{p}" for p in range(P)]}, outputs=[f"y{p}" for p in range(P)])
     out = {}
-    for mode in ("kron", "kron-threads", "dense"):
-        gp = ArrayGP(X, y, [f"x{j}" for j in range(d)], multioutput="dense" if mode == "dense" else "kron", **kw)
+    for mode in ("kron", "kron-threads", "kron-fused", "kron-fused-threads", "dense-fused", "dense"):
+        gp = ArrayGP(X, y, [f"x{j}" for j in range(d)], multioutput="dense" if mode.startswith("dense") else "kron", **kw)
         gp.build_model()
-        if mode == "kron-threads":
+        fused = "fused" in mode                                        # one-pass factorise+predict per (block) engine
+        if mode.endswith("threads"):
             gp.engine.threads = P                                      # all blocks in flight at once on this GPU
         gp.find_MAP(point=point)
-        gp.predict_cold(Xs)                                            # warm-up: allocations, module load
+        gp.predict_cold(Xs, fused=fused)                               # warm-up: allocations, module load
         t0 = time.perf_counter()
         for _ in range(steps):
-            mu, var = gp.predict_cold(Xs)                              # K-build + Cholesky + solve + H2D/D2H, every call
+            mu, var = gp.predict_cold(Xs, fused=fused)                 # K-build + Cholesky + solve + H2D/D2H, every call
         ms = (time.perf_counter() - t0) * 1e3 / steps
         t0 = time.perf_counter()
         gp.predict(Xs)
