@@ -58,7 +58,7 @@ class Kernel(C.Structure):
 EXPORTS = [
     "gb2_abi_version", "gb2_create", "gb2_destroy", "gb2_last_error", "gb2_set_train", "gb2_set_train_dev",
     "gb2_set_kernel", "gb2_factorize", "gb2_mll", "gb2_mll_grad", "gb2_get_alpha", "gb2_predict", "gb2_predict_dev", "gb2_predict_full", "gb2_factorize_predict", "gb2_factorize_predict_dev", "gb2_get_K", "gb2_get_L",
-    "gb2_get_v", "gb2_get_timings", "gb2_set_option", "gb2_mark", "gb2_elapsed_ms",
+    "gb2_get_v", "gb2_get_trace", "gb2_get_timings", "gb2_set_option", "gb2_mark", "gb2_elapsed_ms",
     "gb2_nccl_unique_id", "gb2_dist_init", "gb2_dist_finalize", "gb2_dist_allgather_dev",
 ]
 
@@ -105,6 +105,7 @@ def load():
     lib.gb2_get_L.argtypes = [H, dp]
     lib.gb2_get_v.argtypes = [H, dp]
     lib.gb2_get_alpha.argtypes = [H, dp]
+    lib.gb2_get_trace.argtypes = [H, C.POINTER(C.c_uint64), C.c_int64]
     lib.gb2_factorize_predict.argtypes = [H, dp, C.c_int64, C.c_int32, dp, dp]
     lib.gb2_get_timings.argtypes = [H, dp]
     lib.gb2_set_option.argtypes = [H, C.c_char_p, C.c_int]

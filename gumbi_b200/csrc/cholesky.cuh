@@ -431,6 +431,21 @@ struct NcclApi {
 };
 constexpr int NCCL_FLOAT64 = 8;  // ncclDataType_t ncclFloat64 / ncclDouble
 
+// Timeline instrumentation (set_option("trace", 1); off by default): one-thread kernels that write %globaltimer (ns) in stream
+// order.  A stamp needs no shared memory and one thread, so it is scheduled the moment its stream reaches it: the stamp BEFORE a
+// kernel is the time that kernel became eligible, the stamp AFTER it the time it completed.  Slots per block step k (6k + ...):
+//   0 panel stream: diagonal kernel eligible   1 diagonal kernel done   2 panel solve done   3 next-column update done
+//   4 main stream: bulk trailing update eligible   5 bulk trailing update (and the fused predict rows) done
+constexpr int TRACE_SLOTS = 6;
+__global__ void stamp_kernel(unsigned long long* slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    *slot = t;
+}
+inline void trace_stamp(gb2_handle* h, cudaStream_t s, int k, int slot) {
+    if (h->dTrace) stamp_kernel<<<1, 1, 0, s>>>(h->dTrace + (int64_t)k * TRACE_SLOTS + slot);
+}
+
 inline cudaEvent_t pool_event(gb2_handle* h, int idx) {
     while ((int)h->ev_pool.size() <= idx) {
         cudaEvent_t e;
@@ -535,6 +550,7 @@ inline int factor_steps(gb2_handle* h, int k0, int k1, int col_limit) {
         const bool p2p = G > 1 && h->p2p_ready;
         // counters of this block step in the current parity buffer: [0] = diagonal block announced, [1] = panel tiles landed
         const size_t fl = ((size_t)h->p2p_parity * 2) * h->p2p_nbmax + k;
+        trace_stamp(h, sp, k, 0);
         if (owner == me) {
             PushArgs sig{};
             if (p2p) {
@@ -544,6 +560,7 @@ inline int factor_steps(gb2_handle* h, int k0, int k1, int col_limit) {
             }
             potrf_diag_kernel<<<1, PD_THREADS, PD_SMEM, sp>>>(A, ld, g0, h->N, Dk, h->dInfo, Lk, sig);
             launches++;
+            trace_stamp(h, sp, k, 1);
         } else if (p2p) {
             pull_diag_kernel<<<32, 256, 0, sp>>>(h->dFlags + fl, 1u, h->peerDinv[owner] + (int64_t)k * TILE * TILE,
                                                  h->peerLpack[owner] + (int64_t)k * TILE * TILE, Dk, Lk, A + g0 * ld + g0, ld);
@@ -597,6 +614,7 @@ inline int factor_steps(gb2_handle* h, int k0, int k1, int col_limit) {
             // step remain (panel complete -> main; bulk update k-1 done -> next-column update k, normally long satisfied), and
             // neither sits between two kernels of the chain.  (The older schedule, next-column update on the main stream, put two
             // cross-stream hops of ~10 us each on the chain of every block step.)
+            trace_stamp(h, sp, k, 2);
             const bool chain = two && h->opt_chain_on_panel;
             if (two) {
                 cudaEvent_t e = pool_event(h, 2 * k);
@@ -610,11 +628,13 @@ inline int factor_steps(gb2_handle* h, int k0, int k1, int col_limit) {
                                                  TILE, TILE, 1, 0, g0 + TILE, f1, G);
                 launches++;
             }
+            if (chain) trace_stamp(h, sp, k, 3);
             if (two && !chain) {
                 cudaEvent_t e = pool_event(h, 2 * k + 1);
                 cudaEventRecord(e, sm);
                 cudaStreamWaitEvent(sp, e, 0);
             }
+            trace_stamp(h, sm, k, 4);
             if (k + 2 < col_limit) {
                 // rest of the trailing matrix: owned rows >= k+2, column blocks k+2 .. col_limit-1
                 const int f2 = first_owned_after(k + 1, me), c2 = count_from(f2);
@@ -657,6 +677,7 @@ inline int factor_steps(gb2_handle* h, int k0, int k1, int col_limit) {
                 launches++;
             }
         }
+        trace_stamp(h, sm, k, 5);
     }
     if (two) {  // join
         cudaEvent_t e = pool_event(h, 3 * nb + 3);

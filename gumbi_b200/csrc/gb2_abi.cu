@@ -380,6 +380,7 @@ int gb2_destroy(gb2_handle* h) {
     for (auto ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto ev : h->ev_pool) cudaEventDestroy(ev);
     for (auto ev : h->ev_mark) if (ev) cudaEventDestroy(ev);
+    if (h->dTrace) cudaFree(h->dTrace);
     for (auto st : h->s_aux) if (st) cudaStreamDestroy(st);
     for (auto ev : h->ev_join) if (ev) cudaEventDestroy(ev);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -957,6 +958,16 @@ int gb2_get_alpha(gb2_handle* h, double* alpha_out) {
     return 0;
 }
 
+int gb2_get_trace(gb2_handle* h, uint64_t* out, int64_t n) {
+    if (!h) return -1;
+    GB2_ARG(h, out && n >= 0, "invalid argument");
+    GB2_ARG(h, h->dTrace, "gb2_get_trace: set_option(\"trace\", 1) first");
+    GB2_ARG(h, n <= h->trace_cap, "gb2_get_trace: at most 6 * 4096 stamps");
+    GB2_CUDA(h, cudaSetDevice(h->device));
+    GB2_CUDA(h, cudaMemcpy(out, h->dTrace, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int gb2_get_timings(gb2_handle* h, double* out) {
     if (!h || !out) return -1;
     for (int i = 0; i < GB2_N_TIMINGS; i++) out[i] = h->timings[i];
@@ -1091,6 +1102,13 @@ int gb2_set_option(gb2_handle* h, const char* name, int value) {
     if (!strcmp(name, "solve_streams")) {   // fp64 predict solve: row slabs of the prediction points in concurrent streams
         GB2_ARG(h, value >= 1 && value <= 4, "solve_streams must be in [1, 4]");
         h->opt_solve_streams = value;
+        return 0;
+    }
+    if (!strcmp(name, "trace")) {   // timeline stamps around the kernels of every block step (gb2_get_trace); measurement aid
+        if (!value) { if (h->dTrace) cudaFree(h->dTrace); h->dTrace = nullptr; h->trace_cap = 0; return 0; }
+        const int64_t want = (int64_t)TRACE_SLOTS * 4096;     // up to 4096 block steps (N <= 524k)
+        if (!h->dTrace) { GB2_CUDA(h, cudaMalloc(&h->dTrace, want * sizeof(unsigned long long))); h->trace_cap = want; }
+        GB2_CUDA(h, cudaMemset(h->dTrace, 0, want * sizeof(unsigned long long)));
         return 0;
     }
     if (!strcmp(name, "fused_group")) {   // gb2_factorize_predict: column blocks per bulk update of the prediction rows

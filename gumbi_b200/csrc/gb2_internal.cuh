@@ -145,6 +145,8 @@ struct gb2_handle {
     int opt_lookahead = 1;
     // fused cold predict (gb2_factorize_predict): prediction points ride along as ext_rows extra rows of the factor (row-major, ld ext_ld)
     double* ext_At = nullptr; int64_t ext_rows = 0, ext_ld = 0; int ext_ncols = 0;
+    // "trace" option: %globaltimer stamps around the kernels of every block step of factor_steps (6 per step), see gb2_get_trace
+    unsigned long long* dTrace = nullptr; int64_t trace_cap = 0; int trace_steps = 0;
     int opt_fused_group = 4;     // fused cold predict: column blocks per bulk update of the prediction rows (1, 2, 4, 8)
     int opt_solve_streams = 1;   // fp64 predict solve: split the prediction rows over this many concurrent streams (wave-tail filling)
     cudaStream_t s_aux[3] = {nullptr, nullptr, nullptr};

@@ -249,6 +249,14 @@ class GPEngine:
         self._check(self._lib.gb2_get_alpha(self._h, _lib.as_dp(a)), "get_alpha")
         return a
 
+    def get_trace(self):
+        """(steps, 6) uint64 %globaltimer stamps (ns) of the last factorisation, after ``set_option("trace", 1)``; columns: diagonal
+        kernel eligible / done, panel solve done, next-column update done (panel stream), bulk update eligible / done (main stream)."""
+        steps = (self.N + 1 + 127) // 128
+        out = np.zeros(steps * 6, dtype=np.uint64)
+        self._check(self._lib.gb2_get_trace(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64)), out.size), "get_trace")
+        return out.reshape(steps, 6)
+
     def timings(self) -> dict:
         out = np.zeros(_lib.N_TIMINGS, dtype=np.float64)
         self._check(self._lib.gb2_get_timings(self._h, _lib.as_dp(out)), "get_timings")

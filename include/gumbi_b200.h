@@ -146,6 +146,10 @@ int gb2_predict_full(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_no
 int gb2_get_K(gb2_handle* h, double* K_out);   /* rebuilds K+Knoise+jitter into scratch; O(N^2)  */
 int gb2_get_L(gb2_handle* h, double* L_out);
 int gb2_get_v(gb2_handle* h, double* v_out);   /* v = L^-1 y, length N                           */
+/* Measurement aid: with set_option("trace", 1), every block step k of the factorisation writes six %globaltimer stamps (ns) at
+ * out[6k + i]: panel stream -- 0 diagonal kernel eligible, 1 diagonal kernel done, 2 panel solve done, 3 next-column update done;
+ * main stream -- 4 bulk trailing update eligible, 5 bulk trailing update (+ fused predict rows) done.  n = 6 * number of steps. */
+int gb2_get_trace(gb2_handle* h, uint64_t* out, int64_t n);
 
 /* Device-side milliseconds (CUDA events on the handle's stream) of the phases of the most recent
  * gb2_factorize / gb2_predict*: out[0]=feature prep, [1]=K build, [2]=Cholesky(+v),
@@ -180,7 +184,8 @@ int gb2_dist_allgather_dev(gb2_handle* h, const double* dsend, double* drecv, in
  *   "tf32_nb"       0..16  GB2_TF32 factor-panel width in 128-column blocks (0 = auto); "tf32_leaf" 1..16 fp64 leaf width of the solve
  *   "lookahead"     1|0  panel look-ahead on a second stream;  "fastdiag", "kbuild_v1": ablations
  *   "solve_streams" 1..4 fp64 predict solve: row slabs of the prediction points on this many concurrent streams (default 1)
- *   "fused_group"   1|2|4|8  gb2_factorize_predict: column blocks per bulk update of the prediction rows (default 4)            */
+ *   "fused_group"   1|2|4|8  gb2_factorize_predict: column blocks per bulk update of the prediction rows (default 4)
+ *   "trace"         0|1  record the per-step timeline read by gb2_get_trace (measurement aid, off by default)                   */
 int gb2_set_option(gb2_handle* h, const char* name, int value);
 
 #ifdef __cplusplus
