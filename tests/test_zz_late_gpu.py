@@ -211,3 +211,32 @@ def test_periodic_kernels_on_the_device(lib_built, kernel, d):
     np.testing.assert_allclose(var, var0, rtol=1e-5, atol=1e-8)
     assert gp.marginal_log_likelihood() == pytest.approx(orc.mll(ref, X, y), rel=1e-8)
     gp.engine.close()
+
+
+def test_timeline_trace_is_ordered(lib_built):
+    """set_option("trace", 1) / gb2_get_trace: six %globaltimer stamps per block step, ordered along each stream; the factor is the
+    same with and without the stamps."""
+    from gumbi_b200 import GPEngine
+    from oracle import gp_oracle as orc
+
+    spec, X, y, _ = orc.synthetic_problem(700, 3)
+    e = GPEngine()
+    e.set_train(X, y)
+    e.set_kernel(spec)
+    e.factorize()
+    L0 = e.get_L()
+    with pytest.raises(ValueError):
+        e.get_trace()
+    e.set_option("trace", 1)
+    e.factorize()
+    t = e.get_trace().astype(np.int64)
+    assert t.shape == ((700 + 1 + 127) // 128, 6)
+    assert np.array_equal(e.get_L(), L0)
+    steps = t.shape[0]
+    assert np.all(t[:, 0] > 0) and np.all(t[:, 1] >= t[:, 0])                    # diagonal kernel: eligible <= done
+    assert np.all(t[:-1, 2] >= t[:-1, 1]) and np.all(t[:-1, 5] >= t[:-1, 4])     # panel solve after it; bulk update: eligible <= done
+    assert np.all(np.diff(t[:, 0]) > 0)                                          # the panel stream runs the steps in order
+    e.set_option("trace", 0)
+    e.factorize()
+    assert np.array_equal(e.get_L(), L0)
+    e.close()
