@@ -550,7 +550,14 @@ inline int factor_steps(gb2_handle* h, int k0, int k1, int col_limit) {
         const bool p2p = G > 1 && h->p2p_ready;
         // counters of this block step in the current parity buffer: [0] = diagonal block announced, [1] = panel tiles landed
         const size_t fl = ((size_t)h->p2p_parity * 2) * h->p2p_nbmax + k;
-        trace_stamp(h, sp, k, 0);
+        // green_sms: the diagonal kernel runs on its own SM partition (stream s_diag); two event edges tie it into the chain
+        cudaStream_t sd = (h->s_diag && G == 1) ? h->s_diag : sp;
+        if (sd != sp) {
+            cudaEvent_t e = pool_event(h, 4 * nb + 8 + 2 * k);
+            cudaEventRecord(e, sp);
+            cudaStreamWaitEvent(sd, e, 0);
+        }
+        trace_stamp(h, sd, k, 0);
         if (owner == me) {
             PushArgs sig{};
             if (p2p) {
@@ -558,9 +565,14 @@ inline int factor_steps(gb2_handle* h, int k0, int k1, int col_limit) {
                     if (r != me) sig.peerFlag[q++] = h->peerFlags[r] + fl;
                 sig.n_peers = G - 1;
             }
-            potrf_diag_kernel<<<1, PD_THREADS, PD_SMEM, sp>>>(A, ld, g0, h->N, Dk, h->dInfo, Lk, sig);
+            potrf_diag_kernel<<<1, PD_THREADS, PD_SMEM, sd>>>(A, ld, g0, h->N, Dk, h->dInfo, Lk, sig);
             launches++;
-            trace_stamp(h, sp, k, 1);
+            trace_stamp(h, sd, k, 1);
+            if (sd != sp) {
+                cudaEvent_t e = pool_event(h, 4 * nb + 9 + 2 * k);
+                cudaEventRecord(e, sd);
+                cudaStreamWaitEvent(sp, e, 0);
+            }
         } else if (p2p) {
             pull_diag_kernel<<<32, 256, 0, sp>>>(h->dFlags + fl, 1u, h->peerDinv[owner] + (int64_t)k * TILE * TILE,
                                                  h->peerLpack[owner] + (int64_t)k * TILE * TILE, Dk, Lk, A + g0 * ld + g0, ld);

@@ -304,9 +304,19 @@ int predict_common(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_nois
 
 }  // namespace
 
+// driver-API entry point through the runtime (no link-time dependency on libcuda)
+template <typename F>
+static F driver_fn(const char* name) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<F>(p);
+}
+
 extern "C" {
 
 static void p2p_close(gb2_handle* h);
+static void green_close(gb2_handle* h);
 
 int gb2_abi_version(void) { return GB2_ABI_VERSION; }
 
@@ -381,11 +391,13 @@ int gb2_destroy(gb2_handle* h) {
     for (auto ev : h->ev_pool) cudaEventDestroy(ev);
     for (auto ev : h->ev_mark) if (ev) cudaEventDestroy(ev);
     if (h->dTrace) cudaFree(h->dTrace);
+    if (h->s_diag) cudaStreamDestroy(h->s_diag);
     for (auto st : h->s_aux) if (st) cudaStreamDestroy(st);
     for (auto ev : h->ev_join) if (ev) cudaEventDestroy(ev);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->s_main) cudaStreamDestroy(h->s_main);
     if (h->s_panel) cudaStreamDestroy(h->s_panel);
+    green_close(h);   // after the streams that live in the green contexts
     delete h;
     return 0;
 }
@@ -555,6 +567,70 @@ static int p2p_setup(gb2_handle* h) {
         return 0;
     }
     h->p2p_ready = true;
+    return 0;
+}
+
+// ---- SM partition for the diagonal-panel kernel (CUDA green contexts, driver API resolved through the runtime) ---------------
+// The diagonal kernel needs a whole SM (222 KB of shared memory, 512 x 128 registers); the bulk trailing update keeps every SM
+// full and refills every slot that frees, so without a partition the diagonal kernel of step k waits until the bulk update of
+// step k-1 has drained and the look-ahead overlaps nothing.  With "green_sms" = R the device is split into R SMs for s_diag and
+// the rest for s_main / s_panel (both re-created as green-context streams).  Single GPU only; measurement option, off by default.
+static void green_close(gb2_handle* h) {
+    if (!h->green_a && !h->green_b) return;
+    auto fDestroy = driver_fn<CUresult (*)(CUgreenCtx)>("cuGreenCtxDestroy");
+    if (fDestroy) {
+        if (h->green_a) fDestroy((CUgreenCtx)h->green_a);
+        if (h->green_b) fDestroy((CUgreenCtx)h->green_b);
+    }
+    h->green_a = h->green_b = nullptr;
+}
+
+static int green_setup(gb2_handle* h, int sms) {
+    GB2_ARG(h, h->world == 1, "green_sms is a single-GPU option");
+    GB2_ARG(h, !h->green_a, "green_sms is already active on this handle");
+    GB2_ARG(h, sms >= 8 && sms <= 64 && sms % 8 == 0, "green_sms must be a multiple of 8 in [8, 64]");
+    auto fDeviceGet = driver_fn<CUresult (*)(CUdevice*, int)>("cuDeviceGet");
+    auto fGetRes = driver_fn<CUresult (*)(CUdevice, CUdevResource*, CUdevResourceType)>("cuDeviceGetDevResource");
+    auto fSplit = driver_fn<CUresult (*)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int)>(
+        "cuDevSmResourceSplitByCount");
+    auto fDesc = driver_fn<CUresult (*)(CUdevResourceDesc*, CUdevResource*, unsigned int)>("cuDevResourceGenerateDesc");
+    auto fCreate = driver_fn<CUresult (*)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int)>("cuGreenCtxCreate");
+    auto fStream = driver_fn<CUresult (*)(CUstream*, CUgreenCtx, unsigned int, int)>("cuGreenCtxStreamCreate");
+    if (!fDeviceGet || !fGetRes || !fSplit || !fDesc || !fCreate || !fStream) {
+        h->err = "green contexts are not available in this driver";
+        return -2;
+    }
+    GB2_CUDA(h, cudaSetDevice(h->device));
+    GB2_CUDA(h, cudaFree(nullptr));   // primary context up
+#define GB2_CU(call) do { CUresult r_ = (call); if (r_ != CUDA_SUCCESS) { h->err = std::string(#call) + " failed: CUresult " + std::to_string((int)r_); return -2; } } while (0)
+    CUdevice dev;
+    GB2_CU(fDeviceGet(&dev, h->device));
+    CUdevResource all, part, rest;
+    GB2_CU(fGetRes(dev, &all, CU_DEV_RESOURCE_TYPE_SM));
+    unsigned int groups = 1;
+    GB2_CU(fSplit(&part, &groups, &all, &rest, 0, (unsigned int)sms));
+    if (groups != 1 || rest.sm.smCount == 0) { h->err = "SM split did not yield a partition and a remainder"; return -2; }
+    CUdevResourceDesc da, db;
+    GB2_CU(fDesc(&da, &part, 1));
+    GB2_CU(fDesc(&db, &rest, 1));
+    CUgreenCtx ga, gb;
+    GB2_CU(fCreate(&ga, da, dev, CU_GREEN_CTX_DEFAULT_STREAM));
+    GB2_CU(fCreate(&gb, db, dev, CU_GREEN_CTX_DEFAULT_STREAM));
+    int lo, hi;
+    GB2_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CUstream sd, sm, sp;
+    GB2_CU(fStream(&sd, ga, CU_STREAM_NON_BLOCKING, hi));
+    GB2_CU(fStream(&sm, gb, CU_STREAM_NON_BLOCKING, lo));
+    GB2_CU(fStream(&sp, gb, CU_STREAM_NON_BLOCKING, hi));
+#undef GB2_CU
+    GB2_CUDA(h, cudaStreamSynchronize(h->s_main));
+    GB2_CUDA(h, cudaStreamSynchronize(h->s_panel));
+    cudaStreamDestroy(h->s_main);
+    cudaStreamDestroy(h->s_panel);
+    h->s_main = (cudaStream_t)sm; h->s_panel = (cudaStream_t)sp; h->s_diag = (cudaStream_t)sd;
+    h->green_a = ga; h->green_b = gb;
+    h->green_sms_a = (int)part.sm.smCount; h->green_sms_b = (int)rest.sm.smCount;
+    h->factorized = false;
     return 0;
 }
 
@@ -1104,6 +1180,7 @@ int gb2_set_option(gb2_handle* h, const char* name, int value) {
         h->opt_solve_streams = value;
         return 0;
     }
+    if (!strcmp(name, "green_sms")) return value == 0 ? 0 : green_setup(h, value);
     if (!strcmp(name, "trace")) {   // timeline stamps around the kernels of every block step (gb2_get_trace); measurement aid
         if (!value) { if (h->dTrace) cudaFree(h->dTrace); h->dTrace = nullptr; h->trace_cap = 0; return 0; }
         const int64_t want = (int64_t)TRACE_SLOTS * 4096;     // up to 4096 block steps (N <= 524k)

@@ -147,6 +147,9 @@ struct gb2_handle {
     double* ext_At = nullptr; int64_t ext_rows = 0, ext_ld = 0; int ext_ncols = 0;
     // "trace" option: %globaltimer stamps around the kernels of every block step of factor_steps (6 per step), see gb2_get_trace
     unsigned long long* dTrace = nullptr; int64_t trace_cap = 0; int trace_steps = 0;
+    // "green_sms" option: SM partition (CUDA green contexts) -- s_diag runs the diagonal-panel kernel on its own few SMs, s_main and
+    // s_panel are re-created on the remaining ones, so that the 222 KB / 64k-register diagonal kernel never waits for an empty SM
+    cudaStream_t s_diag = nullptr; void* green_a = nullptr; void* green_b = nullptr; int green_sms_a = 0, green_sms_b = 0;
     int opt_fused_group = 4;     // fused cold predict: column blocks per bulk update of the prediction rows (1, 2, 4, 8)
     int opt_solve_streams = 1;   // fp64 predict solve: split the prediction rows over this many concurrent streams (wave-tail filling)
     cudaStream_t s_aux[3] = {nullptr, nullptr, nullptr};

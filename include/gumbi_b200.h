@@ -185,7 +185,9 @@ int gb2_dist_allgather_dev(gb2_handle* h, const double* dsend, double* drecv, in
  *   "lookahead"     1|0  panel look-ahead on a second stream;  "fastdiag", "kbuild_v1": ablations
  *   "solve_streams" 1..4 fp64 predict solve: row slabs of the prediction points on this many concurrent streams (default 1)
  *   "fused_group"   1|2|4|8  gb2_factorize_predict: column blocks per bulk update of the prediction rows (default 4)
- *   "trace"         0|1  record the per-step timeline read by gb2_get_trace (measurement aid, off by default)                   */
+ *   "trace"         0|1  record the per-step timeline read by gb2_get_trace (measurement aid, off by default)
+ *   "green_sms"     8..64 (multiple of 8)  single GPU: give the diagonal-panel kernel its own SM partition (CUDA green contexts) so that
+ *                        it never waits for the bulk trailing update to free a whole SM; experimental, off by default, cannot be undone */
 int gb2_set_option(gb2_handle* h, const char* name, int value);
 
 #ifdef __cplusplus

@@ -240,3 +240,35 @@ def test_timeline_trace_is_ordered(lib_built):
     e.factorize()
     assert np.array_equal(e.get_L(), L0)
     e.close()
+
+
+def test_sm_partition_for_the_diagonal_kernel_keeps_the_numbers(lib_built):
+    """set_option("green_sms", 8): the diagonal-panel kernel runs on its own SM partition (green contexts), everything else on the
+    remaining SMs -- same kernels, same arithmetic: factor and posterior are bit-identical.  Skipped where the driver lacks the API."""
+    from gumbi_b200 import GPEngine
+    from oracle import gp_oracle as orc
+
+    spec, X, y, Xs = orc.synthetic_problem(900, 3, M_res=15)
+    ref = GPEngine()
+    ref.set_train(X, y)
+    ref.set_kernel(spec)
+    ref.factorize()
+    L0, p0 = ref.get_L(), ref.predict(Xs)
+    ref.close()
+    e = GPEngine()
+    try:
+        e.set_option("green_sms", 8)
+    except RuntimeError as err:
+        e.close()
+        pytest.skip(f"green contexts unavailable: {err}")
+    e.set_train(X, y)
+    e.set_kernel(spec)
+    e.factorize()
+    assert np.array_equal(e.get_L(), L0)
+    p1 = e.predict(Xs)
+    assert np.array_equal(p1[0], p0[0]) and np.array_equal(p1[1], p0[1])
+    mu, var = e.factorize_predict(Xs, True)
+    np.testing.assert_allclose(mu, p0[0], rtol=1e-9, atol=1e-10)
+    with pytest.raises(ValueError):
+        e.set_option("green_sms", 8)                               # already active
+    e.close()
