@@ -1180,6 +1180,7 @@ int gb2_set_option(gb2_handle* h, const char* name, int value) {
         h->opt_solve_streams = value;
         return 0;
     }
+    if (!strcmp(name, "small_diag")) { h->opt_small_diag = value ? 1 : 0; return 0; }   // small-footprint diagonal-panel kernel (bit-identical results)
     if (!strcmp(name, "green_sms")) return value == 0 ? 0 : green_setup(h, value);
     if (!strcmp(name, "trace")) {   // timeline stamps around the kernels of every block step (gb2_get_trace); measurement aid
         if (!value) { if (h->dTrace) cudaFree(h->dTrace); h->dTrace = nullptr; h->trace_cap = 0; return 0; }

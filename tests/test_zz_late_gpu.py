@@ -272,3 +272,35 @@ def test_sm_partition_for_the_diagonal_kernel_keeps_the_numbers(lib_built):
     with pytest.raises(ValueError):
         e.set_option("green_sms", 8)                               # already active
     e.close()
+
+
+def test_small_footprint_diagonal_kernel_is_bit_identical(lib_built):
+    """set_option("small_diag", 1): the 256-thread / 130 KB diagonal-panel kernel performs the same block products in the same
+    order as the default one -> identical factor, identical inverse blocks (seen through the predictions), identical pivot report."""
+    from gumbi_b200 import GPEngine
+    from oracle import gp_oracle as orc
+
+    for n, d in ((900, 3), (127, 1), (515, 2)):
+        spec, X, y, Xs = orc.synthetic_problem(n, d, M_res=15 if d >= 2 else 60)
+        e = GPEngine()
+        e.set_train(X, y)
+        e.set_kernel(spec)
+        e.factorize()
+        L0, v0, p0, m0 = e.get_L(), e.get_v(), e.predict(Xs), e.mll()
+        e.set_option("small_diag", 1)
+        e.factorize()
+        assert np.array_equal(e.get_L(), L0) and np.array_equal(e.get_v(), v0) and e.mll() == m0
+        p1 = e.predict(Xs)
+        assert np.array_equal(p1[0], p0[0]) and np.array_equal(p1[1], p0[1])
+        e.close()
+    spec, X, y, _ = orc.synthetic_problem(200, 2)
+    spec["sigma"] = 0.0
+    spec["jitter"] = 0.0
+    X[150] = X[40]
+    e = GPEngine()
+    e.set_option("small_diag", 1)
+    e.set_train(X, y)
+    e.set_kernel(spec)
+    with pytest.raises(np.linalg.LinAlgError, match="not positive definite"):
+        e.factorize()
+    e.close()
