@@ -503,7 +503,8 @@ def run_ours(args):
                    "parallelism": "single GPU" if world == 1 else (
                        f"factor stored row-block-sharded over {world} GPUs (NVLink peer pushes into panel rings), distributed column-sharded solve" if shard else
                        f"row-block-cyclic sharded Cholesky over {world} GPUs (NVLink peer exchange per block step), factor replicated, grid split {world} ways"),
-                   "l2_policy": f"inputs larger than L2: the factor is {8.0 * N * N / 1e6:.0f} MB and is rewritten every step"},
+                   "l2_policy": f"inputs larger than L2: the factor is {8.0 * N * N / 1e6:.0f} MB and is rewritten every step",
+                   "engine_options": list(args.opt)},
         "phases_ms": phase, "wall_ms_per_step": wall_ms / args.steps,
         "warm": {"value": M / (warm_ms * 1e-3), "unit": "predictions/s", "ms_per_step": warm_ms},
         "cholesky_tflops": chol_tflops,
