@@ -1,5 +1,5 @@
 #!/bin/bash
-# first GPU call of round 2 (1 GPU, ~4 min): full GPU suite (includes the Kronecker-solve device tests that round 1 could not
+# first GPU call of round 2 (1 GPU, ~12 min; give gpurun --timeout 1500): full GPU suite (includes the Kronecker-solve device tests that round 1 could not
 # run), Kronecker vs dense cold-predict timing on BASELINE config 3, default bench line.
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -15 | tee gpurun_out/pytest_gpu_r02a.log
@@ -14,7 +14,7 @@ timeout 300 python tools/fused_timing.py 2>&1 | tail -8 | tee gpurun_out/fused_t
 # (2+ GPUs, separate call)  python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/replicate_timing.py
 #                           python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 tools/c5_kron_demo.py
 # timeline of the blocked Cholesky: is the diagonal kernel starved of an SM by the bulk update (222 KB of shared memory)?
-timeout 300 python tools/chol_trace.py 2>&1 | tail -18 | tee gpurun_out/chol_trace_r02a.log
+timeout 300 python tools/chol_trace.py 2>&1 | tail -30 | tee gpurun_out/chol_trace_r02a.log
 # diagonal-panel kernel: phase clocks of both variants + bit-identity of the small-footprint one
 timeout 120 ./tools/micro_potrf 2>&1 | tail -10 | tee gpurun_out/micro_potrf_r02a.log
 for o in small_diag=1 green_sms=8; do timeout 300 python bench.py --no-cpu --opt $o 2>&1 | tail -1 | tee gpurun_out/bench_r02a_$o.log; done
