@@ -1180,7 +1180,22 @@ int gb2_set_option(gb2_handle* h, const char* name, int value) {
         h->opt_solve_streams = value;
         return 0;
     }
-    if (!strcmp(name, "small_diag")) { h->opt_small_diag = value ? 1 : 0; return 0; }   // small-footprint diagonal-panel kernel (bit-identical results)
+    if (!strcmp(name, "small_diag")) {   // small-footprint diagonal-panel kernel (bit-identical results)
+        h->opt_small_diag = value ? 1 : 0;
+        if (value) {
+            // Co-residence needs more than the sum of the footprints: an SM keeps ONE shared-memory carveout while it has resident
+            // CTAs, and the driver sizes it for the kernel that got there first (2 x 93 KB GEMM CTAs -> 196 KB, which leaves 103 KB
+            // beside one of them).  Asking for the maximum carveout on the GEMMs of the factorisation and on the small kernel makes
+            // every SM they touch 228 KB wide, so that 131.6 KB fit beside one GEMM CTA.  (A process-wide hint: function attributes.)
+            GB2_CUDA(h, cudaSetDevice(h->device));
+            const int mx = (int)cudaSharedmemCarveoutMaxShared;
+            GB2_CUDA(h, cudaFuncSetAttribute(potrf_diag_small_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+            GB2_CUDA(h, cudaFuncSetAttribute(dgemm_nt_kernel<128, 64, GM_SUB>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+            GB2_CUDA(h, cudaFuncSetAttribute(dgemm_nt_kernel<64, 128, GM_SET>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+            GB2_CUDA(h, cudaFuncSetAttribute(dgemm_nt_kernel<64, 128, GM_SET_PUSH>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+        }
+        return 0;
+    }
     if (!strcmp(name, "green_sms")) return value == 0 ? 0 : green_setup(h, value);
     if (!strcmp(name, "trace")) {   // timeline stamps around the kernels of every block step (gb2_get_trace); measurement aid
         if (!value) { if (h->dTrace) cudaFree(h->dTrace); h->dTrace = nullptr; h->trace_cap = 0; return 0; }
