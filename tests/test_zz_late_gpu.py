@@ -9,7 +9,10 @@ import pytest
 from conftest import load_golden
 from test_kron import from_golden, random_point, synthetic
 
-pytestmark = pytest.mark.gpu
+# xfail(strict=False): none of this has run on a device yet (the round's GPU minutes were spent before it was written).  A failure
+# here is reported as XFAIL and a success as XPASS, so the verdict on the measured, validated suite above stays readable; the marker
+# goes away once the first device run (tools/gpu_calls/gpu_round_r02_first.sh) is green.
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="built after round 1's GPU minutes were spent: first device run pending")]
 
 
 def pair(X, y, kw, **build):
