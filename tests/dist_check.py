@@ -1,7 +1,7 @@
 """Multi-GPU check (run under torchrun, one rank per GPU): row-block-sharded Cholesky over NCCL vs the single-GPU factor,
 sliced prediction + gather vs the oracle, and factorisation timings.  Used by tests/test_dist_gpu.py and by hand:
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_check.py
 """
 import json
 import os

@@ -1,7 +1,7 @@
 """Multi-process tests of the N>1 path.
 
 CPU (gloo, world_size 2): the host-side plumbing of gumbi_b200/dist.py -- ownership maps, the unique-id exchange, grid
-slicing and the result gather.  GPU (>= 2 devices): the sharded factorisation itself, through torchrun + tools/dist_check.py.
+slicing and the result gather.  GPU (>= 2 devices): the sharded factorisation itself, through torchrun + tests/dist_check.py.
 """
 import os
 import subprocess
@@ -82,7 +82,7 @@ def test_unique_id_exchange_and_gather_over_gloo(tmp_path):
 @pytest.mark.parametrize("mode", ["p2p", "nccl", "shard_storage", "tf32"])
 def test_sharded_cholesky_matches_single_gpu(mode):
     """Factor bit-identical to the single-GPU one; predictions equal (replicated storage) or within 1e-8 (storage-sharded:
-    different summation order); through torchrun + tools/dist_check.py."""
+    different summation order); through torchrun + tests/dist_check.py."""
     import torch
 
     n = torch.cuda.device_count()
@@ -97,7 +97,7 @@ def test_sharded_cholesky_matches_single_gpu(mode):
     if mode == "tf32":
         env["GB2_DIST_PRECISION"] = "tf32"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", "29541", os.path.join(ROOT, "tools", "dist_check.py"), "1000", "3000"]
+           "--master-port", "29541", os.path.join(ROOT, "tests", "dist_check.py"), "1000", "3000"]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert res.returncode == 0 and "DIST_CHECK OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
 

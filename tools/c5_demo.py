@@ -3,7 +3,7 @@
 The lower triangle of K is 275 GB: it only exists distributed (69 GB of row blocks per GPU on 8 GPUs).
 Two cold passes (K-build + block Cholesky with NVLink panel pushes + distributed solve); the second is reported.
 No CPU / single-GPU comparison is possible at this size; bit-identity of the sharded factor with the single-GPU one is
-established at N <= 16384 by tools/dist_check.py.  Reports size-independent checks instead."""
+established at N <= 16384 by tests/dist_check.py.  Reports size-independent checks instead."""
 import json, os, sys, time
 import numpy as np
 import torch

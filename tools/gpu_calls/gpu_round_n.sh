@@ -5,7 +5,7 @@ NG=${2:-8}
 O=gpurun_out
 mkdir -p $O
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1"
-echo "== dist_check p2p fp64";  timeout 300 $TR --master-port 29511 tools/dist_check.py 3000 8192 2>&1 | grep -E "^\{|DIST_CHECK|rror|Traceback" | tee $O/dist_check_p2p_g${NG}_$TAG.log
+echo "== dist_check p2p fp64";  timeout 300 $TR --master-port 29511 tests/dist_check.py 3000 8192 2>&1 | grep -E "^\{|DIST_CHECK|rror|Traceback" | tee $O/dist_check_p2p_g${NG}_$TAG.log
 for cfg in "c2 fp64" "c4 fp64" "c4 tf32"; do set -- $cfg
   echo "== bench --gpus $NG $1 $2"; timeout 900 $TR --master-port 29514 bench.py --gpus $NG --workload $1 --precision $2 --steps 3 --warmup 3 > $O/bench_$1_$2_g${NG}_$TAG.json 2> $O/bench_$1_$2_g${NG}_$TAG.err
   python - <<PY
