@@ -106,3 +106,9 @@ def test_product_package_never_imports_oracle():
                 txt = open(os.path.join(dirpath, f), encoding="utf-8").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
                 assert "gp_oracle" not in txt, f
+    # dev tools measure the product path only: checker programs that need the oracle live under tests/
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith(".py"):
+            txt = open(os.path.join(ROOT, "tools", f), encoding="utf-8").read()
+            assert not re.search(r"^\s*(from|import)\s+(oracle|gen_golden|test_backend_host)\b", txt, flags=re.M), f
+            assert "gp_oracle" not in txt and "OracleEngine" not in txt, f
