@@ -1208,6 +1208,47 @@ inline int cholesky_enqueue(gb2_handle* h) {
             g.a_k0 = 0; g.b_row0 = c1 * TILE; g.b_k0 = 0;
             tc::gemm_tf32x3_launch(sm, h->n_sm, h->mPhi, h->mPlo, h->mPhi, h->mPlo, g, (int)cols, launches);
         }
+    } else if (h->opt_fp64_panel > 1 && h->world == 1 && nb > h->opt_fp64_panel) {
+        // Two-level blocking (option "fp64_panel" = pw, off by default).  The plain algorithm applies every 128-column panel to the
+        // whole trailing matrix: N/128 read-modify-write passes of depth 128 (87 % tensor-pipe activity, prologue/epilogue bound).
+        // Here pw column blocks are factored as one panel (factor_steps restricted to the panel's own columns, exactly what the
+        // tf32 path does), then applied to the trailing matrix by ONE update of depth pw*128 -- split in two so that the next panel
+        // can start early:  (1) the next panel's columns, on the main stream;  (2) everything right of them, on a second bulk
+        // stream, overlapping the next panel's factorisation.  (1) of group g waits for (2) of group g-1, which touched its columns.
+        cudaStream_t sm = h->s_main;
+        if (!h->s_bulk2) {
+            int lo_p, hi_p;
+            cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
+            cudaStreamCreateWithPriority(&h->s_bulk2, cudaStreamNonBlocking, lo_p);
+        }
+        cudaStream_t sb = h->s_bulk2;
+        const int pw2 = h->opt_fp64_panel, ev0 = 6 * nb + 32;
+        double* A = h->dA;
+        int g = 0;
+        for (int c0 = 0; c0 < nb; c0 += pw2, g++) {
+            const int c1 = c0 + pw2 < nb ? c0 + pw2 : nb;
+            launches += factor_steps(h, c0, c1, c1);
+            if (c1 >= nb) break;
+            const int c2 = c1 + pw2 < nb ? c1 + pw2 : nb;
+            const int kd = (c1 - c0) * TILE;
+            const double* Apan = A + (int64_t)c0 * TILE;                  // the panel's columns; rows are addressed through rb_first
+            cudaEvent_t eP = pool_event(h, ev0 + 2 * g);
+            cudaEventRecord(eP, sm);                                     // panel g complete (factor_steps joined its panel stream)
+            if (g > 0) cudaStreamWaitEvent(sm, pool_event(h, ev0 + 2 * (g - 1) + 1), 0);
+            dgemm_nt_launch<128, 64, GM_SUB>(sm, Apan, ld, A + (int64_t)c1 * TILE * ld + (int64_t)c0 * TILE, ld, A + (int64_t)c1 * TILE, ld,
+                                             (int64_t)(nb - c1) * TILE, (int64_t)(c2 - c1) * TILE, kd, 1, 0, (int64_t)c1 * TILE, c1, 1);
+            launches++;
+            cudaStreamWaitEvent(sb, eP, 0);
+            if (c2 < nb) {
+                dgemm_nt_launch<128, 64, GM_SUB>(sb, Apan, ld, A + (int64_t)c2 * TILE * ld + (int64_t)c0 * TILE, ld, A + (int64_t)c2 * TILE, ld,
+                                                 (int64_t)(nb - c2) * TILE, (int64_t)(nb - c2) * TILE, kd, 1, 0, (int64_t)c2 * TILE, c2, 1);
+                launches++;
+            }
+            cudaEventRecord(pool_event(h, ev0 + 2 * g + 1), sb);
+        }
+        cudaEvent_t eJ = pool_event(h, ev0 + 2 * g + 2);
+        cudaEventRecord(eJ, sb);
+        cudaStreamWaitEvent(sm, eJ, 0);
     } else {
         launches += factor_steps(h, 0, nb, nb);
     }

@@ -392,6 +392,7 @@ int gb2_destroy(gb2_handle* h) {
     for (auto ev : h->ev_mark) if (ev) cudaEventDestroy(ev);
     if (h->dTrace) cudaFree(h->dTrace);
     if (h->s_diag) cudaStreamDestroy(h->s_diag);
+    if (h->s_bulk2) cudaStreamDestroy(h->s_bulk2);
     for (auto st : h->s_aux) if (st) cudaStreamDestroy(st);
     for (auto ev : h->ev_join) if (ev) cudaEventDestroy(ev);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -1178,6 +1179,12 @@ int gb2_set_option(gb2_handle* h, const char* name, int value) {
     if (!strcmp(name, "solve_streams")) {   // fp64 predict solve: row slabs of the prediction points in concurrent streams
         GB2_ARG(h, value >= 1 && value <= 4, "solve_streams must be in [1, 4]");
         h->opt_solve_streams = value;
+        return 0;
+    }
+    if (!strcmp(name, "fp64_panel")) {   // two-level blocking of the fp64 factorisation: column blocks per panel (0/1 = plain algorithm)
+        GB2_ARG(h, value >= 0 && value <= 16, "fp64_panel must be in [0, 16]");
+        h->opt_fp64_panel = value;
+        h->factorized = false;
         return 0;
     }
     if (!strcmp(name, "small_diag")) {   // small-footprint diagonal-panel kernel (bit-identical results)

@@ -150,6 +150,8 @@ struct gb2_handle {
     // "green_sms" option: SM partition (CUDA green contexts) -- s_diag runs the diagonal-panel kernel on its own few SMs, s_main and
     // s_panel are re-created on the remaining ones, so that the 222 KB / 64k-register diagonal kernel never waits for an empty SM
     cudaStream_t s_diag = nullptr; void* green_a = nullptr; void* green_b = nullptr; int green_sms_a = 0, green_sms_b = 0;
+    // two-level blocking of the fp64 factorisation (single GPU): panels of opt_fp64_panel column blocks, one deep DMMA update per panel
+    int opt_fp64_panel = 0; cudaStream_t s_bulk2 = nullptr;
     int opt_small_diag = 0;      // diagonal-panel kernel variant that fits on an SM beside a GEMM CTA (256 threads, 130 KB) instead of needing an empty SM
     int opt_fused_group = 4;     // fused cold predict: column blocks per bulk update of the prediction rows (1, 2, 4, 8)
     int opt_solve_streams = 1;   // fp64 predict solve: split the prediction rows over this many concurrent streams (wave-tail filling)

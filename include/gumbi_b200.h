@@ -186,6 +186,8 @@ int gb2_dist_allgather_dev(gb2_handle* h, const double* dsend, double* drecv, in
  *   "solve_streams" 1..4 fp64 predict solve: row slabs of the prediction points on this many concurrent streams (default 1)
  *   "fused_group"   1|2|4|8  gb2_factorize_predict: column blocks per bulk update of the prediction rows (default 4)
  *   "trace"         0|1  record the per-step timeline read by gb2_get_trace (measurement aid, off by default)
+ *   "fp64_panel"    0..16  single GPU, fp64: two-level blocking -- panels of this many 128-column blocks are factored with updates
+ *                        restricted to the panel, then applied to the trailing matrix by one update of depth 128*value (default 0: off)
  *   "small_diag"    0|1  diagonal-panel kernel variant of 256 threads / 130 KB that can share an SM with a GEMM CTA (the default
  *                        one needs an empty SM: 512 x 128 registers, 222 KB); same products in the same order -> bit-identical results
  *   "green_sms"     8..64 (multiple of 8)  single GPU: give the diagonal-panel kernel its own SM partition (CUDA green contexts) so that

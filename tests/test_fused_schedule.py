@@ -56,3 +56,40 @@ def test_prediction_rows_end_as_the_solved_panel(N, w):
     np.testing.assert_allclose(L[:N, :N], Lnn, rtol=1e-10, atol=1e-12)
     np.testing.assert_allclose(E[:, :N], np.linalg.solve(Lnn, Ks[:, :N].T).T, rtol=1e-9, atol=1e-11)
     np.testing.assert_allclose(L[N, :N], np.linalg.solve(Lnn, y), rtol=1e-9, atol=1e-11)   # the augmented row became v^T
+
+
+def emulate_two_level(K, T, pw):
+    """cholesky_enqueue with the "fp64_panel" option: panels of pw column blocks factored by factor_steps(c0, c1, col_limit=c1)
+    (every update restricted to the panel's own columns), then one deep update of the trailing matrix, split into the next panel's
+    columns (1) and the rest (2)."""
+    A = K.copy()
+    Np = A.shape[0]
+    nb = Np // T
+    blk = lambda b0, b1: slice(b0 * T, b1 * T)
+    for c0 in range(0, nb, pw):
+        c1 = min(c0 + pw, nb)
+        for k in range(c0, c1):                                               # factor_steps(c0, c1, c1)
+            Lkk = np.linalg.cholesky(A[blk(k, k + 1), blk(k, k + 1)])
+            A[blk(k, k + 1), blk(k, k + 1)] = Lkk
+            if k + 1 < nb:
+                A[blk(k + 1, nb), blk(k, k + 1)] = A[blk(k + 1, nb), blk(k, k + 1)] @ np.linalg.inv(Lkk).T   # panel solve: ALL rows below
+                if k + 1 < c1:                                               # updates: columns (k, c1) only
+                    P = A[blk(k + 1, nb), blk(k, k + 1)]
+                    A[blk(k + 1, nb), blk(k + 1, c1)] -= P @ A[blk(k + 1, c1), blk(k, k + 1)].T
+        if c1 >= nb:
+            break
+        c2 = min(c1 + pw, nb)
+        A[blk(c1, nb), blk(c1, c2)] -= A[blk(c1, nb), blk(c0, c1)] @ A[blk(c1, c2), blk(c0, c1)].T          # (1) next panel's columns
+        if c2 < nb:
+            A[blk(c2, nb), blk(c2, nb)] -= A[blk(c2, nb), blk(c0, c1)] @ A[blk(c2, nb), blk(c0, c1)].T      # (2) the rest
+    return np.tril(A)
+
+
+@pytest.mark.parametrize("pw", [2, 3, 4])
+@pytest.mark.parametrize("nb", [3, 5, 8, 9])
+def test_two_level_blocking_gives_the_cholesky_factor(nb, pw):
+    T = 3
+    rng = np.random.default_rng(nb * 10 + pw)
+    B = rng.standard_normal((nb * T, nb * T))
+    K = B @ B.T + nb * T * np.eye(nb * T)
+    np.testing.assert_allclose(emulate_two_level(K, T, pw), np.linalg.cholesky(K), rtol=1e-10, atol=1e-12)

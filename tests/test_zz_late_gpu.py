@@ -307,3 +307,30 @@ def test_small_footprint_diagonal_kernel_is_bit_identical(lib_built):
     with pytest.raises(np.linalg.LinAlgError, match="not positive definite"):
         e.factorize()
     e.close()
+
+
+@pytest.mark.parametrize("pw", [2, 4])
+def test_two_level_blocking_of_the_fp64_factorisation(lib_built, pw):
+    """set_option("fp64_panel", pw): panels of pw column blocks, one deep update per panel (split: next panel's columns / the rest on a
+    second bulk stream).  Different summation grouping only: factor, v, log-likelihood and posterior agree to rounding; fused path too."""
+    from gumbi_b200 import GPEngine
+    from oracle import gp_oracle as orc
+
+    for n, d in ((1500, 3), (700, 2), (300, 2)):
+        spec, X, y, Xs = orc.synthetic_problem(n, d, M_res=15)
+        e = GPEngine()
+        e.set_train(X, y)
+        e.set_kernel(spec)
+        e.factorize()
+        L0, v0, m0, p0 = e.get_L(), e.get_v(), e.mll(), e.predict(Xs)
+        e.set_option("fp64_panel", pw)
+        e.factorize()
+        np.testing.assert_allclose(e.get_L(), L0, rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(e.get_v(), v0, rtol=1e-8, atol=1e-10)
+        assert e.mll() == pytest.approx(m0, rel=1e-10)
+        p1 = e.predict(Xs)
+        np.testing.assert_allclose(p1[0], p0[0], rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(p1[1], p0[1], rtol=1e-6, atol=1e-10)
+        mu, var = e.factorize_predict(Xs, True)
+        np.testing.assert_allclose(mu, p0[0], rtol=1e-8, atol=1e-10)
+        e.close()

@@ -18,3 +18,5 @@ timeout 300 python tools/chol_trace.py 2>&1 | tail -30 | tee gpurun_out/chol_tra
 # diagonal-panel kernel: phase clocks of both variants + bit-identity of the small-footprint one
 timeout 120 ./tools/micro_potrf 2>&1 | tail -10 | tee gpurun_out/micro_potrf_r02a.log
 for o in small_diag=1 green_sms=8; do timeout 300 python bench.py --no-cpu --opt $o 2>&1 | tail -1 | tee gpurun_out/bench_r02a_$o.log; done
+# two-level blocking of the fp64 factorisation (panels of 2 / 4 column blocks), C2 and C4
+for w in c2 c4; do for o in fp64_panel=2 fp64_panel=4; do timeout 400 python bench.py --no-cpu --workload $w --steps 5 --opt $o 2>&1 | tail -1 | tee gpurun_out/bench_r02a_${w}_$o.log; done; done
