@@ -149,6 +149,15 @@ def test_not_positive_definite_reports_pivot(engine):
         engine.factorize()
     with pytest.raises(ValueError, match="before a successful gb2_factorize"):
         engine.predict(X[:3])
+    # robustly indefinite (not a rounding residue): Linear term with tau < 0, K_ii = 1 - 4 x_i0^2 < 0 wherever |x_i0| > 1/2
+    spec2, X2, y2, _ = orc.synthetic_problem(300, 2)
+    spec2["terms"][0].update(lin_idx=[0], c=[0.0], tau=-4.0)
+    engine.set_train(X2, y2)
+    engine.set_kernel(spec2)
+    with pytest.raises(np.linalg.LinAlgError, match="not positive definite") as ei:
+        engine.factorize()
+    first_bad = int(np.argmax(1.0 - 4.0 * X2[:, 0] ** 2 + spec2["sigma"] ** 2 + 1e-6 <= 0)) + 1
+    assert f"order {first_bad}" in str(ei.value) or int(str(ei.value).split("order")[-1]) <= first_bad
 
 
 def test_argument_errors(engine):
