@@ -2,6 +2,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC gb2_abi.cu -o libgumbi_b200.so
 #include "predict.cuh"
 #include "mllgrad.cuh"
+#include "kbuild_persist.cuh"
 
 #include <dlfcn.h>
 
@@ -105,7 +106,7 @@ int predict_compact(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_noi
         prep_features<<<(unsigned)((Mp + 255) / 256), 256, 0, s>>>(dXs_all + m0 * h->D_in, Mc, Mp, h->pp, h->dFs, h->dCs, h->dInfo + 1);
         dim3 grid((unsigned)(Np / KB_T), (unsigned)(Mp / KB_T));
         kbuild_dmma_launch<false>(s, grid, kbuild_dmma_smem_bytes(h->kp), h->kp, h->dBtab, h->dFs, h->dCs, Mp, Mc, h->dF, h->dC, Np, N, nullptr,
-                                  h->dAt, ldt, G, me, 1);
+                                  h->dAt, ldt, G, me, 1, 4, h->opt_kbuild_persist ? h->dKbCtr : nullptr, h->n_sm);
         GB2_CUDA(h, cudaEventRecord(h->ev[1], s));
         launches += 2;
         // Step counters of this chunk: two buffers behind the factorisation's counters; the one used now was cleared one chunk
@@ -245,7 +246,7 @@ int predict_common(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_nois
                                                                                      nullptr, h->dAt, Np, 1, 0);
         else
             kbuild_dmma_launch<false>(s, grid, kbuild_dmma_smem_bytes(h->kp), h->kp, h->dBtab, h->dFs, h->dCs, Mp, Mc, h->dF, h->dC, Np, N, nullptr,
-                                      h->dAt, Np, 1, 0, 0, h->opt_kbuild_occ);
+                                      h->dAt, Np, 1, 0, 0, h->opt_kbuild_occ, h->opt_kbuild_persist ? h->dKbCtr : nullptr, h->n_sm);
         GB2_CUDA(h, cudaEventRecord(h->ev[2], s));
         launches += 2;
         const int n_str = (int)std::min<int64_t>(h->opt_solve_streams, Mp / TILE);
@@ -367,7 +368,13 @@ int gb2_create(gb2_handle** out, int device, int precision) {
         double tab[64];
         for (int j = 0; j < 64; j++) tab[j] = std::exp2((double)j / 64.0);
         if ((e = cudaMemcpyToSymbol(g_exp2_tab, tab, sizeof(tab))) != cudaSuccess) return fail(e, "cudaMemcpyToSymbol");
+        std::vector<double> tab2(KB4_TAB);
+        for (int j = 0; j < KB4_TAB; j++) tab2[j] = std::exp2((double)j / KB4_TAB);
+        if ((e = cudaMemcpyToSymbol(g_exp2_tab2k, tab2.data(), KB4_TAB * sizeof(double))) != cudaSuccess) return fail(e, "cudaMemcpyToSymbol");
     }
+    // work counters of the persistent K-build kernel (self-resetting; zeroed once here)
+    if ((e = cudaMalloc(&h->dKbCtr, 4 * sizeof(int))) != cudaSuccess) return fail(e, "cudaMalloc");
+    if ((e = cudaMemset(h->dKbCtr, 0, 4 * sizeof(int))) != cudaSuccess) return fail(e, "cudaMemset");
     if ((e = cudaFuncSetAttribute(mll_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 164 * 1024)) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
     if ((e = dgemm_nt_configure<128, 64, GM_SET>()) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
     *out = h;
@@ -383,7 +390,7 @@ int gb2_destroy(gb2_handle* h) {
     cudaFree(h->dLpack); cudaFree(h->dSend); cudaFree(h->dRecv); cudaFree(h->dFlags); cudaFree(h->dIpcXch);
     cudaFree(h->dRing); cudaFree(h->dV); cudaFree(h->dPart); cudaFree(h->dCov);
     cudaFree(h->dX); cudaFree(h->dy); cudaFree(h->dBtab); cudaFree(h->dF); cudaFree(h->dC); cudaFree(h->dA);
-    cudaFree(h->dDinv); cudaFree(h->dInfo); cudaFree(h->dScal); cudaFree(h->dXs); cudaFree(h->dFs); cudaFree(h->dCs);
+    cudaFree(h->dDinv); cudaFree(h->dInfo); cudaFree(h->dKbCtr); cudaFree(h->dScal); cudaFree(h->dXs); cudaFree(h->dFs); cudaFree(h->dCs);
     cudaFree(h->dAt); cudaFree(h->dMean); cudaFree(h->dVar);
     cudaFree(h->dW); cudaFree(h->dS); cudaFree(h->dAlpha); cudaFree(h->dGrad);
     cudaFree(h->dPhi); cudaFree(h->dPlo); cudaFree(h->dLhi); cudaFree(h->dLlo); cudaFree(h->dAthi); cudaFree(h->dAtlo);
@@ -732,7 +739,7 @@ static int build_K(gb2_handle* h, int& launches) {
                                                                                 h->dA, Np, h->world, h->rank);
     else
         kbuild_dmma_launch<true>(s, grid, kbuild_dmma_smem_bytes(h->kp), h->kp, h->dBtab, h->dF, h->dC, Np, N, h->dF, h->dC, Np, N, h->dy, h->dA, Np,
-                                 h->world, h->rank, h->compact ? 1 : 0, h->opt_kbuild_occ);
+                                 h->world, h->rank, h->compact ? 1 : 0, h->opt_kbuild_occ, h->opt_kbuild_persist ? h->dKbCtr : nullptr, h->n_sm);
     GB2_CUDA(h, cudaEventRecord(h->ev[2], s));
     launches += 2;
     return 0;
@@ -772,7 +779,7 @@ static int factorize_impl(gb2_handle* h, const ExtPredict& x) {
         prep_features<<<(unsigned)((Mp + 255) / 256), 256, 0, s>>>(dXs, x.M, Mp, h->pp, h->dFs, h->dCs, h->dInfo + 1);
         dim3 grid((unsigned)(Np / KB_T), (unsigned)(Mp / KB_T));
         kbuild_dmma_launch<false>(s, grid, kbuild_dmma_smem_bytes(h->kp), h->kp, h->dBtab, h->dFs, h->dCs, Mp, x.M, h->dF, h->dC, Np, N, nullptr,
-                                  h->dAt, Np, 1, 0, 0, h->opt_kbuild_occ);
+                                  h->dAt, Np, 1, 0, 0, h->opt_kbuild_occ, h->opt_kbuild_persist ? h->dKbCtr : nullptr, h->n_sm);
         GB2_CUDA(h, cudaEventRecord(h->ev[2], s));   // "K build" now covers K and K*
         launches += 2;
         h->ext_At = h->dAt; h->ext_rows = Mp; h->ext_ld = Np; h->ext_ncols = (int)((N + TILE - 1) / TILE);
@@ -945,12 +952,12 @@ int gb2_predict_full(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_no
     prep_features<<<(unsigned)((Mp + 255) / 256), 256, 0, s>>>(h->dXs, M, Mp, h->pp, h->dFs, h->dCs, h->dInfo + 1);
     // A^T (rows = prediction points), exactly as gb2_predict
     dim3 grid((unsigned)(Np / KB_T), (unsigned)(Mp / KB_T));
-    kbuild_dmma_launch<false>(s, grid, kbuild_dmma_smem_bytes(h->kp), h->kp, h->dBtab, h->dFs, h->dCs, Mp, M, h->dF, h->dC, Np, N, nullptr, h->dAt, Np, 1, 0);
+    kbuild_dmma_launch<false>(s, grid, kbuild_dmma_smem_bytes(h->kp), h->kp, h->dBtab, h->dFs, h->dCs, Mp, M, h->dF, h->dC, Np, N, nullptr, h->dAt, Np, 1, 0, 0, 4, h->opt_kbuild_persist ? h->dKbCtr : nullptr, h->n_sm);
     trsm_rec(s, h->dA, Np, h->dDinv, h->dAt, Np, Mp, 0, ncols, launches);
     // K(X*, X*) (all tiles) and cov -= At At^T over the training columns only (depth = ncols * 128: the augmented / padding
     // columns right of N inside the last block are zero in At by construction of K(X*,X) and stay zero through the solve)
     dim3 g2((unsigned)(Mp / KB_T), (unsigned)(Mp / KB_T));
-    kbuild_dmma_launch<false>(s, g2, kbuild_dmma_smem_bytes(h->kp), h->kp, h->dBtab, h->dFs, h->dCs, Mp, M, h->dFs, h->dCs, Mp, M, nullptr, h->dCov, Mp, 1, 0);
+    kbuild_dmma_launch<false>(s, g2, kbuild_dmma_smem_bytes(h->kp), h->kp, h->dBtab, h->dFs, h->dCs, Mp, M, h->dFs, h->dCs, Mp, M, nullptr, h->dCov, Mp, 1, 0, 0, 4, h->opt_kbuild_persist ? h->dKbCtr : nullptr, h->n_sm);
     mask_columns_kernel<<<(unsigned)((Mp + 255) / 256), 256, 0, s>>>(h->dAt, Np, Mp, N, (int64_t)ncols * TILE);
     dgemm_nt_launch<128, 64, GM_SUB>(s, h->dAt, Np, h->dAt, Np, h->dCov, Mp, Mp, Mp, ncols * TILE, 0, 0, 0);
     posterior_reduce_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>(h->kp, h->dBtab, h->dFs, h->dCs, Mp, h->dAt, Np, h->dA + N * Np, N, M, pred_noise,
@@ -1223,6 +1230,7 @@ int gb2_set_option(gb2_handle* h, const char* name, int value) {
         h->opt_kbuild_occ = value;
         return 0;
     }
+    if (!strcmp(name, "kbuild_persist")) { h->opt_kbuild_persist = value ? 1 : 0; h->factorized = false; return 0; }   // ablation: 0 = round-1 strip / per-tile kernels
     if (!strcmp(name, "kbuild_v1")) { h->opt_kbuild_v1 = value ? 1 : 0; h->factorized = false; return 0; }   // ablation: scalar-FMA + libm exp K-build
     if (!strcmp(name, "tf32_nb")) {   // panel width of the GB2_TF32 factorisation / leaf width of its solve, in 128-column blocks
         GB2_ARG(h, value >= 0 && value <= 16, "tf32_nb must be in [0, 16] (0 = auto)");

@@ -139,6 +139,8 @@ struct gb2_handle {
     int opt_tf32_leaf = 4;   // GB2_TF32 solve: sub-solves up to this many blocks stay on the fp64 kernels
     int tf32_nb() const { return opt_tf32_nb > 0 ? opt_tf32_nb : (Np >= 8192 ? 8 : 4); }
     int opt_kbuild_v1 = 0;
+    int opt_kbuild_persist = 1;   // single-term models: persistent strip kernel (kbuild_persist.cuh); 0 = round-1 kernels (ablation)
+    int* dKbCtr = nullptr;        // its work counters (self-resetting)
     int opt_kbuild_occ = 4;
     int opt_chain_on_panel = 1;   // Cholesky: keep the next-column update on the panel stream (no cross-stream hop on the chain)
     int opt_fastdiag = 0;    // single GPU: "row-fix" schedule for the next diagonal block (cholesky.cuh); measured slower, kept as ablation

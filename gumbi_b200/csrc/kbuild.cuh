@@ -611,11 +611,24 @@ kbuild_strip_kernel(KParams kp, const double* __restrict__ Fi, int64_t stride_i,
 
 inline size_t kbuild_strip_smem_bytes(const KParams& kp) { return (size_t)(3 * kb2_ka(kp.t[0].d) * KB2_TS + 64) * sizeof(double); }
 
+// persistent kernel for the single-term models (kbuild_persist.cuh, included at the end of this header's users)
+inline bool kb4_eligible(const KParams& kp, bool train, int compact);
+template <bool TRAIN>
+inline void kbuild_persist_launch(cudaStream_t s, int n_sm, const KParams& kp, const double* Btab, const double* Fi, const int* Ci, int64_t stride_i,
+                                  int64_t n_i, const double* Fj, const int* Cj, int64_t stride_j, int64_t n_j, int n_row_tiles, int n_col_tiles,
+                                  const double* y, double* out, int64_t ld, int own_stride, int own_rank, int compact, int* ctr);
+
 // host-side dispatch over the specialisations
 template <bool TRAIN>
 inline void kbuild_dmma_launch(cudaStream_t s, dim3 grid, size_t smem, const KParams& kp, const double* Btab, const double* Fi, const int* Ci,
                                int64_t stride_i, int64_t n_i, const double* Fj, const int* Cj, int64_t stride_j, int64_t n_j, const double* y,
-                               double* out, int64_t ld, int own_stride, int own_rank, int compact = 0, int occ = 4) {
+                               double* out, int64_t ld, int own_stride, int own_rank, int compact = 0, int occ = 4, int* ctr = nullptr, int n_sm = 0) {
+    // single-term models without a Linear part: persistent strip kernel (kbuild_persist.cuh); ctr == nullptr keeps the round-1 kernels (ablation)
+    if (ctr && kb4_eligible(kp, TRAIN, compact)) {
+        kbuild_persist_launch<TRAIN>(s, n_sm, kp, Btab, Fi, Ci, stride_i, n_i, Fj, Cj, stride_j, n_j, (int)grid.y, (int)grid.x, y, out, ld, own_stride,
+                                     own_rank, compact, ctr);
+        return;
+    }
     // (the strip kernel's prefetch pipeline walks consecutive column tiles; the column-sharded K* build uses the per-tile kernel)
     const bool simple = kp.n_terms == 1 && kp.t[0].n_lin == 0 && kp.t[0].n_coreg == 0 && kp.noise_cat < 0 && (TRAIN || !compact);
     if (simple && (kp.t[0].kind == GB2_EXPQUAD || kp.t[0].kind == GB2_MATERN52)) {

@@ -26,6 +26,21 @@ def test_reference_arm_json_line():
     assert d["value"] > 0 and d["ms_per_step"] > 0
 
 
+def test_reference_arm_uses_all_cores_under_torchrun_env():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must not inherit it (round 1: the N>1 reference runs were
+    single-threaded and the driver's ratios at N>1 void).  Also: both arms print the same ``config`` keys."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", LOCAL_RANK="0", WORLD_SIZE="2")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1", "--gpus", "2", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert res.returncode == 0, res.stderr[-2000:]
+    d = json.loads(res.stdout.strip().splitlines()[-1])
+    cores = os.cpu_count()
+    assert d["cpu_baseline"]["cores"] == cores
+    assert f"openblas:{cores}" in d["cpu_baseline"]["sample"] or cores == 1, d["cpu_baseline"]["sample"]
+    assert set(d["config"]) == {"workload", "precision", "N", "M", "d", "outputs", "kernel", "n_gpus", "parallelism", "l2_policy", "engine_options"}
+    assert d["config"]["n_gpus"] == 2 and d["scaling"] == "strong"
+
+
 def test_reference_arm_other_ranks_exit_quietly():
     env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1", "--gpus", "2"],

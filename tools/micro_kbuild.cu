@@ -1,0 +1,178 @@
+// Stand-alone timing + accuracy check of the K-build kernels (strip kernel of round 1 vs the persistent kernel), one GPU.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --expt-relaxed-constexpr tools/micro_kbuild.cu -o tools/micro_kbuild
+//   ./tools/micro_kbuild [N=32768]
+// Prints, per (kind, d, P): ms and algorithmic GB/s (8 N (N+1) / 2 bytes) of each kernel, max relative deviation between the two
+// over the whole lower triangle, and max relative error of sampled entries against a long-double host evaluation of the
+// reference formula (Stationary.square_dist expanded form, clipped; Matern: sqrt(r2 + 1e-12)).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <vector>
+#include "../gumbi_b200/csrc/kbuild_persist.cuh"
+
+using namespace gb2;
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at line %d\n", cudaGetErrorString(e_), __LINE__); exit(1); } } while (0)
+
+__global__ void maxdiff_kernel(const double* A, const double* B, int64_t n, int64_t ld, double* out) {
+    double m = 0;
+    for (int64_t r = blockIdx.x; r < n; r += gridDim.x)
+        for (int64_t c = threadIdx.x; c <= r; c += blockDim.x) {
+            const double a = A[r * ld + c], b = B[r * ld + c];
+            const double dlt = fabs(a - b) / fmax(fabs(b), 1e-300);
+            if (dlt > m) m = dlt;
+        }
+    for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(m));
+}
+
+static long double ref_entry(int kind, const std::vector<double>& X, int D_in, int d, const double* ls, int64_t i, int64_t j) {
+    long double si = 0, sj = 0, dot = 0;
+    for (int k = 0; k < d; k++) {
+        const double ui = X[i * D_in + k] * (1.0 / ls[k]), uj = X[j * D_in + k] * (1.0 / ls[k]);   // Stationary: X * (1/ls) in fp64
+        si += (long double)ui * ui; sj += (long double)uj * uj; dot += (long double)ui * uj;
+    }
+    long double r2 = si + sj - 2 * dot;
+    if (r2 < 0) r2 = 0;
+    if (kind == GB2_EXPQUAD) return expl(-0.5L * r2);
+    const long double r = sqrtl(r2 + 1e-12L);
+    if (kind == GB2_MATERN52) return (1 + sqrtl(5.0L) * r + 5.0L / 3 * r * r) * expl(-sqrtl(5.0L) * r);
+    if (kind == GB2_MATERN32) return (1 + sqrtl(3.0L) * r) * expl(-sqrtl(3.0L) * r);
+    if (kind == GB2_MATERN12) return expl(-r);
+    return expl(-0.5L * r);
+}
+
+template <int KIND, int KS, int NCG, int OCC>
+static float time_persist(const KParams& kp, KB4Args a, int n_sm, int strip, int reps) {
+    CK(cudaFuncSetAttribute(kbuild_persist_kernel<true, KIND, KS, NCG, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kb4_smem_bytes<KS, NCG>()));
+    a.strip = strip;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 2; i++) kbuild_persist_kernel<true, KIND, KS, NCG, OCC><<<n_sm * OCC, KB_THREADS, kb4_smem_bytes<KS, NCG>()>>>(kp, a);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < reps; i++) kbuild_persist_kernel<true, KIND, KS, NCG, OCC><<<n_sm * OCC, KB_THREADS, kb4_smem_bytes<KS, NCG>()>>>(kp, a);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    return ms / reps;
+}
+
+template <int KIND, int KS, int NCG>
+static void run_case(int64_t n, int d, int P, int n_sm) {
+    const int64_t N = n * P, Np = round_up(N + 1, TILE);
+    const int D_in = d + (P > 1 ? 1 : 0);
+    std::mt19937_64 rng(2021);
+    std::normal_distribution<double> nd;
+    std::vector<double> X((size_t)N * D_in), y(N), ls(d);
+    for (int k = 0; k < d; k++) ls[k] = (1.0 + 0.25 * k) * std::sqrt((double)d);
+    for (int64_t i = 0; i < n; i++)
+        for (int k = 0; k < d; k++) {
+            const double v = nd(rng);
+            for (int p = 0; p < P; p++) X[(size_t)(p * n + i) * D_in + k] = v;
+        }
+    if (P > 1) for (int p = 0; p < P; p++) for (int64_t i = 0; i < n; i++) X[(size_t)(p * n + i) * D_in + d] = p;
+    for (auto& v : y) v = nd(rng);
+    KParams kp{}; PrepParams pp{};
+    kp.n_terms = pp.n_terms = 1; pp.D_in = D_in;
+    kp.t[0].kind = KIND; kp.t[0].d = pp.d[0] = d; kp.t[0].n_lin = pp.n_lin[0] = 0; kp.t[0].feat_off = pp.feat_off[0] = 0;
+    kp.t[0].eta2 = 1.3; kp.t[0].tau = 0; kp.n_feat = d + 1; kp.sigma2 = 0.01; kp.jitter = 1e-6; kp.noise_cat = -1;
+    for (int k = 0; k < d; k++) { pp.cont_idx[0][k] = k; pp.inv_ls[0][k] = 1.0 / ls[k]; }
+    std::vector<double> B;
+    if (P > 1) {
+        kp.n_cat = pp.n_cat = 1; pp.cat_col[0] = d; pp.cat_P[0] = P;
+        kp.t[0].n_coreg = 1; kp.t[0].cg_cat[0] = 0; kp.t[0].cg_P[0] = P; kp.t[0].cg_Boff[0] = 0;
+        B.resize(P * P);
+        std::vector<double> W(P * 2);
+        for (auto& v : W) v = nd(rng);
+        for (int p = 0; p < P; p++) for (int q = 0; q < P; q++) B[p * P + q] = W[2 * p] * W[2 * q] + W[2 * p + 1] * W[2 * q + 1] + (p == q ? 1.0 : 0.0);
+    }
+    double *dX, *dy, *dF, *dA, *dB2, *dBtab = nullptr, *dMax;
+    int *dC, *dBad, *dCtr;
+    CK(cudaMalloc(&dX, X.size() * 8)); CK(cudaMalloc(&dy, y.size() * 8)); CK(cudaMalloc(&dF, (size_t)(d + 1) * Np * 8));
+    CK(cudaMalloc(&dC, (size_t)Np * 4)); CK(cudaMalloc(&dBad, 4)); CK(cudaMalloc(&dCtr, 16)); CK(cudaMalloc(&dMax, 8));
+    CK(cudaMalloc(&dA, (size_t)Np * Np * 8)); CK(cudaMalloc(&dB2, (size_t)Np * Np * 8));
+    CK(cudaMemset(dCtr, 0, 16)); CK(cudaMemset(dBad, 0, 4)); CK(cudaMemset(dMax, 0, 8));
+    CK(cudaMemcpy(dX, X.data(), X.size() * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dy, y.data(), y.size() * 8, cudaMemcpyHostToDevice));
+    if (P > 1) { CK(cudaMalloc(&dBtab, B.size() * 8)); CK(cudaMemcpy(dBtab, B.data(), B.size() * 8, cudaMemcpyHostToDevice)); }
+    prep_features<<<(unsigned)((Np + 255) / 256), 256>>>(dX, N, Np, pp, dF, dC, dBad);
+    CK(cudaDeviceSynchronize());
+
+    // round-1 kernels (strip kernel for the plain model, generic DMMA kernel with Coregion) into dB2
+    dim3 grid((unsigned)(Np / KB_T), (unsigned)(Np / KB_T));
+    CK(kbuild_dmma_configure<true>());
+    const int reps = N >= 16384 ? 5 : 20;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 2; i++)
+        kbuild_dmma_launch<true>(0, grid, kbuild_dmma_smem_bytes(kp), kp, dBtab, dF, dC, Np, N, dF, dC, Np, N, dy, dB2, Np, 1, 0, 0, 4);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < reps; i++)
+        kbuild_dmma_launch<true>(0, grid, kbuild_dmma_smem_bytes(kp), kp, dBtab, dF, dC, Np, N, dF, dC, Np, N, dy, dB2, Np, 1, 0, 0, 4);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms_old;
+    CK(cudaEventElapsedTime(&ms_old, e0, e1));
+    ms_old /= reps;
+    const double bytes = 8.0 * N * (N + 1) / 2 + 8.0 * N * D_in;
+    printf("kind %d d %d P %d N %lld | round-1 kernel %.3f ms %.0f GB/s\n", KIND, d, P, (long long)N, ms_old, bytes / ms_old / 1e6);
+
+    KB4Args a{};
+    a.Fi = dF; a.stride_i = Np; a.n_i = N; a.Fj = dF; a.stride_j = Np; a.n_j = N; a.Ci = dC; a.Cj = dC; a.Btab = dBtab; a.y = dy; a.out = dA; a.ld = Np;
+    a.n_row_tiles = a.n_col_tiles = (int)(Np / KB_T); a.own_stride = 1; a.own_rank = 0; a.compact = 0; a.ctr = dCtr;
+    for (int strip : {4, 8, 16}) {
+        const float m2 = time_persist<KIND, KS, NCG, 2>(kp, a, n_sm, strip, reps);
+        const float m3 = time_persist<KIND, KS, NCG, 3>(kp, a, n_sm, strip, reps);
+        const float m4 = time_persist<KIND, KS, NCG, 4>(kp, a, n_sm, strip, reps);
+        printf("   persistent strip %2d : occ2 %.3f ms %.0f GB/s | occ3 %.3f ms %.0f GB/s | occ4 %.3f ms %.0f GB/s\n", strip, m2, bytes / m2 / 1e6, m3,
+               bytes / m3 / 1e6, m4, bytes / m4 / 1e6);
+    }
+    // accuracy: new vs round-1 over the whole lower triangle (incl. the y row), sampled entries vs long double
+    maxdiff_kernel<<<1024, 256>>>(dA, dB2, N + 1, Np, dMax);
+    double md;
+    CK(cudaMemcpy(&md, dMax, 8, cudaMemcpyDeviceToHost));
+    double worst_new = 0, worst_old = 0;
+    std::uniform_int_distribution<int64_t> ui(0, N - 1);
+    for (int s = 0; s < 4000; s++) {
+        int64_t i = ui(rng), j = ui(rng);
+        if (s < 400) j = i;                 // diagonal entries
+        else if (s < 800) j = std::max<int64_t>(0, i - (s & 63));   // near-diagonal
+        if (j > i) std::swap(i, j);
+        double vn, vo;
+        CK(cudaMemcpy(&vn, dA + i * Np + j, 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&vo, dB2 + i * Np + j, 8, cudaMemcpyDeviceToHost));
+        long double r = 1.3L * ref_entry(KIND, X, D_in, d, ls.data(), i, j);
+        if (P > 1) r *= B[(int)X[i * D_in + d] * P + (int)X[j * D_in + d]];
+        if (i == j) r += 0.01L + 1e-6L;
+        const double den = std::max((double)fabsl(r), 1e-300);
+        worst_new = std::max(worst_new, (double)fabsl(vn - r) / den);
+        worst_old = std::max(worst_old, (double)fabsl(vo - r) / den);
+    }
+    printf("   max rel dev new vs round-1 (lower triangle) %.3e | sampled vs long double: new %.3e  round-1 %.3e\n", md, worst_new, worst_old);
+    cudaFree(dX); cudaFree(dy); cudaFree(dF); cudaFree(dC); cudaFree(dBad); cudaFree(dCtr); cudaFree(dMax); cudaFree(dA); cudaFree(dB2);
+    if (dBtab) cudaFree(dBtab);
+}
+
+int main(int argc, char** argv) {
+    const int64_t N = argc > 1 ? atoll(argv[1]) : 32768;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    {
+        double tab[64];
+        for (int j = 0; j < 64; j++) tab[j] = std::exp2((double)j / 64.0);
+        CK(cudaMemcpyToSymbol(g_exp2_tab, tab, sizeof(tab)));
+        std::vector<double> t2(KB4_TAB);
+        for (int j = 0; j < KB4_TAB; j++) t2[j] = std::exp2((double)j / KB4_TAB);
+        CK(cudaMemcpyToSymbol(g_exp2_tab2k, t2.data(), KB4_TAB * sizeof(double)));
+    }
+    const int n_sm = prop.multiProcessorCount;
+    printf("%s, %d SMs\n", prop.name, n_sm);
+    run_case<GB2_EXPQUAD, 2, 0>(N, 8, 1, n_sm);
+    run_case<GB2_MATERN52, 2, 0>(N, 8, 1, n_sm);
+    run_case<GB2_EXPQUAD, 1, 1>(N / 2, 4, 2, n_sm);
+    run_case<GB2_MATERN32, 2, 0>(N / 4, 5, 1, n_sm);
+    run_case<GB2_EXPQUAD, 2, 0>(8192, 8, 1, n_sm);
+    return 0;
+}
