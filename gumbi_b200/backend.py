@@ -409,9 +409,27 @@ class B200Backend:
             # every rank holds the factor: each serves a contiguous slice of the points, slices are gathered on all ranks
             from . import dist as gdist
 
-            lo, hi = gdist.grid_slice(len(points_array), self.engine.rank, self.engine.world)
+            M, world = len(points_array), self.engine.world
+            lo, hi = gdist.grid_slice(M, self.engine.rank, world)
+            if hasattr(self.engine, "allgather_device"):
+                # slices stay on the device: predict into [mean | var] of a padded slot, one NCCL all-gather on the handle's
+                # stream (gb2_dist_allgather_dev), one D2H copy -- no pickling of host arrays through torch.distributed
+                import torch
+
+                dev = torch.device("cuda", self.engine.device)
+                slot = -(-M // world)
+                dXs = torch.from_numpy(np.ascontiguousarray(self._engine_points(points_array[lo:hi]))).to(dev)
+                dloc = torch.zeros(2 * slot, dtype=torch.float64, device=dev)
+                dall = torch.empty(2 * slot * world, dtype=torch.float64, device=dev)
+                torch.cuda.synchronize(dev)
+                if hi > lo:
+                    self.engine.predict_device(dXs.data_ptr(), hi - lo, bool(with_noise), dloc.data_ptr(), dloc.data_ptr() + 8 * slot)
+                self.engine.allgather_device(dloc.data_ptr(), dall.data_ptr(), 2 * slot)
+                a = dall.cpu().numpy().reshape(world, 2, slot)
+                cnt = [gdist.grid_slice(M, r, world)[1] - gdist.grid_slice(M, r, world)[0] for r in range(world)]
+                return (np.concatenate([a[r, 0, :cnt[r]] for r in range(world)]), np.concatenate([a[r, 1, :cnt[r]] for r in range(world)]))
             mu, var = self.engine.predict(self._engine_points(points_array[lo:hi]), pred_noise=bool(with_noise))
-            return gdist.gather_grid(mu, var, len(points_array))
+            return gdist.gather_grid(mu, var, M)
         return self.engine.predict(self._engine_points(points_array), pred_noise=bool(with_noise))
 
     # -- conditional / posterior samples (GP.py:861-979) ------------------------------------------------------------

@@ -12,7 +12,10 @@
 // distinct banks per half-warp (row stride = 8 banks mod 32), i.e. conflict-free LDS.64.
 // All extents are multiples of the tile (the host pads N and M to 128), so the main loop has no bounds checks.
 #pragma once
+#include <mutex>
+#include <unordered_map>
 #include "gb2_internal.cuh"
+#include "tf32gemm.cuh"   // mbarrier / TMA helpers (tc::mbar_*, tc::tma_load_2d, tc::encode_tiled_fn)
 
 namespace gb2 {
 
@@ -182,6 +185,252 @@ inline cudaError_t dgemm_nt_configure() {
                                 (int)dgemm_smem_bytes<BM, BN, BK, STAGES>());
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// TMA-staged variant (the product path; the cp.async kernel above stays as fallback for operands outside a registered
+// allocation and as the ablation, set_option("dgemm_tma", 0)).
+//
+// Same CTA tile (128x64 / 64x128, 8 warps of 32x32, DMMA m8n8k4), same epilogue.  What changes is operand delivery:
+//   * one elected thread issues two cp.async.bulk.tensor.2d per k-tile (A: BM rows x 16 doubles, B: BN rows x 16 doubles =
+//     128-byte rows, hardware 128-byte swizzle) into a 4-stage ring; completion is tracked by an mbarrier per stage
+//     (complete_tx), consumption by a second mbarrier per stage that every warp arrives on -- no __syncthreads and no
+//     LDGSTS address arithmetic in the compute warps, and a warp never waits for another warp, only for data;
+//   * fragments are read with conflict-free LDS.64 straight out of the swizzled tile: DMMA step j of a k-tile takes the four
+//     k indices  8 (t >> 1) + 2 j + (t & 1)  (t = lane % 4) for BOTH operands -- a permutation of the summation order inside
+//     the k-tile -- so that the 16 lanes of a half-warp (4 rows x 4 t) hit the 16 distinct 8-byte slots of a 128-byte line:
+//     physical 16-byte chunk = (4 (t >> 1) + j) ^ (row & 7), 8-byte half = t & 1.
+// Operands are addressed through CUtensorMaps of the ALLOCATION they live in (cuMemGetAddressRange + a cache keyed by
+// base / row stride / box rows); the launch passes element coordinates.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int GT_STAGES = 4;
+constexpr int GT_BK = 16;
+
+template <int BM, int BN>
+constexpr size_t dgemm_tma_smem_bytes() { return (size_t)GT_STAGES * (BM + BN) * 128 + 1024 /*alignment slack*/ + 128 /*barriers*/; }
+
+template <int BM, int BN, int MODE, int MINB = 2>
+__global__ void __launch_bounds__(256, MINB)
+dgemm_tma_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mB, int a_row0, int a_col0, int b_row0, int b_col0,
+                 double* C, int64_t ldc, int kdepth, int lower_only, int64_t row_off, int64_t col_off, int rb_first, int rb_stride,
+                 PushArgs push, int rb_local_first, int n_bi, int n_bj) {
+    constexpr int WM = 32, WN = 32, MI = WM / 8, NI = WN / 8;
+    constexpr int STAGE_BYTES = (BM + BN) * 128;
+    constexpr int TPB = TILE / BM;
+    static_assert(TILE % BM == 0 && (BM / WM) * (BN / WN) == 8, "8 warps of 32x32");
+
+    extern __shared__ unsigned char gt_smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)gt_smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + GT_STAGES * STAGE_BYTES);   // [STAGES] TMA bytes landed
+    uint64_t* empty = full + GT_STAGES;                                              // [STAGES] all 8 warps done reading
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp % (BM / WM), wn = warp / (BM / WM);
+    const int g = lane >> 2, t = lane & 3;
+
+    if (tid == 0) {
+        for (int s = 0; s < GT_STAGES; s++) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int nk = kdepth / GT_BK;
+    const int n_tiles = n_bi * n_bj;
+    // tile id -> rows / first k-tile; false: the tile lies above the diagonal (lower_only) and is skipped
+    auto tile_info = [&](int tile, int& bj, int64_t& grow, int64_t& lrow, int& kt0) -> bool {
+        const int bi = tile % n_bi;
+        bj = tile / n_bi;
+        grow = ((int64_t)rb_first + (int64_t)(bi / TPB) * rb_stride) * TILE + (int64_t)(bi % TPB) * BM;
+        lrow = rb_local_first >= 0 ? ((int64_t)rb_local_first + (int64_t)(bi / TPB)) * TILE + (int64_t)(bi % TPB) * BM : grow;
+        if (lower_only && col_off + (int64_t)bj * BN > row_off + grow + (BM - 1)) return false;
+        // lower_only == 2: both operands are rows of an upper-triangular matrix (W = L^-T), terms start at k = max(first rows)
+        kt0 = lower_only == 2 ? (int)(((grow > (int64_t)bj * BN) ? grow : (int64_t)bj * BN) / GT_BK) : 0;
+        return true;
+    };
+
+    // ---- producer state (thread 0 only): the ring runs ahead of the consumers ACROSS tiles, so the operands of the next tile
+    // stream in while this tile's epilogue reads and writes C
+    int p_tile = blockIdx.x, p_it = 0, p_nit = 0, p_arow = 0, p_brow = 0, p_kt0 = 0;
+    uint32_t p_g = 0;        // k-tiles issued so far
+    bool p_open = false;     // p_tile's coordinates are loaded
+    auto produce = [&](uint32_t upto) {   // issue k-tiles until p_g == upto or the CTA's tiles are exhausted
+        while (p_g < upto) {
+            if (!p_open) {
+                int bj, kt0; int64_t grow, lrow;
+                while (p_tile < n_tiles && !tile_info(p_tile, bj, grow, lrow, kt0)) p_tile += gridDim.x;
+                if (p_tile >= n_tiles) return;
+                p_arow = a_row0 + (int)lrow; p_brow = b_row0 + bj * BN; p_kt0 = kt0; p_nit = nk - kt0; p_it = 0;
+                p_open = true;
+                if (p_nit <= 0) { p_open = false; p_tile += gridDim.x; continue; }
+            }
+            const int st = (int)(p_g % GT_STAGES);
+            if (p_g >= (uint32_t)GT_STAGES) tc::mbar_wait(empty + st, (p_g / GT_STAGES - 1) & 1u);
+            unsigned char* dst = base + st * STAGE_BYTES;
+            tc::mbar_expect_tx(full + st, STAGE_BYTES);
+            tc::tma_load_2d(dst, &mA, a_col0 + (p_kt0 + p_it) * GT_BK, p_arow, full + st);
+            tc::tma_load_2d(dst + BM * 128, &mB, b_col0 + (p_kt0 + p_it) * GT_BK, p_brow, full + st);
+            p_g++;
+            if (++p_it == p_nit) { p_open = false; p_tile += gridDim.x; }
+        }
+    };
+
+    // byte offset of this lane's fragment element inside a 128-byte row, per DMMA step j: chunk (4 (t>>1) + j) ^ g, half t & 1
+    const uint32_t off0 = (uint32_t)((((4 * (t >> 1)) ^ g) << 4) | ((t & 1) << 3));
+    const uint32_t a_base = tc::smem_u32(base) + (uint32_t)((wm * WM + g) * 128);
+    const uint32_t b_base = tc::smem_u32(base) + (uint32_t)(BM * 128 + (wn * WN + g) * 128);
+
+    uint32_t c_g = 0;        // k-tiles consumed so far (same sequence as the producer's)
+    if (tid == 0) produce(GT_STAGES - 1);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int bj, kt0; int64_t grow, lrow;
+        if (!tile_info(tile, bj, grow, lrow, kt0)) continue;
+        const int n_it = nk - kt0;
+        double acc[MI][NI][2];
+#pragma unroll
+        for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+            for (int ni = 0; ni < NI; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+        for (int it = 0; it < n_it; it++, c_g++) {
+            if (tid == 0) produce(c_g + GT_STAGES);
+            const int st = (int)(c_g % GT_STAGES);
+            tc::mbar_wait(full + st, (c_g / GT_STAGES) & 1u);
+            const uint32_t sa = a_base + (uint32_t)(st * STAGE_BYTES), sb = b_base + (uint32_t)(st * STAGE_BYTES);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t o = off0 ^ (uint32_t)(j << 4);
+                double a[MI], b[NI];
+#pragma unroll
+                for (int mi = 0; mi < MI; mi++) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a[mi]) : "r"(sa + o + mi * 1024));
+#pragma unroll
+                for (int ni = 0; ni < NI; ni++) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b[ni]) : "r"(sb + o + ni * 1024));
+#pragma unroll
+                for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < NI; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+            }
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(empty + st);
+        }
+
+        double* Cg = C + (lrow + wm * WM + g) * ldc + (int64_t)bj * BN + wn * WN + 2 * t;
+#pragma unroll
+        for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+            for (int ni = 0; ni < NI; ni++) {
+                double2* p = reinterpret_cast<double2*>(Cg + (int64_t)mi * 8 * ldc + ni * 8);
+                if (MODE == GM_SUB) {
+                    double2 c = *p;
+                    c.x -= acc[mi][ni][0];
+                    c.y -= acc[mi][ni][1];
+                    *p = c;
+                } else {
+                    *p = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+                }
+            }
+        if (MODE == GM_SET_PUSH) {
+            const int64_t pld = push.ld ? push.ld : ldc;
+            const int64_t off = (grow + wm * WM + g) * pld + (int64_t)bj * BN + wn * WN + 2 * t;
+            for (int pr = 0; pr < push.n_peers; pr++) {
+                double* Pg = push.peerC[pr] + off;
+#pragma unroll
+                for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < NI; ni++)
+                        *reinterpret_cast<double2*>(Pg + (int64_t)mi * 8 * pld + ni * 8) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+            }
+            __threadfence_system();          // this thread's peer stores are performed system-wide ...
+            __syncthreads();                 // ... for every thread of the CTA, before the CTA announces its tile
+            if (tid == 0)
+                for (int pr = 0; pr < push.n_peers; pr++)
+                    if (push.peerFlag[pr]) atomicAdd_system(push.peerFlag[pr], 1u);
+        }
+    }
+}
+
+// ---- host side: tensor maps of whole allocations, cached -----------------------------------------------------------------
+typedef CUresult (*MemGetAddressRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+inline MemGetAddressRangeFn mem_range_fn() {
+    static MemGetAddressRangeFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<MemGetAddressRangeFn>(p);
+    }
+    return fn;
+}
+
+struct TmaOperand { CUtensorMap map; int row0, col0; };
+
+inline int g_dgemm_tma = 1;          // set_option("dgemm_tma", 0/1): process-wide switch (ablation)
+inline int g_dgemm_persistent = 1;   // set_option("dgemm_persistent", 0/1): 0 = one CTA per tile (ablation)
+inline int tma_sm_count() {
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+    return n;
+}
+
+// Tensor map (fp64, box = 16 columns x box_rows rows, 128-byte swizzle) of the allocation holding `ptr`, viewed as a row-major
+// matrix with row stride `ld`; (row0, col0) = position of `ptr` inside it.  False if the operand cannot go through TMA.
+inline bool tma_operand(const double* ptr, int64_t ld, int box_rows, TmaOperand& out) {
+    if (!g_dgemm_tma || ld % 2 != 0 || ld < GT_BK) return false;
+    MemGetAddressRangeFn range = mem_range_fn();
+    tc::EncodeTiledFn encode = tc::encode_tiled_fn();
+    if (!range || !encode) return false;
+    CUdeviceptr basep = 0; size_t size = 0;
+    if (range(&basep, &size, (CUdeviceptr)(uintptr_t)ptr) != CUDA_SUCCESS || (basep & 15) != 0) return false;
+    const int64_t off = (int64_t)(((uintptr_t)ptr - (uintptr_t)basep) / sizeof(double));
+    const int64_t rows = (int64_t)(size / sizeof(double)) / ld;
+    if (rows < 1 || off / ld > 0x7fffffff) return false;
+    struct Key { uintptr_t base; size_t size; int64_t ld; int box; bool operator==(const Key& o) const { return base == o.base && size == o.size && ld == o.ld && box == o.box; } };
+    struct Hash { size_t operator()(const Key& k) const { return (size_t)k.base * 1315423911u ^ k.size ^ ((size_t)k.ld << 7) ^ (size_t)k.box; } };
+    static std::unordered_map<Key, CUtensorMap, Hash> cache;
+    static std::mutex mu;
+    const Key key{(uintptr_t)basep, size, ld, box_rows};
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto itc = cache.find(key);
+        if (itc == cache.end()) {
+            CUtensorMap m;
+            cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+            cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+            cuuint32_t box[2] = {(cuuint32_t)GT_BK, (cuuint32_t)box_rows};
+            cuuint32_t estr[2] = {1, 1};
+            if (encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)(uintptr_t)basep, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return false;
+            if (cache.size() > 4096) cache.clear();   // handles come and go (tests): bound the cache
+            itc = cache.emplace(key, m).first;
+        }
+        out.map = itc->second;
+    }
+    out.row0 = (int)(off / ld);
+    out.col0 = (int)(off % ld);
+    return true;
+}
+
+template <int BM, int BN, int MODE>
+inline bool dgemm_tma_try_launch(cudaStream_t s, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t rows,
+                                 int64_t cols, int kdepth, int lower_only, int64_t row_off, int64_t col_off, int rb_first, int rb_stride,
+                                 const PushArgs& pa, int rb_local_first) {
+    TmaOperand oa, ob;
+    if (kdepth % GT_BK != 0 || !tma_operand(A, lda, BM, oa) || !tma_operand(B, ldb, BN, ob)) return false;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(dgemm_tma_kernel<BM, BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgemm_tma_smem_bytes<BM, BN>()) != cudaSuccess)
+            return false;
+        configured = true;
+    }
+    // persistent: at most two CTAs per SM walk the tile list (row tile fastest, so concurrent CTAs share the B tile in L2)
+    const int n_bi = (int)(rows / BM), n_bj = (int)(cols / BN);
+    const int64_t n_tiles = (int64_t)n_bi * n_bj;
+    const int slots = 2 * tma_sm_count();
+    const unsigned grid = (unsigned)(g_dgemm_persistent && n_tiles > slots ? slots : n_tiles);
+    dgemm_tma_kernel<BM, BN, MODE><<<grid, 256, dgemm_tma_smem_bytes<BM, BN>(), s>>>(oa.map, ob.map, oa.row0, oa.col0, ob.row0, ob.col0, C, ldc, kdepth,
+                                                                                    lower_only, row_off, col_off, rb_first, rb_stride, pa, rb_local_first,
+                                                                                    n_bi, n_bj);
+    return true;
+}
+
 // rows x cols output, both multiples of the tile.
 template <int BM, int BN, int MODE, int BK = GM_BK, int STAGES = GM_STAGES, int WM = 32, int WN = 32, int MINB = 2>
 inline void dgemm_nt_launch(cudaStream_t s, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
@@ -192,6 +441,11 @@ inline void dgemm_nt_launch(cudaStream_t s, const double* A, int64_t lda, const 
     dim3 grid((unsigned)(rows / BM), (unsigned)(cols / BN));
     PushArgs pa{};
     if (push) pa = *push;
+    if constexpr (BK == GM_BK && STAGES == GM_STAGES && WM == 32 && WN == 32 && MINB == 2) {   // the product instantiations
+        if (dgemm_tma_try_launch<BM, BN, MODE>(s, A, lda, B, ldb, C, ldc, rows, cols, kdepth, lower_only, row_off, col_off, rb_first, rb_stride, pa,
+                                               rb_local_first))
+            return;
+    }
     dgemm_nt_kernel<BM, BN, MODE, BK, STAGES, WM, WN, MINB><<<grid, (BM / WM) * (BN / WN) * 32, dgemm_smem_bytes<BM, BN, BK, STAGES>(), s>>>(
         A, lda, B, ldb, C, ldc, kdepth, lower_only, row_off, col_off, rb_first, rb_stride, pa, rb_local_first);
 }

@@ -1230,6 +1230,8 @@ int gb2_set_option(gb2_handle* h, const char* name, int value) {
         h->opt_kbuild_occ = value;
         return 0;
     }
+    if (!strcmp(name, "dgemm_tma")) { g_dgemm_tma = value ? 1 : 0; h->factorized = false; return 0; }   // ablation (process-wide): 0 = cp.async-staged fp64 GEMM
+    if (!strcmp(name, "dgemm_persistent")) { g_dgemm_persistent = value ? 1 : 0; return 0; }   // ablation (process-wide): 0 = one CTA per output tile
     if (!strcmp(name, "kbuild_persist")) { h->opt_kbuild_persist = value ? 1 : 0; h->factorized = false; return 0; }   // ablation: 0 = round-1 strip / per-tile kernels
     if (!strcmp(name, "kbuild_v1")) { h->opt_kbuild_v1 = value ? 1 : 0; h->factorized = false; return 0; }   // ablation: scalar-FMA + libm exp K-build
     if (!strcmp(name, "tf32_nb")) {   // panel width of the GB2_TF32 factorisation / leaf width of its solve, in 128-column blocks

@@ -46,8 +46,9 @@ struct KB4Args {
 template <int ZS2>   // ZS2 = 2 * zs: 1 (ExpQuad, z = r^2, exp(-z/2)) or 2 (Matern family, z = w, exp(-z))
 __device__ __forceinline__ double kb4_exp(double z, const double* __restrict__ tab) {
     constexpr double zs = 0.5 * ZS2;
-    constexpr double LOG2E_2048 = 2954.63944374059729;     // 2048 / ln 2
-    constexpr double LN2_2048 = 3.38450771664611258e-4;     // ln 2 / 2048
+    constexpr double LN2 = 0.693147180559945309417232121458176568;
+    constexpr double LOG2E_2048 = (double)KB4_TAB / LN2;    // 2048 / ln 2   (constant-folded by the host compiler, correctly rounded)
+    constexpr double LN2_2048 = LN2 / (double)KB4_TAB;      // ln 2 / 2048
     constexpr double MAGIC = 6755399441055744.0;            // 1.5 * 2^52
     const double t = fma(z, -zs * LOG2E_2048, MAGIC);
     const int n = __double2loint(t);                         // round(-zs z 2048 / ln2) <= 0
@@ -316,7 +317,7 @@ inline bool kb4_eligible(const KParams& kp, bool train, int compact) {
     return kp.n_terms == 1 && kp.t[0].n_lin == 0 && kp.t[0].n_coreg <= KB4_MAXCG && kp.t[0].d >= 1 && kp.t[0].d <= 16 && (train || !compact);
 }
 
-constexpr int KB4_OCC = 3;   // resident CTAs per SM the register allocation is bounded for (tools/micro_kbuild.cu times 2, 3, 4)
+constexpr int KB4_OCC = 4;   // resident CTAs per SM the register allocation is bounded for (tools/micro_kbuild.cu times 2, 3, 4)
 
 template <bool TRAIN, int KIND, int KS, int NCG, int OCC = KB4_OCC>
 inline void kb4_launch_one(cudaStream_t s, int n_sm, const KParams& kp, const KB4Args& a) {

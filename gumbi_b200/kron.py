@@ -176,7 +176,22 @@ class KronEngine:
                 return None
             return e.factorize_predict(_predict_points, pred_noise=False)
 
-        self._block_posteriors = self._each(one)
+        # A non-PD block on one rank must fail the call on EVERY rank: the ranks own different blocks, and a rank that raised
+        # alone would skip the next gather while the others wait in it (and later pair with a stale one).
+        def guarded(q):
+            try:
+                return ("ok", one(q))
+            except np.linalg.LinAlgError as ex:
+                return ("not_pd", str(ex))
+
+        self.factorized = False
+        local = self._each(guarded)
+        verdicts = {q: (v[0], v[1] if v[0] != "ok" else None) for q, v in local.items()}
+        parts = [verdicts] if self.kron_world == 1 else self.gather(verdicts)
+        bad = sorted((q, v[1]) for part in parts for q, v in part.items() if v[0] != "ok")
+        if bad:
+            raise np.linalg.LinAlgError(f"Kronecker block {bad[0][0]}: {bad[0][1]}")
+        self._block_posteriors = {q: v[1] for q, v in local.items()}
         self.factorized = True
 
     def factorize_predict(self, Xs, pred_noise: bool = True):

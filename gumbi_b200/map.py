@@ -44,13 +44,14 @@ def _min_max_nonzero_distance(points):
         d = pdist(points)
         d = d[d != 0]
         return (float(d.min()), float(d.max())) if d.size else (None, None)
+    from scipy.spatial.distance import cdist
+
     lo, hi = np.inf, 0.0
-    for s in range(0, n, 1024):  # blocked, O(N * 1024) memory
-        blk = points[s:s + 1024]
-        d2 = np.maximum((blk ** 2).sum(1)[:, None] + (points ** 2).sum(1)[None, :] - 2.0 * blk @ points.T, 0.0)
-        nz = d2[d2 > 1e-24]
+    for s in range(0, n, 1024):  # blocked, O(N * 1024) memory; direct differences (as pdist), so identical points give an exact 0
+        d = cdist(points[s:s + 1024], points[s:])   # pairs (i, j >= i): every unordered pair once, plus the exact-zero self pairs
+        nz = d[d != 0]
         if nz.size:
-            lo, hi = min(lo, float(np.sqrt(nz.min()))), max(hi, float(np.sqrt(nz.max())))
+            lo, hi = min(lo, float(nz.min())), max(hi, float(nz.max()))
     return (lo, hi) if hi > 0 else (None, None)
 
 
@@ -278,7 +279,24 @@ def make_objective(gp, start=None):
             point[n] = v.reshape(shapes[n]) if shapes[n] != () else float(v[0])
         return point
 
+    def lockstep(val, grad):
+        """Multi-GPU: every rank runs this optimiser over a collective objective.  The device gradient is summed with fp64 atomics, so
+        it is not bitwise identical between ranks; rank 0's (value, gradient) is broadcast so that all ranks take the same steps,
+        stop at the same evaluation and never meet in different collectives."""
+        if getattr(gp.engine, "world", 1) <= 1 and getattr(gp.engine, "kron_world", 1) <= 1:
+            return val, grad
+        import torch.distributed as tdist
+
+        if not (tdist.is_available() and tdist.is_initialized()) or tdist.get_world_size() == 1:
+            return val, grad
+        payload = [(float(val), np.asarray(grad, dtype=np.float64)) if tdist.get_rank() == 0 else None]
+        tdist.broadcast_object_list(payload, src=0)
+        return payload[0][0], payload[0][1].copy()
+
     def fun(x):
+        return lockstep(*fun_local(x))
+
+    def fun_local(x):
         fun.n_eval += 1
         point = unpack(x)
         spec = gp.spec_from_point(point)

@@ -163,3 +163,16 @@ def test_oracle_mll_gradient_against_central_differences():
               (g["noise_coreg"]["kappa"][0], ["noise_coreg", "kappa", 0])]
     for got, path in checks:
         assert got == pytest.approx(fd(bump(path)), rel=2e-6, abs=1e-7), path
+
+
+def test_blocked_oracle_of_the_full_size_gpu_tests_matches_the_plain_one():
+    """tests/test_gpu_fullsize.py assembles K by row blocks to bound host memory at N = 32768; same numbers as orc.factorize/conditional."""
+    from test_gpu_fullsize import oracle_subsample
+
+    spec, X, y, Xs = orc.synthetic_problem(350, 4, P=2, M_res=9, kind="Matern52")
+    ref = oracle_subsample(spec, X, y, Xs[:40], block=128)
+    L, v = orc.factorize(spec, X, y)
+    mu, var = orc.conditional(spec, X, L, v, Xs[:40], True)
+    np.testing.assert_allclose(ref["mu"], mu, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(ref["var"], var, rtol=1e-10, atol=1e-12)
+    assert ref["mll"] == pytest.approx(orc.mll(spec, X, y), rel=1e-12)

@@ -3,6 +3,7 @@
 // itself from the cuBLAS DGEMM figure on a full-wave problem, and how much do partial last waves cost on the recursion's shapes.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I gumbi_b200/csrc -o tools/micro_dgemm tools/micro_dgemm.cu
 #include "dgemm.cuh"
+#include <cmath>
 #include <cstdio>
 #include <vector>
 using namespace gb2;
@@ -44,6 +45,9 @@ int main() {
         // right-looking update of prediction rows appended below the factor (k = one 128-column panel per launch): the rate that
         // decides whether fusing the predict solve into the factorisation's trailing updates would pay
         {10112, 8192, 128}, {10112, 4096, 128}, {10112, 1024, 128}, {10112, 8192, 256}};
+    for (int tma : {1, 0}) {
+    g_dgemm_tma = tma;
+    printf("---- operand staging: %s\n", tma ? "TMA (cp.async.bulk.tensor.2d + mbarrier ring)" : "cp.async + __syncthreads (round 1)");
     for (auto s : shapes) {
         const double ms = run<128, 64, GM_SUB>(A, B, C, ld, s.r, s.c, s.k, 0, 10);
         const double ctas = (double)(s.r / 128) * (s.c / 64);
@@ -64,6 +68,24 @@ int main() {
         char name[64];
         snprintf(name, sizeof name, "SYRK lower  %d blocks, k=128", m);
         printf("%-34s %9.3f %9.2f %8.0f %8.2f\n", name, ms, (double)m * (m + 1) / 2 * 2.0 * 128 * 128 * 128 / ms / 1e9, ctas, ctas / slots);
+    }
+    }   // tma
+    {   // TMA-staged kernel against the cp.async kernel on the same product: same arithmetic, permuted summation order inside a k-tile
+        const int64_t r = 2048, c = 1024; const int k = 1024;
+        std::vector<double> ref((size_t)r * ld), got((size_t)r * ld);
+        double worst = 0, scale = 0;
+        for (int tma : {0, 1}) {
+            g_dgemm_tma = tma;
+            cudaMemset(C, 0, (size_t)r * ld * 8);
+            run<128, 64, GM_SUB>(A + 3 * 128 * ld + 256, B + 128 * ld + 512, C, ld, r, c, k, 0, 0);   // operands at an offset inside their allocations
+            run<64, 128, GM_SET>(A + 256, B + 5 * 128 * ld, C + 1024, ld, r, 128, 128, 0, 0);
+            cudaMemcpy((tma ? got : ref).data(), C, (size_t)r * ld * 8, cudaMemcpyDeviceToHost);
+        }
+        for (int64_t i = 0; i < r; i++)
+            for (int64_t j = 0; j < c + 128; j++) { worst = fmax(worst, fabs(got[i * ld + j] - ref[i * ld + j])); scale = fmax(scale, fabs(ref[i * ld + j])); }
+        printf("check TMA-staged vs cp.async-staged kernel: max |diff| %.3e at scale %.3e (k = %d: rounding-level, different summation order)\n", worst, scale, k);
+        g_dgemm_tma = 0;
+        cudaMemset(C, 0, (size_t)R * ld * 8);
     }
     // kernel variants on a full-wave shape and on the k = 128 update shape (same arithmetic, different staging / warp tiling):
     //   BK=32 x 2 stages: half the barriers per flop;  32x64 warp tiles, 4 warps per 64x128 CTA: 0.375 instead of 0.5 LDS per DMMA

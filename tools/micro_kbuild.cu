@@ -12,6 +12,7 @@
 #include "../gumbi_b200/csrc/kbuild_persist.cuh"
 
 using namespace gb2;
+static bool g_one = false;
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at line %d\n", cudaGetErrorString(e_), __LINE__); exit(1); } } while (0)
 
 __global__ void maxdiff_kernel(const double* A, const double* B, int64_t n, int64_t ld, double* out) {
@@ -24,6 +25,61 @@ __global__ void maxdiff_kernel(const double* A, const double* B, int64_t n, int6
         }
     for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(m));
+}
+
+// write-only ceilings: (a) plain streaming fill of the whole square, (b) the K-build's own store pattern (lower-triangle 64x64 tiles,
+// 8 warps x (8 rows x 64 B) per store instruction, persistent CTAs over strips) with the arithmetic removed
+__global__ void fill_kernel(double2* p, size_t n2) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) p[i] = make_double2(1.0, 2.0);
+}
+__global__ void __launch_bounds__(256) tile_fill_kernel(double* out, int64_t ld, int n_tiles, int strip, int* ctr) {
+    __shared__ int s_item;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const int r0 = (warp >> 1) * 16, c0 = (warp & 1) * 32;
+    const int ng = (n_tiles + strip - 1) / strip, full = ng - 1;
+    const int n_items = strip * (full * (full + 1) / 2) + (n_tiles - full * strip) * ng;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(ctr, 1);
+        __syncthreads();
+        const int w = s_item;
+        if (w >= n_items) break;
+        int q = (int)((sqrt(8.0 * (double)w / strip + 1.0) - 1.0) * 0.5);
+        while (strip * ((q + 1) * (q + 2) / 2) <= w) q++;
+        while (q > 0 && strip * (q * (q + 1) / 2) > w) q--;
+        const int rem = w - strip * (q * (q + 1) / 2);
+        const int bi = q * strip + rem / (q + 1), sidx = rem % (q + 1);
+        const int jt0 = sidx * strip;
+        int jt1 = jt0 + strip < n_tiles ? jt0 + strip : n_tiles;
+        if (jt1 > bi + 1) jt1 = bi + 1;
+        for (int jt = jt0; jt < jt1; jt++)
+            for (int mi = 0; mi < 2; mi++) {
+                double* dst = out + ((int64_t)bi * 64 + r0 + mi * 8 + g) * ld + (int64_t)jt * 64 + c0 + 2 * t4;
+                for (int ni = 0; ni < 4; ni++) *reinterpret_cast<double2*>(dst + ni * 8) = make_double2((double)w, (double)jt);
+            }
+    }
+    if (tid == 0) { __threadfence(); if (atomicAdd(ctr + 1, 1) == (int)gridDim.x - 1) { ctr[0] = 0; ctr[1] = 0; } }
+}
+
+static void write_ceilings(int64_t Np, int n_sm) {
+    double* d; int* ctr;
+    CK(cudaMalloc(&d, (size_t)Np * Np * 8)); CK(cudaMalloc(&ctr, 16)); CK(cudaMemset(ctr, 0, 16));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float ms;
+    const double sq = (double)Np * Np * 8, tri = 8.0 * Np * (Np + 64) / 2;
+    for (int it = 0; it < 2; it++) { CK(cudaEventRecord(e0)); CK(cudaMemsetAsync(d, 0, (size_t)Np * Np * 8)); CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize()); }
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    printf("write-only ceilings, %lld x %lld fp64: cudaMemset %.3f ms %.0f GB/s", (long long)Np, (long long)Np, ms, sq / ms / 1e6);
+    for (int it = 0; it < 2; it++) { CK(cudaEventRecord(e0)); fill_kernel<<<n_sm * 8, 256>>>((double2*)d, (size_t)Np * Np / 2); CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize()); }
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    printf(" | streaming STG.128 fill %.3f ms %.0f GB/s", ms, sq / ms / 1e6);
+    for (int occ : {2, 4, 8}) {
+        for (int it = 0; it < 2; it++) { CK(cudaEventRecord(e0)); tile_fill_kernel<<<n_sm * occ, 256>>>(d, Np, (int)(Np / 64), 8, ctr); CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize()); }
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        printf(" | K-build store pattern (lower tiles, %d CTAs/SM) %.3f ms %.0f GB/s", occ, ms, tri / ms / 1e6);
+    }
+    printf("\n");
+    cudaFree(d); cudaFree(ctr);
 }
 
 static long double ref_entry(int kind, const std::vector<double>& X, int D_in, int d, const double* ls, int64_t i, int64_t j) {
@@ -122,6 +178,10 @@ static void run_case(int64_t n, int d, int P, int n_sm) {
     KB4Args a{};
     a.Fi = dF; a.stride_i = Np; a.n_i = N; a.Fj = dF; a.stride_j = Np; a.n_j = N; a.Ci = dC; a.Cj = dC; a.Btab = dBtab; a.y = dy; a.out = dA; a.ld = Np;
     a.n_row_tiles = a.n_col_tiles = (int)(Np / KB_T); a.own_stride = 1; a.own_rank = 0; a.compact = 0; a.ctr = dCtr;
+    if (g_one) {   // profiling mode: the product configuration only
+        const float m4 = time_persist<KIND, KS, NCG, KB4_OCC>(kp, a, n_sm, 8, 3);
+        printf("   persistent strip 8 occ%d %.3f ms %.0f GB/s\n", KB4_OCC, m4, bytes / m4 / 1e6);
+    } else
     for (int strip : {4, 8, 16}) {
         const float m2 = time_persist<KIND, KS, NCG, 2>(kp, a, n_sm, strip, reps);
         const float m3 = time_persist<KIND, KS, NCG, 3>(kp, a, n_sm, strip, reps);
@@ -167,10 +227,13 @@ int main(int argc, char** argv) {
         for (int j = 0; j < KB4_TAB; j++) t2[j] = std::exp2((double)j / KB4_TAB);
         CK(cudaMemcpyToSymbol(g_exp2_tab2k, t2.data(), KB4_TAB * sizeof(double)));
     }
+    g_one = argc > 2;
     const int n_sm = prop.multiProcessorCount;
     printf("%s, %d SMs\n", prop.name, n_sm);
+    if (!g_one) write_ceilings(round_up(N + 1, TILE), n_sm);
     run_case<GB2_EXPQUAD, 2, 0>(N, 8, 1, n_sm);
     run_case<GB2_MATERN52, 2, 0>(N, 8, 1, n_sm);
+    if (g_one) return 0;
     run_case<GB2_EXPQUAD, 1, 1>(N / 2, 4, 2, n_sm);
     run_case<GB2_MATERN32, 2, 0>(N / 4, 5, 1, n_sm);
     run_case<GB2_EXPQUAD, 2, 0>(8192, 8, 1, n_sm);
