@@ -377,6 +377,24 @@ int gb2_create(gb2_handle** out, int device, int precision) {
     if ((e = cudaMemset(h->dKbCtr, 0, 4 * sizeof(int))) != cudaSuccess) return fail(e, "cudaMemset");
     if ((e = cudaFuncSetAttribute(mll_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 164 * 1024)) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
     if ((e = dgemm_nt_configure<128, 64, GM_SET>()) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
+    // GB2_OPTS="name=value,name=value": ablation switches applied to every handle of the process (measurement scripts); the
+    // same names as gb2_set_option
+    if (const char* env = getenv("GB2_OPTS")) {
+        std::string sopt(env);
+        size_t pos = 0;
+        while (pos < sopt.size()) {
+            size_t end = sopt.find(',', pos);
+            if (end == std::string::npos) end = sopt.size();
+            const std::string kv = sopt.substr(pos, end - pos);
+            const size_t eq = kv.find('=');
+            if (eq != std::string::npos && gb2_set_option(h, kv.substr(0, eq).c_str(), atoi(kv.c_str() + eq + 1)) != 0) {
+                g_create_err = "GB2_OPTS: " + h->err;
+                gb2_destroy(h);
+                return -1;
+            }
+            pos = end + 1;
+        }
+    }
     *out = h;
     return 0;
 }
