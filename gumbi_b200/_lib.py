@@ -57,7 +57,7 @@ class Kernel(C.Structure):
 
 EXPORTS = [
     "gb2_abi_version", "gb2_create", "gb2_destroy", "gb2_last_error", "gb2_set_train", "gb2_set_train_dev",
-    "gb2_set_kernel", "gb2_factorize", "gb2_mll", "gb2_mll_grad", "gb2_get_alpha", "gb2_predict", "gb2_predict_dev", "gb2_predict_full", "gb2_factorize_predict", "gb2_factorize_predict_dev", "gb2_get_K", "gb2_get_L",
+    "gb2_set_kernel", "gb2_factorize", "gb2_mll", "gb2_mll_grad", "gb2_get_alpha", "gb2_predict", "gb2_predict_dev", "gb2_predict_full", "gb2_fitc_factorize", "gb2_fitc_mll", "gb2_fitc_predict", "gb2_factorize_predict", "gb2_factorize_predict_dev", "gb2_get_K", "gb2_get_L",
     "gb2_get_v", "gb2_get_trace", "gb2_get_timings", "gb2_set_option", "gb2_mark", "gb2_elapsed_ms",
     "gb2_nccl_unique_id", "gb2_dist_init", "gb2_dist_finalize", "gb2_dist_allgather_dev",
 ]
@@ -101,6 +101,9 @@ def load():
     lib.gb2_predict_full.argtypes = [H, dp, C.c_int64, C.c_int32, dp, dp]
     lib.gb2_predict_dev.argtypes = [H, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
     lib.gb2_factorize_predict_dev.argtypes = [H, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.gb2_fitc_factorize.argtypes = [H, dp, C.c_int64]
+    lib.gb2_fitc_mll.argtypes = [H, dp]
+    lib.gb2_fitc_predict.argtypes = [H, dp, C.c_int64, C.c_int32, dp, dp]
     lib.gb2_get_K.argtypes = [H, dp]
     lib.gb2_get_L.argtypes = [H, dp]
     lib.gb2_get_v.argtypes = [H, dp]

@@ -2,7 +2,8 @@
 
 Host-side mirror of ``gumbi.regression.pymc.GP.PymcGP`` (gumbi/regression/pymc/GP.py:21-979) for the hot path only:
 ``fit`` (:255-387), ``build_model`` (:468-583), ``_construct_kernels`` (:652-757), ``find_MAP`` (:799-813) and
-``predict`` (:837-849) keep their names, arguments, ``MAP`` keys and error behaviour, but no PyMC model is built: the
+``predict`` (:837-849) keep their names, arguments, ``MAP`` keys and error behaviour (``sparse=True`` selects the FITC
+approximation of :571-578 on the device, ``gb2_fitc_*``), but no PyMC model is built: the
 kernel composition is lowered to the plain ``spec`` dict of ``gumbi_b200._lib.make_kernel_struct`` and everything
 O(N^2) and up happens behind the C ABI on the GPU.  There is no CPU fallback.
 
@@ -84,8 +85,8 @@ class B200Backend:
                     heteroskedastic_outputs=True, sparse=False, n_u=100, ARD=True, ls_bounds=None, mass=0.98):
         if heteroskedastic_inputs:
             raise NotImplementedError("Heteroskedasticity over inputs is not yet implemented.")
-        if sparse:
-            raise NotImplementedError("The B200 backend implements the exact (dense) GP only; sparse=True is out of scope.")
+        if sparse and (self.distributed or self.precision != "fp64"):
+            raise NotImplementedError("sparse=True (FITC) runs on one GPU in fp64")
         kernels = CONTINUOUS_KERNELS + ["Periodic"]
         kernels += [k + "+Periodic" for k in kernels if k != "Periodic"]          # GP.py:664-674
         assert_in("Continuous kernel", continuous_kernel, kernels)
@@ -120,7 +121,17 @@ class B200Backend:
         self._y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
         self._layout = self._model_layout()
         self._layout["warp"] = self._periodic_warp(continuous_kernel, period)
-        want_kron = self._wants_kron()
+        self._Xu = None
+        if sparse:
+            # GP.py:571-578: k-means inducing points over the full shaped X, MarginalSparse(approx="FITC") with the scalar sigma
+            import warnings
+
+            from .sparse import kmeans_inducing_points
+
+            if heteroskedastic_outputs and self._layout["multi"]:
+                warnings.warn("Heteroskedasticity over outputs is not yet implemented for sparse GP. Reverting to scalar-valued noise.")
+            self._Xu = kmeans_inducing_points(n_u, self._X, seed=seed)
+        want_kron = (not sparse) and self._wants_kron()
         if self.engine is not None and want_kron != (type(self.engine).__name__ == "KronEngine"):
             self.engine.close()      # the structure changed between two build_model calls
             self.engine = None
@@ -283,10 +294,10 @@ class B200Backend:
                     t["coreg"].append(out_cg)
                 terms.append(t)
         noise_cg = None
-        if self.heteroskedastic_outputs and multi:
+        if self.heteroskedastic_outputs and multi and not self.sparse:   # sparse: scalar sigma (GP.py:573-578)
             noise_cg = ("Output_noise", idxs["p"], out_cg[2])
         return {"terms": terms, "noise_coreg": noise_cg, "idx_s": idxs["s"], "idx_l": idxs["l"], "n_s": ns["s"],
-                "n_l": ns["l"]}
+                "n_l": ns["l"], "multi": multi}
 
     def param_shapes(self):
         """Names and shapes of the free hyper-parameters, in the order PyMC would register them."""
@@ -388,7 +399,10 @@ class B200Backend:
         key = self._map_key()
         if self._factor_key != key:
             self.engine.set_kernel(self.spec_from_point(self.MAP))
-            self.engine.factorize()
+            if self.sparse:
+                self.engine.fitc_factorize(self._engine_points(self._Xu))
+            else:
+                self.engine.factorize()
             self._factor_key = key
 
     def _map_key(self):
@@ -405,6 +419,8 @@ class B200Backend:
             raise TypeError(f"unsupported predict arguments for the B200 backend: {sorted(kwargs)}")
         self._ensure_factorized()
         points_array = np.atleast_2d(np.asarray(points_array, dtype=np.float64))
+        if self.sparse:
+            return self.engine.fitc_predict(self._engine_points(points_array), pred_noise=bool(with_noise))
         if getattr(self.engine, "world", 1) > 1 and not getattr(self.engine, "shard_storage", False):
             # every rank holds the factor: each serves a contiguous slice of the points, slices are gathered on all ranks
             from . import dist as gdist
@@ -435,6 +451,8 @@ class B200Backend:
     # -- conditional / posterior samples (GP.py:861-979) ------------------------------------------------------------
     def conditional(self, points_array, pred_noise=False):
         """Mean and full covariance of ``gp_dict["total"].conditional(var_name, points_array)`` (GP.py:913-914), on device."""
+        if self.sparse:
+            raise NotImplementedError("full-covariance conditionals of the sparse (FITC) model are not implemented")
         self._ensure_factorized()
         points_array = np.atleast_2d(np.asarray(points_array, dtype=np.float64))
         return self.engine.predict_full(self._engine_points(points_array), pred_noise=bool(pred_noise))
@@ -492,7 +510,7 @@ class B200Backend:
         ``fused=True``: one pass through ``gb2_factorize_predict`` (prediction points carried through the factorisation as extra
         rows of the factor) instead of factorise-then-solve; single GPU, fp64, dense solver only."""
         self._factor_key = None
-        if not fused:
+        if not fused or self.sparse:
             return self.predict(points_array, with_noise=with_noise)
         if self.MAP is None:
             raise RuntimeError("predict called before find_MAP/fit")
@@ -508,11 +526,14 @@ class B200Backend:
         """log p(y | X, theta) of ``gp.marginal_likelihood("ml", ...)`` (GP.py:580) at ``point`` (default: MAP)."""
         if point is not None:
             self.engine.set_kernel(self.spec_from_point(self._complete_point(point)))
-            self.engine.factorize()
+            if self.sparse:
+                self.engine.fitc_factorize(self._engine_points(self._Xu))
+            else:
+                self.engine.factorize()
             self._factor_key = None
         else:
             self._ensure_factorized()
-        return self.engine.mll()
+        return self.engine.fitc_mll() if self.sparse else self.engine.mll()
 
 
 class ArrayRegressor:

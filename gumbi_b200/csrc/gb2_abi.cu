@@ -3,6 +3,7 @@
 #include "predict.cuh"
 #include "mllgrad.cuh"
 #include "kbuild_persist.cuh"
+#include "fitc.cuh"
 
 #include <dlfcn.h>
 
@@ -41,7 +42,7 @@ int set_train_common(gb2_handle* h, const double* X, int64_t N, int32_t D_in, co
     GB2_CUDA(h, cudaMemcpyAsync(h->dy, y, (size_t)N * sizeof(double), kind, h->s_main));
     GB2_CUDA(h, cudaStreamSynchronize(h->s_main));
     h->N = N; h->Np = Np; h->D_in = D_in;
-    h->have_train = true; h->factorized = false;
+    h->have_train = true; h->factorized = false; h->fitc_ready = false;
     return 0;
 }
 
@@ -415,6 +416,10 @@ int gb2_destroy(gb2_handle* h) {
     for (auto ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto ev : h->ev_pool) cudaEventDestroy(ev);
     for (auto ev : h->ev_mark) if (ev) cudaEventDestroy(ev);
+    if (h->fitc_u) gb2_destroy(h->fitc_u);
+    if (h->fitc_b) gb2_destroy(h->fitc_b);
+    cudaSetDevice(h->device);
+    cudaFree(h->dFitc); cudaFree(h->dSt); cudaFree(h->dFitcScal);
     if (h->dTrace) cudaFree(h->dTrace);
     if (h->s_diag) cudaStreamDestroy(h->s_diag);
     if (h->s_bulk2) cudaStreamDestroy(h->s_bulk2);
@@ -514,7 +519,23 @@ int gb2_set_kernel(gb2_handle* h, const gb2_kernel* k) {
     h->kp = kp; h->pp = pp;
     for (int t = 0; t < k->n_terms; t++) h->eta_host[t] = k->terms[t].eta;
     h->sigma_host = k->sigma;
-    h->have_kernel = true; h->factorized = false;
+    {   // deep copy of the description (the caller's Coregion tables need not outlive this call): the FITC inner systems re-use it
+        h->kernel_host = *k;
+        size_t total = 0;
+        for (int t = 0; t < k->n_terms; t++)
+            for (int c = 0; c < k->terms[t].n_coreg; c++) total += (size_t)k->terms[t].coreg_P[c] * k->terms[t].coreg_P[c];
+        h->kernel_Bstore.assign(total, 0.0);
+        size_t off = 0;
+        for (int t = 0; t < k->n_terms; t++)
+            for (int c = 0; c < k->terms[t].n_coreg; c++) {
+                const size_t n = (size_t)k->terms[t].coreg_P[c] * k->terms[t].coreg_P[c];
+                std::copy(k->terms[t].coreg_B[c], k->terms[t].coreg_B[c] + n, h->kernel_Bstore.begin() + off);
+                h->kernel_host.terms[t].coreg_B[c] = h->kernel_Bstore.data() + off;
+                off += n;
+            }
+        h->kernel_host.noise_B = nullptr;    // only consulted through noise_col (FITC refuses a noise Coregion)
+    }
+    h->have_kernel = true; h->factorized = false; h->fitc_ready = false;
     return 0;
 }
 
@@ -764,7 +785,9 @@ static int build_K(gb2_handle* h, int& launches) {
 }
 
 // Prediction points of a fused cold predict (gb2_factorize_predict); M == 0: plain factorisation.
-struct ExtPredict { const double* Xs = nullptr; int64_t M = 0; int32_t pred_noise = 0; double* mean = nullptr; double* var = nullptr; bool dev = false; };
+struct ExtPredict { const double* Xs = nullptr; int64_t M = 0; int32_t pred_noise = 0; double* mean = nullptr; double* var = nullptr; bool dev = false;
+                    // fill: called after the K-build to overwrite the matrix that gets factorised (FITC B system)
+                    int (*fill)(gb2_handle*, void*) = nullptr; void* fill_arg = nullptr; };
 
 static int factorize_impl(gb2_handle* h, const ExtPredict& x) {
     GB2_ARG(h, h->have_train, "gb2_factorize: no training data (call gb2_set_train)");
@@ -774,6 +797,7 @@ static int factorize_impl(gb2_handle* h, const ExtPredict& x) {
     h->L_split_valid = false;
     int launches = 0, rc;
     if ((rc = build_K(h, launches))) return rc;
+    if (x.fill && (rc = x.fill(h, x.fill_arg))) return rc;
     const int64_t Np = h->Np, N = h->N, Mp = round_up(x.M, TILE);
     cudaStream_t s = h->s_main;
     if (x.M > 0) {
@@ -988,6 +1012,124 @@ int gb2_predict_full(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_no
     GB2_CUDA(h, cudaMemcpyAsync(&bad, h->dInfo + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
     GB2_CUDA(h, cudaStreamSynchronize(s));
     GB2_ARG(h, bad == 0, "a Coregion column of Xs holds a level index outside [0, P)");
+    return 0;
+}
+
+// ---- sparse FITC approximation (fitc.cuh) -------------------------------------------------------------------------------------
+static int fitc_fill_B(gb2_handle* hb, void* arg) {
+    gb2_handle* h = static_cast<gb2_handle*>(arg);
+    const int64_t Npb = hb->Np, Nk = round_up(h->N, TILE);
+    cudaStream_t s = hb->s_main;
+    // [B - I, b ; b^T, .] = S S^T over the training points (lower tiles), in the augmented layout the Cholesky expects
+    dgemm_nt_launch<128, 64, GM_SET>(s, h->dSt, Nk, h->dSt, Nk, hb->dA, Npb, Npb, Npb, (int)Nk, /*lower*/ 1, 0, 0);
+    fitc_fix_diag_kernel<<<(unsigned)((Npb + 255) / 256), 256, 0, s>>>(hb->dA, Npb, h->fitc_m, Npb);
+    GB2_CUDA(hb, cudaGetLastError());
+    return 0;
+}
+
+static int fitc_inner(gb2_handle* h, gb2_handle*& inner) {
+    if (inner) return 0;
+    if (gb2_create(&inner, h->device, GB2_FP64) != 0) { h->err = "FITC: " + g_create_err; inner = nullptr; return -1; }
+    return 0;
+}
+
+// Factorise the FITC approximation for the training set / kernel of `h` with inducing points Xu (m x D_in, host).
+// Returns 0, > 0 (the inducing system Kuu + jitter I is not positive definite: first failing pivot) or < 0 (error).
+// Replaces MarginalApprox.marginal_likelihood(X, Xu, y, sigma) as built at gumbi/regression/pymc/GP.py:571-578.
+int gb2_fitc_factorize(gb2_handle* h, const double* Xu, int64_t m) {
+    if (!h) return -1;
+    GB2_ARG(h, Xu, "Xu is null");
+    GB2_ARG(h, h->have_train && h->have_kernel, "gb2_fitc_factorize needs training data and a kernel");
+    GB2_ARG(h, h->world == 1, "the FITC approximation is single-GPU");
+    GB2_ARG(h, h->kernel_host.noise_col < 0, "the FITC approximation takes a scalar noise sigma (GP.py:573-577): no noise Coregion");
+    GB2_ARG(h, m >= 1 && m <= 16384, "the number of inducing points must be in [1, 16384]");
+    const int64_t N = h->N, Npu = round_up(m + 1, TILE), Nk = round_up(N, TILE);
+    GB2_ARG(h, Nk * Npu * (int64_t)sizeof(double) <= ((int64_t)8 << 30), "N x n_u too large for one FITC pass (K(X,Xu) Luu^-T must fit in 8 GiB)");
+    h->fitc_ready = false;
+    int rc;
+    if ((rc = fitc_inner(h, h->fitc_u)) || (rc = fitc_inner(h, h->fitc_b))) return rc;
+    gb2_handle *hu = h->fitc_u, *hb = h->fitc_b;
+    auto inner_fail = [&](gb2_handle* in, const char* what, int code) { h->err = std::string("FITC ") + what + ": " + in->err; return code; };
+    std::vector<double> zeros((size_t)m, 0.0);
+    gb2_kernel ku = h->kernel_host;
+    ku.noise_col = -1; ku.noise_P = 0;
+    ku.sigma = 0.0;                      // stabilize(Kuu): jitter only
+    if ((rc = gb2_set_train(hu, Xu, m, h->D_in, zeros.data()))) return inner_fail(hu, "inducing system", rc);
+    if ((rc = gb2_set_kernel(hu, &ku))) return inner_fail(hu, "inducing system", rc);
+    if ((rc = gb2_factorize(hu))) return inner_fail(hu, "inducing system (Kuu + jitter I)", rc);
+    GB2_CUDA(h, cudaSetDevice(h->device));
+    if ((rc = ensure(h, h->dFitc, h->fitc_cap, 3 * Nk))) return rc;
+    if ((rc = ensure(h, h->dSt, h->St_cap, Npu * Nk))) return rc;
+    if (!h->dFitcScal) GB2_CUDA(h, cudaMalloc(&h->dFitcScal, 2 * sizeof(double)));
+    double* dLam = h->dFitc; double* dTmp = h->dFitc + Nk; double* dVar1 = h->dFitc + 2 * Nk;
+    // A^T = K(X,Xu) Luu^-T  (rows = training points) and diag(Kff) - colsum(A*A): an exact-GP prediction of the inducing system at X
+    if ((rc = predict_common(hu, h->dX, N, 0, dTmp, dVar1, true))) return inner_fail(hu, "K(X,Xu) solve", rc);
+    cudaStream_t s = hu->s_main;
+    const double sigma2 = h->kernel_host.sigma * h->kernel_host.sigma;
+    fitc_lambda_kernel<<<1, 1024, 0, s>>>(dVar1, h->dy, N, sigma2, dLam, h->dFitcScal);
+    fitc_scale_transpose_kernel<<<dim3((unsigned)(Nk / 32), (unsigned)(Npu / 32)), 256, 0, s>>>(hu->dAt, Npu, dLam, h->dy, N, m, h->dSt, Nk);
+    GB2_CUDA(h, cudaGetLastError());
+    GB2_CUDA(h, cudaStreamSynchronize(s));
+    // B system: same shape as the inducing system; its K-build only sizes the buffers, fitc_fill_B overwrites the matrix
+    h->fitc_m = m;
+    if ((rc = gb2_set_train(hb, Xu, m, h->D_in, zeros.data()))) return inner_fail(hb, "B system", rc);
+    if ((rc = gb2_set_kernel(hb, &ku))) return inner_fail(hb, "B system", rc);
+    ExtPredict x;
+    x.fill = fitc_fill_B; x.fill_arg = h;
+    if ((rc = factorize_impl(hb, x))) return inner_fail(hb, "B system (I + A Lambda^-1 A^T)", rc);
+    h->fitc_ready = true;
+    return 0;
+}
+
+// logp of MarginalApprox(approx="FITC").marginal_likelihood at the current kernel (needs gb2_fitc_factorize).
+int gb2_fitc_mll(gb2_handle* h, double* out) {
+    if (!h) return -1;
+    GB2_ARG(h, out, "out is null");
+    GB2_ARG(h, h->fitc_ready, "gb2_fitc_mll called before a successful gb2_fitc_factorize");
+    GB2_CUDA(h, cudaSetDevice(h->device));
+    double sc[2], fs[2];
+    GB2_CUDA(h, cudaMemcpy(sc, h->fitc_b->dScal, 2 * sizeof(double), cudaMemcpyDeviceToHost));    // sum log diag(L_B), c^T c
+    GB2_CUDA(h, cudaMemcpy(fs, h->dFitcScal, 2 * sizeof(double), cudaMemcpyDeviceToHost));        // sum log Lambda, y^T Lambda^-1 y
+    *out = -0.5 * (double)h->N * 1.8378770664093454836 - 0.5 * fs[0] - sc[0] - 0.5 * (fs[1] - sc[1]);
+    return 0;
+}
+
+// Posterior mean / variance of the FITC conditional (MarginalApprox._build_conditional, diag=True) at M host points.
+int gb2_fitc_predict(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_noise, double* mean, double* var) {
+    if (!h) return -1;
+    GB2_ARG(h, h->fitc_ready, "gb2_fitc_predict called before a successful gb2_fitc_factorize");
+    GB2_ARG(h, Xs && mean && var, "null pointer");
+    GB2_ARG(h, M >= 0, "M must be >= 0");
+    if (M == 0) return 0;
+    GB2_CUDA(h, cudaSetDevice(h->device));
+    gb2_handle *hu = h->fitc_u, *hb = h->fitc_b;
+    const int64_t m = h->fitc_m, Npu = hu->Np;
+    const int ncols_b = (int)((m + TILE - 1) / TILE);
+    const int64_t chunk = std::min<int64_t>(round_up(M, TILE), std::max<int64_t>(TILE, ((int64_t)4 << 30) / (Npu * (int64_t)sizeof(double)) / TILE * TILE));
+    int rc;
+    if ((rc = ensure(h, h->dXs, h->Xs_cap, M * h->D_in))) return rc;
+    int64_t oc = h->out_cap;
+    if ((rc = ensure(h, h->dMean, oc, M))) return rc;
+    if ((rc = ensure(h, h->dVar, h->out_cap, M))) return rc;
+    if ((rc = ensure(h, h->dFitc, h->fitc_cap, std::max<int64_t>(3 * round_up(h->N, TILE), 3 * chunk)))) return rc;   // Lambda is no longer needed
+    cudaStream_t s = hu->s_main;
+    GB2_CUDA(h, cudaMemcpyAsync(h->dXs, Xs, (size_t)M * h->D_in * sizeof(double), cudaMemcpyHostToDevice, s));
+    GB2_CUDA(h, cudaStreamSynchronize(s));
+    const double add = pred_noise ? h->kernel_host.sigma * h->kernel_host.sigma : 0.0;
+    double* dTmp = h->dFitc; double* dVar1 = h->dFitc + chunk;
+    int launches = 0;
+    for (int64_t m0 = 0; m0 < M; m0 += chunk) {
+        const int64_t Mc = std::min(chunk, M - m0), Mp = round_up(Mc, TILE);
+        // As^T = K(X*,Xu) Luu^-T in the inducing system's solve panel, var1 = kss - colsum(As*As)
+        if ((rc = predict_common(hu, h->dXs + m0 * h->D_in, Mc, 0, dTmp, dVar1, true))) { h->err = "FITC K(X*,Xu) solve: " + hu->err; return rc; }
+        mask_columns_kernel<<<(unsigned)((Mp + 255) / 256), 256, 0, s>>>(hu->dAt, Npu, Mp, m, Npu);
+        trsm_rec(s, hb->dA, Npu, hb->dDinv, hu->dAt, Npu, Mp, 0, ncols_b, launches);      // C^T = As^T L_B^-T
+        fitc_reduce_kernel<<<(unsigned)((Mc + 7) / 8), 256, 0, s>>>(hu->dAt, Npu, hb->dA + m * Npu, m, Mc, dVar1, add, h->dMean + m0, h->dVar + m0);
+        GB2_CUDA(h, cudaGetLastError());
+    }
+    GB2_CUDA(h, cudaMemcpyAsync(mean, h->dMean, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, s));
+    GB2_CUDA(h, cudaMemcpyAsync(var, h->dVar, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, s));
+    GB2_CUDA(h, cudaStreamSynchronize(s));
     return 0;
 }
 

@@ -160,6 +160,16 @@ struct gb2_handle {
     cudaStream_t s_aux[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
 
+    // sparse FITC approximation (gb2_fitc_*, fitc.cuh): the inducing-point system and the m x m B system are two inner single-GPU
+    // fp64 handles; kernel_host = the description last given to gb2_set_kernel (the inner systems get copies with sigma = 0)
+    gb2_handle* fitc_u = nullptr; gb2_handle* fitc_b = nullptr;
+    gb2_kernel kernel_host{};
+    std::vector<double> kernel_Bstore;
+    double* dFitc = nullptr; int64_t fitc_cap = 0;    // [Lambda | scratch mean | scratch var], 3 x max(Np, Mp)
+    double* dSt = nullptr; int64_t St_cap = 0;        // S = [A Lambda^-1/2 ; y^T Lambda^-1/2], (round_up(m+1,128) x round_up(N,128))
+    double* dFitcScal = nullptr;                      // [0] sum log Lambda, [1] y^T Lambda^-1 y
+    int64_t fitc_m = 0; bool fitc_ready = false;
+
     // timing
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_panel[2] = {nullptr, nullptr}, ev_col[2] = {nullptr, nullptr};

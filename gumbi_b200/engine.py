@@ -204,6 +204,33 @@ class GPEngine:
         self._check(self._lib.gb2_predict_full(self._h, _lib.as_dp(Xs), M, int(bool(pred_noise)), _lib.as_dp(mean), _lib.as_dp(cov)), "predict_full")
         return mean, cov
 
+    # -- sparse FITC approximation (gb2_fitc_*; pm.gp.MarginalSparse(approx="FITC"), GP.py:571-578) ------------------------
+    def fitc_factorize(self, Xu):
+        """Factorise the FITC approximation with inducing points ``Xu`` (m, D_in) for the current training set and kernel."""
+        Xu = _c_f64(np.atleast_2d(Xu), 2)
+        if Xu.shape[1] != self.D_in:
+            raise ValueError(f"Xu has {Xu.shape[1]} columns, model has {self.D_in} dims")
+        if not np.all(np.isfinite(Xu)):
+            raise ValueError("Xu must be finite")
+        self._check(self._lib.gb2_fitc_factorize(self._h, _lib.as_dp(Xu), Xu.shape[0]), "fitc_factorize")
+
+    def fitc_mll(self) -> float:
+        out = C.c_double(0.0)
+        self._check(self._lib.gb2_fitc_mll(self._h, C.byref(out)), "fitc_mll")
+        return float(out.value)
+
+    def fitc_predict(self, Xs, pred_noise: bool = True):
+        Xs = _c_f64(np.atleast_2d(Xs), 2)
+        if Xs.shape[1] != self.D_in:
+            raise ValueError(f"points_array has {Xs.shape[1]} columns, model has {self.D_in} dims")
+        if not np.all(np.isfinite(Xs)):
+            raise ValueError("points_array must be finite")
+        M = Xs.shape[0]
+        mean = np.empty(M, dtype=np.float64)
+        var = np.empty(M, dtype=np.float64)
+        self._check(self._lib.gb2_fitc_predict(self._h, _lib.as_dp(Xs), M, int(bool(pred_noise)), _lib.as_dp(mean), _lib.as_dp(var)), "fitc_predict")
+        return mean, var
+
     def predict_device(self, dXs_ptr: int, M: int, pred_noise: bool, dmean_ptr: int, dvar_ptr: int):
         self._check(
             self._lib.gb2_predict_dev(self._h, C.c_void_p(dXs_ptr), int(M), int(bool(pred_noise)), C.c_void_p(dmean_ptr), C.c_void_p(dvar_ptr)),

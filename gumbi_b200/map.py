@@ -296,7 +296,40 @@ def make_objective(gp, start=None):
     def fun(x):
         return lockstep(*fun_local(x))
 
+    def fitc_value(xv):
+        gp.engine.set_kernel(gp.spec_from_point(unpack(xv)))
+        gp.engine.fitc_factorize(gp._engine_points(gp._Xu))
+        return gp.engine.fitc_mll()
+
+    def fun_sparse(x):
+        """sparse=True: the FITC marginal likelihood (gb2_fitc_mll) with a central-difference gradient in the optimiser's own
+        (log-transformed) coordinates -- 2 p + 1 device factorisations of the n_u x n_u systems per evaluation, each O(N n_u^2).
+        (PyMC differentiates the same logp by reverse mode; the step 1e-5 keeps the gradient error ~1e-8 relative.)"""
+        fun.n_eval += 1
+        point = unpack(x)
+        try:
+            val = fitc_value(x)
+            gx = np.zeros_like(x)
+            h = 1e-5
+            for k in range(len(x)):
+                xp = x.copy(); xp[k] += h
+                xm = x.copy(); xm[k] -= h
+                gx[k] = (fitc_value(xp) - fitc_value(xm)) / (2 * h)
+        except (np.linalg.LinAlgError, FloatingPointError):
+            return 1e100, np.zeros_like(x)
+        grad = gx
+        for i, n in enumerate(names):
+            xv = np.asarray(point[n], dtype=np.float64).reshape(-1)
+            val += float(pri[n][0](np.asarray(point[n], dtype=np.float64)))
+            gi = np.asarray(pri[n][1](xv), dtype=np.float64).reshape(-1)
+            grad[offs[i]:offs[i + 1]] += gi * xv if positive[i] else gi
+        if not np.isfinite(val):
+            return 1e100, np.zeros_like(x)
+        return -val, -grad
+
     def fun_local(x):
+        if getattr(gp, "sparse", False):
+            return fun_sparse(x)
         fun.n_eval += 1
         point = unpack(x)
         spec = gp.spec_from_point(point)

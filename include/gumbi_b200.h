@@ -141,6 +141,17 @@ int gb2_factorize_predict_dev(gb2_handle* h, const double* dXs, int64_t M, int32
  * (GP.py:861-979; pm.gp.Marginal.conditional, diag=False).  M <= 32768.                                                */
 int gb2_predict_full(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_noise, double* mean, double* cov);
 
+/* Sparse FITC approximation.  Replaces pm.gp.MarginalSparse(approx="FITC") as gumbi builds it for sparse=True:
+ * gp.marginal_likelihood("ml", X=X, Xu=Xu, y=y, sigma=sigma) (gumbi/regression/pymc/GP.py:571-578, :589-591) and the
+ * MarginalApprox conditional behind predict (GP.py:845-847).  Xu:(m,D_in) host, row-major = the inducing points
+ * (pm.gp.util.kmeans_inducing_points, GP.py:572; computed by the caller).  Uses the training set of gb2_set_train and the
+ * kernel of gb2_set_kernel with its scalar sigma (a noise Coregion is refused: the reference reverts to the scalar sigma for
+ * sparse models, GP.py:573-577).  fp64, single GPU, round_up(N,128) * round_up(m+1,128) * 8 bytes <= 8 GiB.
+ * gb2_fitc_factorize returns 0, > 0 (Kuu + jitter I not positive definite: first failing pivot) or < 0 (error).             */
+int gb2_fitc_factorize(gb2_handle* h, const double* Xu, int64_t m);
+int gb2_fitc_mll(gb2_handle* h, double* out);
+int gb2_fitc_predict(gb2_handle* h, const double* Xs, int64_t M, int32_t pred_noise, double* mean, double* var);
+
 /* Test hooks: copy the dense objects back (row-major, n x n with n = N).  The strict upper
  * triangle is returned as zero for L and mirrored for K.                                        */
 int gb2_get_K(gb2_handle* h, double* K_out);   /* rebuilds K+Knoise+jitter into scratch; O(N^2)  */

@@ -39,6 +39,17 @@ class OracleEngine:
 
         return solve_triangular(self.L, self.v, lower=True, trans="T")
 
+    def fitc_factorize(self, Xu):
+        self.Xu = np.asarray(Xu, dtype=np.float64)
+        orc.fitc_factorize(self.spec, self.X, self.y, self.Xu)   # raises LinAlgError like the device path
+        self.n_fitc = getattr(self, "n_fitc", 0) + 1
+
+    def fitc_mll(self):
+        return orc.fitc_mll(self.spec, self.X, self.y, self.Xu)
+
+    def fitc_predict(self, Xs, pred_noise=True):
+        return orc.fitc_predict(self.spec, self.X, self.y, self.Xu, Xs, pred_noise)
+
     def set_option(self, name, value):
         pass
 
@@ -119,8 +130,10 @@ def test_error_behaviour_mirrors_pymcgp():
         gp.build_model(heteroskedastic_inputs=True)  # GP.py:518-519
     with pytest.raises(ValueError, match="Continuous kernel must be one of"):
         gp.build_model(continuous_kernel="RatQuad")  # assert_in, GP.py:674
-    with pytest.raises(NotImplementedError):
-        gp.build_model(sparse=True)
+    gp.precision = "tf32"
+    with pytest.raises(NotImplementedError, match="FITC"):
+        gp.build_model(sparse=True)          # the sparse path is fp64, single GPU
+    gp.precision = "fp64"
     with pytest.raises(AssertionError):
         HostGP(g["X"], g["y"], m["continuous_dims"]).find_MAP()  # GP.py:808 `assert self.model is not None`
     gp.build_model()
@@ -383,7 +396,9 @@ def test_inference_modes_left_to_pymc_raise():
         gp.build_latent()
     with pytest.raises(NotImplementedError):
         gp.sample(100)
-    with pytest.raises(NotImplementedError):
-        gp.build_model(sparse=True)
+    gp.precision = "tf32"
+    with pytest.raises(NotImplementedError, match="FITC"):
+        gp.build_model(sparse=True)          # the sparse path is fp64, single GPU
+    gp.precision = "fp64"
     with pytest.raises(NotImplementedError):
         gp.build_model(heteroskedastic_inputs=True)
