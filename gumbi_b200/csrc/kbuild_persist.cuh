@@ -59,9 +59,13 @@ __device__ __forceinline__ double kb4_exp(double z, const double* __restrict__ t
     const double m = rr * q2;                                // exp(-zs rr) - 1
     const double T = tab[n & (KB4_TAB - 1)];
     const double res = fma(T, m, T);
-    // 2^(n >> 11) by exponent arithmetic; below 2^-1000 the result is flushed to an exact 0 (integer pipe: compare + 2 selects)
+    // 2^(n >> 11) by exponent arithmetic.  Arguments with zs z >= 693 (exp < 2^-1000 ~ 1e-301) return an exact 0: decided on the HIGH
+    // WORD OF z (integer pipe; z >= 0 orders like its bit pattern, a rounding-negative z has the sign bit set and compares below),
+    // because for huge scaled distances (z > ~1e6) the low word of t -- n -- wraps around and must not be consulted.  A result whose
+    // exponent field would underflow (tiny eta^2 on top of a tiny exp) is flushed to 0 as well.
+    constexpr int HI_ZMAX = ZS2 == 1 ? 0x4095A800 /* 1386.0 */ : 0x4085A800 /* 693.0 */;
     const int hi = __double2hiint(res) + ((n >> 11) << 20);
-    const bool tiny = n < -1000 * KB4_TAB;
+    const bool tiny = __double2hiint(z) >= HI_ZMAX || hi < 0x00100000;
     return __hiloint2double(tiny ? 0 : hi, tiny ? 0 : __double2loint(res));
 }
 

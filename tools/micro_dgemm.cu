@@ -87,6 +87,52 @@ int main() {
         g_dgemm_tma = 0;
         cudaMemset(C, 0, (size_t)R * ld * 8);
     }
+    {   // the PERSISTENT path of the TMA kernel (more tiles than CTA slots: cross-tile prefetch), repeated to expose races; the test
+        // data are multiples of 2^-16, so every product and partial sum is exact and the two kernels must agree bit for bit
+        struct PS { int64_t r, c; int k; int lower; } ps[] = {{8192, 4096, 512, 0}, {16384, 2048, 128, 0}, {8192, 8192, 128, 1}, {4096, 4096, 2048, 0}};
+        std::vector<double> ref, got;
+        for (auto q : ps) {
+            ref.assign((size_t)q.r * ld, 0.0); got.assign((size_t)q.r * ld, 0.0);
+            g_dgemm_tma = 0;
+            cudaMemset(C, 0, (size_t)q.r * ld * 8);
+            run<128, 64, GM_SUB>(A + 128 * ld + 256, B + 256 * ld + 512, C, ld, q.r, q.c, q.k, q.lower, 0);
+            cudaMemcpy(ref.data(), C, (size_t)q.r * ld * 8, cudaMemcpyDeviceToHost);
+            size_t bad_total = 0;
+            for (int rep = 0; rep < 5; rep++) {
+                g_dgemm_tma = 1;
+                cudaMemset(C, 0, (size_t)q.r * ld * 8);
+                run<128, 64, GM_SUB>(A + 128 * ld + 256, B + 256 * ld + 512, C, ld, q.r, q.c, q.k, q.lower, 0);
+                cudaMemcpy(got.data(), C, (size_t)q.r * ld * 8, cudaMemcpyDeviceToHost);
+                size_t bad = 0;
+                for (int64_t i = 0; i < q.r; i++)
+                    for (int64_t j = 0; j < q.c; j++) bad += got[i * ld + j] != ref[i * ld + j];
+                bad_total += bad;
+            }
+            printf("check persistent TMA SUB %lld x %lld x %d lower=%d: mismatching entries over 5 runs: %zu\n", (long long)q.r, (long long)q.c, q.k, q.lower, bad_total);
+        }
+        // in-place leaf X <- X Dinv^T (64x128 tiles, k = 128) on 16384 rows = 256 tiles
+        {
+            const int64_t r = 16384;
+            ref.assign((size_t)r * ld, 0.0); got.assign((size_t)r * ld, 0.0);
+            size_t bad_total = 0;
+            for (int rep = 0; rep < 6; rep++) {
+                g_dgemm_tma = rep == 0 ? 0 : 1;
+                cudaMemcpy(C, A, (size_t)r * ld * 8, cudaMemcpyDeviceToDevice);
+                dgemm_nt_configure<64, 128, GM_SET>();
+                dgemm_nt_launch<64, 128, GM_SET>(0, C + 384, ld, B + 5 * 128 * ld, ld, C + 384, ld, r, 128, 128, 0, 0, 0);   // ONE in-place pass (exact)
+                if (cudaDeviceSynchronize() != cudaSuccess) { printf("in-place SET failed\n"); exit(1); }
+                cudaMemcpy((rep == 0 ? ref : got).data(), C, (size_t)r * ld * 8, cudaMemcpyDeviceToHost);
+                if (rep == 0) continue;
+                size_t bad = 0;
+                for (int64_t i = 0; i < r; i++)
+                    for (int64_t j = 0; j < 1024; j++) bad += got[i * ld + j] != ref[i * ld + j];
+                bad_total += bad;
+            }
+            printf("check persistent TMA in-place SET 16384 x 128 x 128: mismatching entries over 5 runs: %zu\n", bad_total);
+        }
+        g_dgemm_tma = 0;
+        cudaMemset(C, 0, (size_t)R * ld * 8);
+    }
     // kernel variants on a full-wave shape and on the k = 128 update shape (same arithmetic, different staging / warp tiling):
     //   BK=32 x 2 stages: half the barriers per flop;  32x64 warp tiles, 4 warps per 64x128 CTA: 0.375 instead of 0.5 LDS per DMMA
     //   (what the cuBLAS kernel of the same tile, cutlass_80_tensorop_d884gemm_64x128_16x3, uses);  128x128 CTA, 1 per SM
