@@ -56,6 +56,8 @@ class B200Backend:
         self.n_u = 100
         self.ARD = True
         self._factor_key = None
+        # lengthscale prior of find_MAP: "InverseGamma" (today's reference, GP.py:385,407) or "Gamma(2,1)" (its older code, GP.py:408)
+        self.ls_prior = "InverseGamma"
         self.model_specs = {
             "seed": self.seed,
             "continuous_kernel": self.continuous_kernel,

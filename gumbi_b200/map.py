@@ -199,13 +199,19 @@ def build_priors(gp):
     lay = gp._layout
     X = gp._X
     Xs = X[:, lay["idx_s"]]
-    lower, upper = ls_bounds_z(gp)
-    ls_params = get_ls_prior(Xs, ARD=gp.ARD, lower=lower, upper=upper, mass=gp.mass)
+    ls_prior = getattr(gp, "ls_prior", "InverseGamma")
+    if ls_prior not in ("InverseGamma", "Gamma(2,1)"):
+        raise ValueError(f"ls_prior must be 'InverseGamma' or 'Gamma(2,1)', got {ls_prior!r}")
+    if ls_prior == "InverseGamma":     # today's reference: constrained InverseGamma from the data's distance range (GP.py:385,407)
+        lower, upper = ls_bounds_z(gp)
+        ls_params = get_ls_prior(Xs, ARD=gp.ARD, lower=lower, upper=upper, mass=gp.mass)
     pri = {}
     for name, shape in gp.param_shapes().items():
         kind = name.split("_")[0]
         if kind == "ls":
-            pri[name] = _invgamma(ls_params["alpha"], ls_params["beta"])
+            # "Gamma(2,1)": the prior of the reference's older code, kept in its source as a comment (GP.py:408) -- the one the
+            # executed Multioutput_Regression notebook was run with (tests/test_notebook_parity.py)
+            pri[name] = _invgamma(ls_params["alpha"], ls_params["beta"]) if ls_prior == "InverseGamma" else _gamma(2.0, 1.0)
         elif kind == "η":
             pri[name] = _gamma(2.0, 1.0)
         elif kind == "c":
