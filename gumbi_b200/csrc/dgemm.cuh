@@ -211,7 +211,7 @@ template <int BM, int BN, int MODE, int MINB = 2>
 __global__ void __launch_bounds__(256, MINB)
 dgemm_tma_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mB, int a_row0, int a_col0, int b_row0, int b_col0,
                  double* C, int64_t ldc, int kdepth, int lower_only, int64_t row_off, int64_t col_off, int rb_first, int rb_stride,
-                 PushArgs push, int rb_local_first, int n_bi, int n_bj) {
+                 PushArgs push, int rb_local_first, int n_bi, int n_bj, int c_cg, int xprefetch) {
     constexpr int WM = 32, WN = 32, MI = WM / 8, NI = WN / 8;
     constexpr int STAGE_BYTES = (BM + BN) * 128;
     constexpr int TPB = TILE / BM;
@@ -229,6 +229,10 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
     if (tid == 0) {
         for (int s = 0; s < GT_STAGES; s++) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // The operands were written by the preceding kernels with ordinary (generic-proxy) stores; the loads below go through the
+        // async proxy.  Grid completion orders those stores before this kernel in the generic proxy; this fence carries that order
+        // over to the async proxy for global memory.
+        if (c_cg & 2) asm volatile("fence.proxy.async.global;" ::: "memory");
     }
     __syncthreads();
 
@@ -248,6 +252,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
 
     // ---- producer state (thread 0 only): the ring runs ahead of the consumers ACROSS tiles, so the operands of the next tile
     // stream in while this tile's epilogue reads and writes C
+    int cur_tile = blockIdx.x;   // the consumers' current tile (xprefetch == 0: the producer never opens a later one)
     int p_tile = blockIdx.x, p_it = 0, p_nit = 0, p_arow = 0, p_brow = 0, p_kt0 = 0;
     uint32_t p_g = 0;        // k-tiles issued so far
     bool p_open = false;     // p_tile's coordinates are loaded
@@ -257,6 +262,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
                 int bj, kt0; int64_t grow, lrow;
                 while (p_tile < n_tiles && !tile_info(p_tile, bj, grow, lrow, kt0)) p_tile += gridDim.x;
                 if (p_tile >= n_tiles) return;
+                if (!xprefetch && p_tile > cur_tile) return;
                 p_arow = a_row0 + (int)lrow; p_brow = b_row0 + bj * BN; p_kt0 = kt0; p_nit = nk - kt0; p_it = 0;
                 p_open = true;
                 if (p_nit <= 0) { p_open = false; p_tile += gridDim.x; continue; }
@@ -282,6 +288,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         int bj, kt0; int64_t grow, lrow;
         if (!tile_info(tile, bj, grow, lrow, kt0)) continue;
+        cur_tile = tile;
         const int n_it = nk - kt0;
         double acc[MI][NI][2];
 #pragma unroll
@@ -318,7 +325,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
             for (int ni = 0; ni < NI; ni++) {
                 double2* p = reinterpret_cast<double2*>(Cg + (int64_t)mi * 8 * ldc + ni * 8);
                 if (MODE == GM_SUB) {
-                    double2 c = *p;
+                    double2 c = (c_cg & 1) ? __ldcg(p) : *p;
                     c.x -= acc[mi][ni][0];
                     c.y -= acc[mi][ni][1];
                     *p = c;
@@ -343,6 +350,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
                 for (int pr = 0; pr < push.n_peers; pr++)
                     if (push.peerFlag[pr]) atomicAdd_system(push.peerFlag[pr], 1u);
         }
+        if (!xprefetch) __syncthreads();   // diagnostic mode: tiles of a CTA are fully serialised
     }
 }
 
@@ -361,8 +369,15 @@ inline MemGetAddressRangeFn mem_range_fn() {
 
 struct TmaOperand { CUtensorMap map; int row0, col0; };
 
-inline int g_dgemm_tma = 1;          // set_option("dgemm_tma", 0/1): process-wide switch (ablation)
-inline int g_dgemm_persistent = 1;   // set_option("dgemm_persistent", 0/1): 0 = one CTA per tile (ablation)
+// set_option("dgemm_tma", mask): process-wide switch, see dgemm_tma_try_launch; 1 -> 7.  DEFAULT OFF: stand-alone the TMA-staged
+// kernel is exact (tools/micro_dgemm check, compute-sanitizer racecheck clean) and 7 % faster, but inside the factorisation pipeline
+// it produced intermittently corrupted tiles on the device (profiles/r02e..r02i_*diag*.log); until that is understood the product
+// path stays on the cp.async kernel, which is bit-reproducible run to run.
+inline int g_dgemm_tma = 0;
+inline int g_dgemm_fence = 1;         // set_option("dgemm_fence", 0/1): fence.proxy.async.global before the first TMA load of a CTA
+inline int g_dgemm_promo = 1;         // set_option("dgemm_promo", 0/1): L2 promotion 256B / none in the tensor maps (diagnostic)
+inline int g_dgemm_cg = 0;            // set_option("dgemm_cg", 1): read-modify-write epilogue loads C with ld.global.cg (L2 only) -- diagnostic
+inline int g_dgemm_persistent = 1;   // set_option("dgemm_persistent", 0/1/2): 0 = one CTA per tile (ablation), 2 = persistent without cross-tile prefetch
 inline int tma_sm_count() {
     static int n = 0;
     if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
@@ -382,10 +397,12 @@ inline bool tma_operand(const double* ptr, int64_t ld, int box_rows, TmaOperand&
     const int64_t rows = (int64_t)(size / sizeof(double)) / ld;
     if (rows < 1 || off / ld > 0x7fffffff) return false;
     struct Key { uintptr_t base; size_t size; int64_t ld; int box; bool operator==(const Key& o) const { return base == o.base && size == o.size && ld == o.ld && box == o.box; } };
+    box_rows |= g_dgemm_promo ? 0 : (1 << 20);   // separate cache entries per promotion setting
     struct Hash { size_t operator()(const Key& k) const { return (size_t)k.base * 1315423911u ^ k.size ^ ((size_t)k.ld << 7) ^ (size_t)k.box; } };
     static std::unordered_map<Key, CUtensorMap, Hash> cache;
     static std::mutex mu;
     const Key key{(uintptr_t)basep, size, ld, box_rows};
+    box_rows &= (1 << 20) - 1;
     {
         std::lock_guard<std::mutex> lk(mu);
         auto itc = cache.find(key);
@@ -396,7 +413,8 @@ inline bool tma_operand(const double* ptr, int64_t ld, int box_rows, TmaOperand&
             cuuint32_t box[2] = {(cuuint32_t)GT_BK, (cuuint32_t)box_rows};
             cuuint32_t estr[2] = {1, 1};
             if (encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)(uintptr_t)basep, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                       CU_TENSOR_MAP_SWIZZLE_128B, g_dgemm_promo ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                 return false;
             if (cache.size() > 4096) cache.clear();   // handles come and go (tests): bound the cache
             itc = cache.emplace(key, m).first;
@@ -413,6 +431,10 @@ inline bool dgemm_tma_try_launch(cudaStream_t s, const double* A, int64_t lda, c
                                  int64_t cols, int kdepth, int lower_only, int64_t row_off, int64_t col_off, int rb_first, int rb_stride,
                                  const PushArgs& pa, int rb_local_first) {
     TmaOperand oa, ob;
+    // g_dgemm_tma is a bit mask (diagnostic): 1 = the in-place SET products (panel solves, solve leaves), 2 = SUB updates one
+    // 128-column block wide (next-column updates), 4 = all other SUB updates
+    const int usage = MODE != GM_SUB ? 1 : (cols <= TILE ? 2 : 4);
+    if (!(g_dgemm_tma & usage)) return false;
     if (kdepth % GT_BK != 0 || !tma_operand(A, lda, BM, oa) || !tma_operand(B, ldb, BN, ob)) return false;
     static bool configured = false;
     if (!configured) {
@@ -427,7 +449,7 @@ inline bool dgemm_tma_try_launch(cudaStream_t s, const double* A, int64_t lda, c
     const unsigned grid = (unsigned)(g_dgemm_persistent && n_tiles > slots ? slots : n_tiles);
     dgemm_tma_kernel<BM, BN, MODE><<<grid, 256, dgemm_tma_smem_bytes<BM, BN>(), s>>>(oa.map, ob.map, oa.row0, oa.col0, ob.row0, ob.col0, C, ldc, kdepth,
                                                                                     lower_only, row_off, col_off, rb_first, rb_stride, pa, rb_local_first,
-                                                                                    n_bi, n_bj);
+                                                                                    n_bi, n_bj, g_dgemm_cg | (g_dgemm_fence << 1), g_dgemm_persistent == 2 ? 0 : 1);
     return true;
 }
 

@@ -22,7 +22,11 @@
 
 namespace gb2 {
 
-constexpr int KB4_TAB = 2048;
+constexpr int KB4_TAB = 2048;       // entries of the exp table: 2^(j/2048)
+constexpr int KB4_REP = 1;          // copies of every entry.  Measured (profiles/r02g_micro_kbuild.log): a 256-entry table with 16 copies (one
+                                    // per lane of a half-warp: no bank conflicts on the lookup, quartic instead of cubic) is 8-13 % SLOWER than
+                                    // this single copy with its 2-3-way conflicts -- the extra fp64 operation costs more than the conflicts
+constexpr int KB4_TAB_LOG2 = 11;
 constexpr int KB4_STAGES = 3;
 constexpr int KB4_TS = 68;          // shared row stride (doubles) of a staged column tile: conflict-free 4x8 DMMA B fragments
 constexpr int KB4_MAXCG = 2;
@@ -47,24 +51,24 @@ template <int ZS2>   // ZS2 = 2 * zs: 1 (ExpQuad, z = r^2, exp(-z/2)) or 2 (Mate
 __device__ __forceinline__ double kb4_exp(double z, const double* __restrict__ tab) {
     constexpr double zs = 0.5 * ZS2;
     constexpr double LN2 = 0.693147180559945309417232121458176568;
-    constexpr double LOG2E_2048 = (double)KB4_TAB / LN2;    // 2048 / ln 2   (constant-folded by the host compiler, correctly rounded)
-    constexpr double LN2_2048 = LN2 / (double)KB4_TAB;      // ln 2 / 2048
+    constexpr double LOG2E_TAB = (double)KB4_TAB / LN2;    // 2048 / ln 2   (constant-folded by the host compiler, correctly rounded)
+    constexpr double LN2_TAB = LN2 / (double)KB4_TAB;      // ln 2 / 2048
     constexpr double MAGIC = 6755399441055744.0;            // 1.5 * 2^52
-    const double t = fma(z, -zs * LOG2E_2048, MAGIC);
+    const double t = fma(z, -zs * LOG2E_TAB, MAGIC);
     const int n = __double2loint(t);                         // round(-zs z 2048 / ln2) <= 0
     const double kf = t - MAGIC;
-    const double rr = fma(kf, LN2_2048 / zs, z);             // |rr| <= ln2 / (4096 zs)
+    const double rr = fma(kf, LN2_TAB / zs, z);             // |rr| <= ln2 / (4096 zs)
     const double q1 = fma(rr, -zs * zs * zs / 6.0, 0.5 * zs * zs);
     const double q2 = fma(q1, rr, -zs);
     const double m = rr * q2;                                // exp(-zs rr) - 1
-    const double T = tab[n & (KB4_TAB - 1)];
+    const double T = tab[(n & (KB4_TAB - 1)) * KB4_REP];
     const double res = fma(T, m, T);
     // 2^(n >> 11) by exponent arithmetic.  Arguments with zs z >= 693 (exp < 2^-1000 ~ 1e-301) return an exact 0: decided on the HIGH
     // WORD OF z (integer pipe; z >= 0 orders like its bit pattern, a rounding-negative z has the sign bit set and compares below),
     // because for huge scaled distances (z > ~1e6) the low word of t -- n -- wraps around and must not be consulted.  A result whose
     // exponent field would underflow (tiny eta^2 on top of a tiny exp) is flushed to 0 as well.
     constexpr int HI_ZMAX = ZS2 == 1 ? 0x4095A800 /* 1386.0 */ : 0x4085A800 /* 693.0 */;
-    const int hi = __double2hiint(res) + ((n >> 11) << 20);
+    const int hi = __double2hiint(res) + ((n >> KB4_TAB_LOG2) << 20);
     const bool tiny = __double2hiint(z) >= HI_ZMAX || hi < 0x00100000;
     return __hiloint2double(tiny ? 0 : hi, tiny ? 0 : __double2loint(res));
 }
@@ -92,10 +96,14 @@ __host__ __device__ inline double kb4_scale(int kind) {
 }
 
 template <int KIND>
-__device__ __forceinline__ double kb4_value(int kind_rt, double z, const double* __restrict__ tab) {
+__device__ __forceinline__ double kb4_value(int kind_rt, double z, double zmin, const double* __restrict__ tab) {
     const int kind = KIND >= 0 ? KIND : kind_rt;
-    if (kind == GB2_EXPQUAD) return kb4_exp<1>(z, tab);
-    const double w = kb4_sqrt(z);                    // z >= c * 1e-12 * (1 - 1e-3) > 0: Stationary.euclidean_dist's epsilon
+    // clip(r^2, 0, inf) of Stationary.square_dist, on the integer pipe (doubles order like their bit patterns as signed 64-bit
+    // integers when the right-hand side is >= 0): the expanded form can come out negative by ~1e-16 |u|^2 (duplicated points, the
+    // diagonal) -- harmless for exp at ordinary scales, but NaN under the Matern square root once it exceeds the 1e-12 epsilon
+    if (kind == GB2_EXPQUAD) return kb4_exp<1>(__double2hiint(z) < 0 ? 0.0 : z, tab);
+    z = __double_as_longlong(z) < __double_as_longlong(zmin) ? zmin : z;   // zmin = c * 1e-12: clip(r^2, 0) + 1e-12 (euclidean_dist)
+    const double w = kb4_sqrt(z);
     const double e = kb4_exp<2>(w, tab);
     if (kind == GB2_MATERN52) return e * fma(fma(1.0 / 3.0, w, 1.0), w, 1.0);   // 1 + w + w^2/3 = 1 + sqrt5 r + 5/3 r^2
     if (kind == GB2_MATERN32) return e * (1.0 + w);
@@ -107,8 +115,8 @@ template <bool TRAIN, int KIND, int KS, int NCG, int OCC>
 __global__ void __launch_bounds__(KB_THREADS, OCC)
 kbuild_persist_kernel(KParams kp, KB4Args a) {
     extern __shared__ __align__(16) unsigned char kb_smem[];
-    double* sTab = reinterpret_cast<double*>(kb_smem);                         // [2048]
-    double* sB = sTab + KB4_TAB;                                                // [STAGES][4 KS][TS]
+    double* sTab = reinterpret_cast<double*>(kb_smem);                         // [2048] x KB4_REP
+    double* sB = sTab + KB4_TAB * KB4_REP;                                                // [STAGES][4 KS][TS]
     double* sS = sB + KB4_STAGES * 4 * KS * KB4_TS;                             // [STAGES][64]  column squared norms (raw)
     double* sBt = sS + KB4_STAGES * KB_T;                                       // [NCG][P*P <= 64] Coregion tables
     int* sCj = reinterpret_cast<int*>(sBt + (NCG > 0 ? NCG : 1) * GB2_MAX_P * GB2_MAX_P);   // [STAGES][NCG][64]
@@ -126,7 +134,8 @@ kbuild_persist_kernel(KParams kp, KB4Args a) {
     const double* Fjt = a.Fj + (int64_t)T.feat_off * a.stride_j;
 
     // one-time per CTA: exp table scaled by eta^2, zero rows of the staged tiles (features d .. 4 KS - 1), Coregion tables
-    for (int e = tid; e < KB4_TAB; e += KB_THREADS) sTab[e] = T.eta2 * g_exp2_tab2k[e];
+    for (int e = tid; e < KB4_TAB * KB4_REP; e += KB_THREADS) sTab[e] = T.eta2 * g_exp2_tab2k[e / KB4_REP];
+    const double* tabl = sTab + (lane & (KB4_REP - 1));      // this lane's copy of the table
     for (int e = tid; e < KB4_STAGES * 4 * KS * KB4_TS; e += KB_THREADS) sB[e] = 0.0;
     if (NCG > 0)
         for (int e = tid; e < NCG * GB2_MAX_P * GB2_MAX_P; e += KB_THREADS) {
@@ -249,9 +258,7 @@ kbuild_persist_kernel(KParams kp, KB4Args a) {
                 for (int mi = 0; mi < 2; mi++)
 #pragma unroll
                     for (int e = 0; e < 2; e++) {
-                        // No clip(r^2, 0) here: a rounding-negative r^2 (|.| ~ 1e-16 |u|^2, duplicated points / the diagonal) gives
-                        // exp(+1e-16) = 1 + 1e-16 where the reference gets exactly 1; the Matern kinds carry their 1e-12 under the root.
-                        double v = kb4_value<KIND>(kind_rt, acc[mi][ni][e], sTab);
+                        double v = kb4_value<KIND>(kind_rt, acc[mi][ni][e], ceps, tabl);
 #pragma unroll
                         for (int f = 0; f < NCG; f++) v *= sBt[rowoff[f][mi] + cj[f][e]];
                         acc[mi][ni][e] = v;
@@ -312,7 +319,7 @@ kbuild_persist_kernel(KParams kp, KB4Args a) {
 
 template <int KS, int NCG>
 constexpr size_t kb4_smem_bytes() {
-    return (size_t)(KB4_TAB + KB4_STAGES * 4 * KS * KB4_TS + KB4_STAGES * KB_T + (NCG > 0 ? NCG : 1) * GB2_MAX_P * GB2_MAX_P) * sizeof(double) +
+    return (size_t)(KB4_TAB * KB4_REP + KB4_STAGES * 4 * KS * KB4_TS + KB4_STAGES * KB_T + (NCG > 0 ? NCG : 1) * GB2_MAX_P * GB2_MAX_P) * sizeof(double) +
            (size_t)KB4_STAGES * (NCG > 0 ? NCG : 1) * KB_T * sizeof(int);
 }
 

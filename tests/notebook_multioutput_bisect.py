@@ -1,8 +1,14 @@
 """Bisect of the multi-output notebook deviation (container only, needs /root/reference): today's model with ONE prior changed at a time,
 max relative deviation of mean / variance from the executed cell (Multioutput_Regression.ipynb:270-274).  Result recorded in
 tests/test_notebook_parity.py; the winner (ls ~ Gamma(2,1), GP.py:408) is a committed test."""
-import sys, numpy as np
-import notebook_multioutput_probe as P
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import notebook_multioutput_probe as P  # noqa: E402
 import gumbi_b200.map as M
 from scipy import stats, optimize
 from scipy.spatial.distance import pdist

@@ -256,6 +256,28 @@ def test_full_size_config2_properties(engine):
     np.testing.assert_allclose(engine.mll(), -0.5 * 8192 * np.log(2 * np.pi) - np.log(np.diag(L0)).sum() - 0.5 * v0 @ v0, rtol=1e-10)
 
 
+@pytest.mark.slow
+@pytest.mark.parametrize("sigma", [1e-2, 1e-3])
+def test_small_noise_regime_inverse_based_solve(engine, sigma):
+    """The predict solve multiplies by explicit inverses of the 128 x 128 diagonal blocks of L (predict.cuh) instead of substituting.
+    Near the jitter-limited regime (dense 2-d design, sigma -> 0: cond(K) ~ N / (sigma^2 + 1e-6) ~ 1e7..4e9) that is where an
+    inverse-based TRSM would lose digits first.  Gate: the north-star rtol 1e-5 against the LAPACK oracle (substitution), with the
+    posterior variance compared relative to the prior variance it is a cancellation residue of."""
+    spec, X, y, Xs = orc.synthetic_problem(4096, 2, M_res=40, kind="ExpQuad")
+    spec["sigma"] = sigma
+    mu, var = run_case(engine, spec, X, y, Xs, True)
+    mu0, var0 = orc.predict(spec, X, y, Xs, True)
+    scale = np.max(np.abs(mu0))
+    err_mu = np.max(np.abs(mu - mu0)) / scale
+    err_var = np.max(np.abs(var - var0)) / (spec["terms"][0]["eta"] ** 2)
+    print(f"sigma={sigma}: max |dmu| / max|mu| = {err_mu:.2e}, max |dvar| / eta^2 = {err_var:.2e}")
+    assert err_mu <= RTOL_GATE and err_var <= RTOL_GATE
+    # the factor itself: L L^T z = K z by random probes, to the accuracy cond(K) allows a backward-stable factorisation
+    L = engine.get_L(); K = engine.get_K()
+    z = np.random.default_rng(1).standard_normal((4096, 3))
+    np.testing.assert_allclose(L @ (L.T @ z), K @ z, rtol=0, atol=1e-9 * np.abs(K @ z).max())
+
+
 GRAD_CASES = [
     # n, d, P, kind, Q, linear
     (150, 2, 1, "ExpQuad", 1, False),

@@ -5,6 +5,8 @@
 #include "dgemm.cuh"
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 using namespace gb2;
 
@@ -24,7 +26,76 @@ static double run(const double* A, const double* B, double* C, int64_t ld, int64
     return ms / reps;
 }
 
-int main() {
+// "check" mode: exactness of the persistent TMA path in the regime of the factorisation's trailing update (k = 128: 8 k-tiles per
+// output tile, lower-triangular tile list, many tiles per CTA), repeated; data are multiples of 2^-16 so every sum is exact and the
+// result must equal the cp.async kernel's bit for bit.  Small enough to run under compute-sanitizer --tool racecheck.
+static int check_mode(int reps) {
+    const int64_t ld = 4096, R = 4096 + 512;
+    double *A, *B, *C;
+    cudaMalloc(&A, R * ld * 8); cudaMalloc(&B, R * ld * 8); cudaMalloc(&C, R * ld * 8);
+    std::vector<double> h((size_t)R * ld);
+    for (size_t i = 0; i < h.size(); i++) h[i] = (double)((i * 2654435761u) >> 8 & 0xffff) / 65536.0 - 0.5;
+    cudaMemcpy(A, h.data(), h.size() * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(B, h.data(), h.size() * 8, cudaMemcpyHostToDevice);
+    struct PS { int64_t r, c; int k; int lower; } ps[] = {{3072, 3072, 128, 1}, {4096, 2048, 128, 0}, {4096, 4096, 128, 1}, {4096, 3072, 256, 0}, {2048, 4096, 1024, 0}};
+    std::vector<double> ref((size_t)R * ld), got((size_t)R * ld);
+    int rc = 0;
+    for (int mode : {1, 2}) {
+        for (auto q : ps) {
+            g_dgemm_tma = 0;
+            cudaMemset(C, 0, (size_t)R * ld * 8);
+            dgemm_nt_configure<128, 64, GM_SUB>();
+            dgemm_nt_launch<128, 64, GM_SUB>(0, A + 128 * ld + 256, ld, B + 256 * ld + 512, ld, C, ld, q.r, q.c, q.k, q.lower, 0, 0);
+            cudaDeviceSynchronize();
+            cudaMemcpy(ref.data(), C, (size_t)q.r * ld * 8, cudaMemcpyDeviceToHost);
+            size_t bad_total = 0; int bad_runs = 0;
+            for (int rep = 0; rep < reps; rep++) {
+                g_dgemm_tma = 7; g_dgemm_persistent = mode;
+                cudaMemset(C, 0, (size_t)R * ld * 8);
+                dgemm_nt_launch<128, 64, GM_SUB>(0, A + 128 * ld + 256, ld, B + 256 * ld + 512, ld, C, ld, q.r, q.c, q.k, q.lower, 0, 0);
+                cudaError_t e = cudaDeviceSynchronize();
+                if (e != cudaSuccess) { printf("launch failed: %s\n", cudaGetErrorString(e)); return 2; }
+                cudaMemcpy(got.data(), C, (size_t)q.r * ld * 8, cudaMemcpyDeviceToHost);
+                size_t bad = 0;
+                for (int64_t i = 0; i < q.r; i++)
+                    for (int64_t j = 0; j < q.c; j++) bad += got[i * ld + j] != ref[i * ld + j];
+                bad_total += bad; bad_runs += bad != 0;
+            }
+            printf("check persistent=%d TMA SUB %lld x %lld x %d lower=%d: %zu mismatching entries, %d of %d runs wrong\n", mode, (long long)q.r,
+                   (long long)q.c, q.k, q.lower, bad_total, bad_runs, reps);
+            rc |= bad_total != 0;
+        }
+        // in-place leaf X <- X Dinv^T, 64x128 tiles, k = 128, 24576 rows = 384 tiles (> 296 slots), X inside a narrow matrix (ld 512)
+        {
+            const int64_t r = 24576, ld2 = 512;
+            double *X, *X0;
+            cudaMalloc(&X, r * ld2 * 8); cudaMalloc(&X0, r * ld2 * 8);
+            cudaMemcpy(X0, A, r * ld2 * 8, cudaMemcpyDeviceToDevice);
+            std::vector<double> r2((size_t)r * ld2), g2((size_t)r * ld2);
+            size_t bad_total = 0; int bad_runs = 0;
+            for (int rep = 0; rep <= reps; rep++) {
+                g_dgemm_tma = rep == 0 ? 0 : 7; g_dgemm_persistent = mode;
+                cudaMemcpy(X, X0, r * ld2 * 8, cudaMemcpyDeviceToDevice);
+                dgemm_nt_configure<64, 128, GM_SET>();
+                dgemm_nt_launch<64, 128, GM_SET>(0, X + 128, ld2, B + 5 * 128 * ld, ld, X + 128, ld2, r, 128, 128, 0, 0, 0);
+                cudaDeviceSynchronize();
+                cudaMemcpy((rep == 0 ? r2 : g2).data(), X, r * ld2 * 8, cudaMemcpyDeviceToHost);
+                if (rep == 0) continue;
+                size_t bad = 0;
+                for (size_t i = 0; i < r2.size(); i++) bad += g2[i] != r2[i];
+                bad_total += bad; bad_runs += bad != 0;
+            }
+            printf("check persistent=%d TMA in-place SET %lld x 128 x 128: %zu mismatching entries, %d of %d runs wrong\n", mode, (long long)r, bad_total,
+                   bad_runs, reps);
+            rc |= bad_total != 0;
+            cudaFree(X); cudaFree(X0);
+        }
+    }
+    return rc;
+}
+
+int main(int argc, char** argv) {
+    if (argc > 1 && !strcmp(argv[1], "check")) return check_mode(argc > 2 ? atoi(argv[2]) : 20);
     const int64_t ld = 16384, R = 16384;
     double *A, *B, *C;
     cudaMalloc(&A, R * ld * 8); cudaMalloc(&B, R * ld * 8); cudaMalloc(&C, R * ld * 8);
@@ -46,7 +117,7 @@ int main() {
         // decides whether fusing the predict solve into the factorisation's trailing updates would pay
         {10112, 8192, 128}, {10112, 4096, 128}, {10112, 1024, 128}, {10112, 8192, 256}};
     for (int tma : {1, 0}) {
-    g_dgemm_tma = tma;
+    g_dgemm_tma = tma ? 7 : 0;
     printf("---- operand staging: %s\n", tma ? "TMA (cp.async.bulk.tensor.2d + mbarrier ring)" : "cp.async + __syncthreads (round 1)");
     for (auto s : shapes) {
         const double ms = run<128, 64, GM_SUB>(A, B, C, ld, s.r, s.c, s.k, 0, 10);
@@ -75,7 +146,7 @@ int main() {
         std::vector<double> ref((size_t)r * ld), got((size_t)r * ld);
         double worst = 0, scale = 0;
         for (int tma : {0, 1}) {
-            g_dgemm_tma = tma;
+            g_dgemm_tma = tma ? 7 : 0;
             cudaMemset(C, 0, (size_t)r * ld * 8);
             run<128, 64, GM_SUB>(A + 3 * 128 * ld + 256, B + 128 * ld + 512, C, ld, r, c, k, 0, 0);   // operands at an offset inside their allocations
             run<64, 128, GM_SET>(A + 256, B + 5 * 128 * ld, C + 1024, ld, r, 128, 128, 0, 0);
@@ -89,7 +160,7 @@ int main() {
     }
     {   // the PERSISTENT path of the TMA kernel (more tiles than CTA slots: cross-tile prefetch), repeated to expose races; the test
         // data are multiples of 2^-16, so every product and partial sum is exact and the two kernels must agree bit for bit
-        struct PS { int64_t r, c; int k; int lower; } ps[] = {{8192, 4096, 512, 0}, {16384, 2048, 128, 0}, {8192, 8192, 128, 1}, {4096, 4096, 2048, 0}};
+        struct PS { int64_t r, c; int k; int lower; } ps[] = {{8192, 4096, 512, 0}, {12288, 2048, 128, 0}, {8192, 8192, 128, 1}, {4096, 4096, 2048, 0}};
         std::vector<double> ref, got;
         for (auto q : ps) {
             ref.assign((size_t)q.r * ld, 0.0); got.assign((size_t)q.r * ld, 0.0);
@@ -99,7 +170,7 @@ int main() {
             cudaMemcpy(ref.data(), C, (size_t)q.r * ld * 8, cudaMemcpyDeviceToHost);
             size_t bad_total = 0;
             for (int rep = 0; rep < 5; rep++) {
-                g_dgemm_tma = 1;
+                g_dgemm_tma = 7;
                 cudaMemset(C, 0, (size_t)q.r * ld * 8);
                 run<128, 64, GM_SUB>(A + 128 * ld + 256, B + 256 * ld + 512, C, ld, q.r, q.c, q.k, q.lower, 0);
                 cudaMemcpy(got.data(), C, (size_t)q.r * ld * 8, cudaMemcpyDeviceToHost);
@@ -116,7 +187,7 @@ int main() {
             ref.assign((size_t)r * ld, 0.0); got.assign((size_t)r * ld, 0.0);
             size_t bad_total = 0;
             for (int rep = 0; rep < 6; rep++) {
-                g_dgemm_tma = rep == 0 ? 0 : 1;
+                g_dgemm_tma = rep == 0 ? 0 : 7;
                 cudaMemcpy(C, A, (size_t)r * ld * 8, cudaMemcpyDeviceToDevice);
                 dgemm_nt_configure<64, 128, GM_SET>();
                 dgemm_nt_launch<64, 128, GM_SET>(0, C + 384, ld, B + 5 * 128 * ld, ld, C + 384, ld, r, 128, 128, 0, 0, 0);   // ONE in-place pass (exact)
