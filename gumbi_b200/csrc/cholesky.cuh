@@ -37,11 +37,6 @@ constexpr int PD_NBLK = 10;            // lower sub-blocks of a 4x4 block grid
 // Lb (10 sub-blocks of the factor) + Xt (10 sub-blocks of the inverse, stored transposed) + Xd (4 diagonal inverses)
 constexpr size_t PD_SMEM = (size_t)(2 * PD_NBLK + 4) * PB_SZ * sizeof(double) + (TILE + 2 * PB) * sizeof(double);
 
-// Small-footprint variant (option "small_diag"): 256 threads x <= 128 registers and 14 sub-blocks of shared memory (no transposed
-// copy of the inverse), so that the CTA fits on an SM BESIDE one 92 KB / 30k-register GEMM CTA instead of needing an empty SM.
-constexpr int PDS_THREADS = 256;
-constexpr size_t PDS_SMEM = (size_t)(PD_NBLK + 4) * PB_SZ * sizeof(double) + (TILE + 2 * PB) * sizeof(double);
-
 __device__ __forceinline__ int pd_blk(int i, int j) { return i * (i + 1) / 2 + j; }
 
 // Branch-free 1/sqrt(d): MUFU.RSQ64H seed (rsqrt.approx.ftz.f64, ~2^-22) + two Newton steps in fp64.  The library
@@ -317,283 +312,6 @@ potrf_diag_kernel(double* __restrict__ A, int64_t ld, int64_t g0, int64_t n_real
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Small-footprint twin of potrf_diag_kernel (the kernel above is left untouched, instruction for instruction): the same body with
-// SMALL = true -- 8 warps, no transposed copy of the inverse in shared memory, the inverse assembled block column by block column
-// in the slots of the factor's diagonal sub-blocks.  (SMALL = false reproduces the kernel above and is not instantiated.)
-// ---------------------------------------------------------------------------------------------------------------
-template <bool SMALL>
-__device__ __forceinline__ void potrf_diag_body(double* __restrict__ A, int64_t ld, int64_t g0, int64_t n_real, double* __restrict__ Dinv,
-                                                int* __restrict__ info, double* __restrict__ Lpack, const PushArgs& sig,
-                                                long long* __restrict__ clk) {
-    extern __shared__ __align__(16) unsigned char pd_smem[];
-    int clk_i = 0;
-#define PD_CLK() do { if (clk && threadIdx.x == 0) clk[clk_i++] = clock64(); } while (0)
-    PD_CLK();
-    double* Lb = reinterpret_cast<double*>(pd_smem);     // 10 sub-blocks of the factor, L_ij[r][k]
-    double* Xt = Lb + PD_NBLK * PB_SZ;                    // 10 sub-blocks of inv(L), transposed: Xt_ij[c][r] = X_ij[r][c]  (not SMALL)
-    double* Xd = SMALL ? Lb + PD_NBLK * PB_SZ : Xt + PD_NBLK * PB_SZ;   // the 4 diagonal sub-blocks of inv(L), not transposed
-    double* rdiag = Xd + 4 * PB_SZ;                       // 1 / L[j][j]
-    double* colbuf = rdiag + TILE;                        // 2 x 32: double-buffered column broadcast of potrf32
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = (SMALL ? PDS_THREADS : PD_THREADS) / 32;
-    double* Ab = A + g0 * ld + g0;
-
-    // ---- load the lower sub-blocks: one warp per (sub-block, row) = 256 contiguous bytes, 20 independent loads in flight
-    // per thread; strict upper parts of the diagonal sub-blocks are zeroed
-    constexpr int NLD = PD_NBLK * PB / NW, PASSES = SMALL ? 2 : 1;   // SMALL: two passes of 20 loads keep the registers for potrf32
-#pragma unroll
-    for (int pass = 0; pass < PASSES; pass++) {
-        double v[NLD / PASSES];
-#pragma unroll
-        for (int q = 0; q < NLD / PASSES; q++) {
-            const int pr = warp + (q + pass * (NLD / PASSES)) * NW, b = pr >> 5, r = pr & 31;
-            const int bi = (b >= 6) ? 3 : (b >= 3) ? 2 : (b >= 1) ? 1 : 0;
-            const int bj = b - bi * (bi + 1) / 2;
-            v[q] = (bi != bj || lane <= r) ? Ab[(int64_t)(bi * PB + r) * ld + bj * PB + lane] : 0.0;
-        }
-#pragma unroll
-        for (int q = 0; q < NLD / PASSES; q++) {
-            const int pr = warp + (q + pass * (NLD / PASSES)) * NW;
-            Lb[(pr >> 5) * PB_SZ + (pr & 31) * PB_LD + lane] = v[q];
-        }
-    }
-    __syncthreads();
-    PD_CLK();
-
-    for (int p = 0; p < 4; p++) {
-        double* Lpp = Lb + pd_blk(p, p) * PB_SZ;
-        // ---- potrf32: warp 0, lane r owns row r.  The next pivot's 1/sqrt is started before the column broadcast of
-        // the current column is consumed, so its latency hides behind the rank-1 update.
-        if (warp == 0) {
-            double a[PB];
-            const double2* ar = reinterpret_cast<const double2*>(Lpp + lane * PB_LD);
-#pragma unroll
-            for (int q = 0; q < PB / 2; q++) { const double2 v = ar[q]; a[2 * q] = v.x; a[2 * q + 1] = v.y; }
-            // pivots of the y row / identity padding are 1; a non-positive pivot is replaced by 1 and remembered
-            // (branch-free, so that ptxas can overlap the 1/sqrt chain with the rank-1 update of the previous column)
-            int first_bad = PB;
-            auto pivot = [&](double d, int c) {
-                const bool pad = g0 + p * PB + c >= n_real;
-                const bool bad = !pad && !(d > 0.0);
-                first_bad = (bad && c < first_bad) ? c : first_bad;
-                return (pad || bad) ? 1.0 : d;
-            };
-            double d = pivot(__shfl_sync(0xffffffffu, a[0], 0), 0);
-            double rs = pd_rsqrt(d);
-#pragma unroll
-            for (int c = 0; c < PB; c++) {
-                double* cb = colbuf + (c & 1) * PB;
-                a[c] = (lane == c) ? d * rs : a[c] * rs;
-                if (lane == c) rdiag[p * PB + c] = rs;
-                cb[lane] = a[c];
-                __syncwarp();
-                double rs_next = 0.0, d_next = 0.0;
-                if (c + 1 < PB) {
-                    // lane c+1 owns both numbers the next pivot needs
-                    const double tmp = fma(-a[c], a[c], a[c + 1]);
-                    d_next = pivot(__shfl_sync(0xffffffffu, tmp, c + 1), c + 1);
-                    rs_next = pd_rsqrt(d_next);
-                }
-#pragma unroll
-                for (int c2 = (c + 1) & ~1; c2 < PB; c2 += 2) {
-                    const double2 l = *reinterpret_cast<const double2*>(cb + c2);
-                    if (c2 > c) a[c2] = fma(-a[c], l.x, a[c2]);
-                    a[c2 + 1] = fma(-a[c], l.y, a[c2 + 1]);
-                }
-                d = d_next;
-                rs = rs_next;
-            }
-            if (first_bad < PB && lane == 0) atomicCAS(info, 0, (int)(g0 + p * PB + first_bad + 1));
-            double* wr = Lpp + lane * PB_LD;
-#pragma unroll
-            for (int c = 0; c < PB; c++) wr[c] = (c <= lane) ? a[c] : 0.0;
-        }
-        __syncthreads();
-        PD_CLK();
-
-        // ---- inv32 (warp 0: column `lane` of inv(L_pp)) || trsm32 (warps 1..3-p: rows of the sub-blocks below)
-        if (warp == 0) {
-            double b[PB];
-#pragma unroll
-            for (int k = 0; k < PB; k++) b[k] = (k == lane) ? 1.0 : 0.0;
-#pragma unroll
-            for (int k = 0; k < PB; k++) {
-                b[k] *= rdiag[p * PB + k];
-#pragma unroll
-                for (int r = k + 1; r < PB; r++) b[r] = fma(-Lpp[r * PB_LD + k], b[k], b[r]);
-            }
-            double* X = Xd + p * PB_SZ;
-            double* XT = Xt + pd_blk(p, p) * PB_SZ;
-            double* G = Dinv + (int64_t)(p * PB) * TILE + p * PB;
-#pragma unroll
-            for (int r = 0; r < PB; r++) {       // X[r][c = lane]; exact zeros above the diagonal
-                X[r * PB_LD + lane] = b[r];
-                G[r * TILE + lane] = b[r];
-            }
-            if (!SMALL) {
-                double2* wt = reinterpret_cast<double2*>(XT + lane * PB_LD);
-#pragma unroll
-                for (int q = 0; q < PB / 2; q++) wt[q] = make_double2(b[2 * q], b[2 * q + 1]);
-            }
-        } else if (warp <= 3 - p) {
-            const int i = p + warp;
-            double* Lip = Lb + pd_blk(i, p) * PB_SZ;
-            double x[PB];
-            const double2* ar = reinterpret_cast<const double2*>(Lip + lane * PB_LD);
-#pragma unroll
-            for (int q = 0; q < PB / 2; q++) { const double2 v = ar[q]; x[2 * q] = v.x; x[2 * q + 1] = v.y; }
-#pragma unroll
-            for (int k = 0; k < PB; k++) {
-                x[k] *= rdiag[p * PB + k];
-#pragma unroll
-                for (int c = k + 1; c < PB; c++) x[c] = fma(-Lpp[c * PB_LD + k], x[k], x[c]);
-            }
-            double2* wr = reinterpret_cast<double2*>(Lip + lane * PB_LD);
-#pragma unroll
-            for (int q = 0; q < PB / 2; q++) wr[q] = make_double2(x[2 * q], x[2 * q + 1]);
-        }
-        __syncthreads();
-        PD_CLK();
-
-        // ---- trailing update inside the block: C_ij -= L_ip L_jp^T for p < j <= i, 4 column units per product
-        {
-            const int m = 3 - p;                      // sub-blocks below
-            const int n_units = m * (m + 1) / 2 * 4;
-            for (int u = warp; u < n_units; u += NW) {
-                const int op = u >> 2, chunk = u & 3;
-                const int ii = (op >= 3) ? 2 : (op >= 1) ? 1 : 0;
-                const int jj = op - ii * (ii + 1) / 2;
-                const int i = p + 1 + ii, j = p + 1 + jj;
-                pd_unit<0, false>(Lb + pd_blk(i, j) * PB_SZ, Lb + pd_blk(i, p) * PB_SZ, Lb + pd_blk(j, p) * PB_SZ, nullptr,
-                                  nullptr, chunk * 8, lane);
-            }
-        }
-        __syncthreads();
-        PD_CLK();
-    }
-
-    // ---- factor back to global (lower triangle only); overlaps with stage A below (Lb is read-only from here on)
-#pragma unroll
-    for (int q = 0; q < PD_NBLK * PB / NW; q++) {
-        const int pr = warp + q * NW, b = pr >> 5, r = pr & 31;
-        const int bi = (b >= 6) ? 3 : (b >= 3) ? 2 : (b >= 1) ? 1 : 0;
-        const int bj = b - bi * (bi + 1) / 2;
-        if (bi != bj || lane <= r) {
-            const double v = Lb[b * PB_SZ + r * PB_LD + lane];
-            Ab[(int64_t)(bi * PB + r) * ld + bj * PB + lane] = v;
-            if (Lpack) Lpack[(bi * PB + r) * TILE + bj * PB + lane] = v;   // contiguous copy for the multi-GPU broadcast
-        }
-    }
-    PD_CLK();
-
-    // ---- assemble inv(L):  X_ij = -X_ii T_ij,  T_ij = sum_{k=j..i-1} L_ik X_kj.  T_ij lives (transposed) where X_ij
-    // will go; a unit only ever touches its own 8 columns of a sub-block, so the in-place steps are race-free.
-    auto L = [&](int i, int j) { return Lb + pd_blk(i, j) * PB_SZ; };
-    auto GD = [&](int i, int j) { return Dinv + (int64_t)(i * PB) * TILE + j * PB; };
-    if (SMALL) {
-        // No room for the 10 transposed blocks: block column 0 of the inverse is assembled first in the four diagonal slots of Lb
-        // (dead once the factor is in global memory), then block columns 1 and 2 together in those slots plus the slot of L_10
-        // (dead once column 0 is done).  Every product is the same pd_unit call, on the same operands, in the same order as in
-        // the full-size path below, so factor and inverse are bit-identical; only the number of barriers grows (11 instead of 5).
-        __syncthreads();                                   // the write-back above still reads the diagonal slots
-        double* S0 = L(0, 0); double* S1 = L(1, 1); double* S2 = L(2, 2); double* S3 = L(3, 3); double* S4 = L(1, 0);
-        auto transpose_into = [&](double* dst, const double* src) {   // dst[c][r] = src[r][c]
-            for (int r = warp; r < PB; r += NW) dst[lane * PB_LD + r] = src[r * PB_LD + lane];
-        };
-        auto units = [&](int n_units, auto&& f) { for (int u = warp; u < n_units; u += NW) f(u >> 2, (u & 3) * 8); };
-        // --- block column 0: XT00 -> S0, X10 -> S1, X20 -> S2, X30 -> S3
-        transpose_into(S0, Xd);
-        __syncthreads();
-        units(12, [&](int b, int c0) {                      // T_i0 = L_i0 X_00, i = 1..3
-            double* dst = b == 0 ? S1 : (b == 1 ? S2 : S3);
-            pd_unit<1, true>(dst, L(b + 1, 0), S0, nullptr, nullptr, c0, lane);
-        });
-        __syncthreads();
-        units(4, [&](int, int c0) { pd_unit<3, true>(S1, Xd + 1 * PB_SZ, S1, nullptr, nullptr, c0, lane, GD(1, 0), TILE); });   // X_10
-        __syncthreads();
-        units(4, [&](int, int c0) { pd_unit<2, true>(S2, L(2, 1), S1, nullptr, nullptr, c0, lane); });                          // T_20 += L_21 X_10
-        __syncthreads();
-        units(4, [&](int, int c0) { pd_unit<3, true>(S2, Xd + 2 * PB_SZ, S2, nullptr, nullptr, c0, lane, GD(2, 0), TILE); });   // X_20
-        __syncthreads();
-        if (warp < 4) {                                     // T_30 += L_31 X_10 + L_32 X_20 ;  X_30
-            pd_unit<2, true>(S3, L(3, 1), S1, L(3, 2), S2, warp * 8, lane);
-            __syncwarp();
-            pd_unit<3, true>(S3, Xd + 3 * PB_SZ, S3, nullptr, nullptr, warp * 8, lane, GD(3, 0), TILE);
-        }
-        __syncthreads();
-        // --- block columns 1 and 2: XT11 -> S0, XT22 -> S1, X21 -> S2, X31 -> S3, X32 -> S4
-        transpose_into(S0, Xd + 1 * PB_SZ);
-        transpose_into(S1, Xd + 2 * PB_SZ);
-        __syncthreads();
-        units(12, [&](int b, int c0) {                      // T_21 = L_21 X_11, T_31 = L_31 X_11, T_32 = L_32 X_22
-            if (b == 0) pd_unit<1, true>(S2, L(2, 1), S0, nullptr, nullptr, c0, lane);
-            else if (b == 1) pd_unit<1, true>(S3, L(3, 1), S0, nullptr, nullptr, c0, lane);
-            else pd_unit<1, true>(S4, L(3, 2), S1, nullptr, nullptr, c0, lane);
-        });
-        __syncthreads();
-        units(8, [&](int b, int c0) {                       // X_21, X_32
-            if (b == 0) pd_unit<3, true>(S2, Xd + 2 * PB_SZ, S2, nullptr, nullptr, c0, lane, GD(2, 1), TILE);
-            else pd_unit<3, true>(S4, Xd + 3 * PB_SZ, S4, nullptr, nullptr, c0, lane, GD(3, 2), TILE);
-        });
-        __syncthreads();
-        units(4, [&](int, int c0) { pd_unit<2, true>(S3, L(3, 2), S2, nullptr, nullptr, c0, lane); });                          // T_31 += L_32 X_21
-        __syncthreads();
-        units(4, [&](int, int c0) { pd_unit<3, true>(S3, Xd + 3 * PB_SZ, S3, nullptr, nullptr, c0, lane, GD(3, 1), TILE); });   // X_31
-        PD_CLK();
-    } else {
-    auto XT = [&](int i, int j) { return Xt + pd_blk(i, j) * PB_SZ; };
-    // stage A: T_ij = L_ij X_jj for all i > j (6 products, 24 units)
-    for (int u = warp; u < 24; u += NW) {
-        const int op = u >> 2, chunk = u & 3;
-        const int i = op < 1 ? 1 : (op < 3 ? 2 : 3);
-        const int j = op - (i == 1 ? 0 : (i == 2 ? 1 : 3));
-        pd_unit<1, true>(XT(i, j), L(i, j), XT(j, j), nullptr, nullptr, chunk * 8, lane);
-    }
-    __syncthreads();
-    // stage B: X_{j+1,j} = -X_{j+1,j+1} T_{j+1,j}
-    for (int u = warp; u < 12; u += NW) {
-        const int j = u >> 2, chunk = u & 3;
-        pd_unit<3, true>(XT(j + 1, j), Xd + (j + 1) * PB_SZ, XT(j + 1, j), nullptr, nullptr, chunk * 8, lane, GD(j + 1, j), TILE);
-    }
-    __syncthreads();
-    // stage C1: T_{j+2,j} += L_{j+2,j+1} X_{j+1,j}
-    for (int u = warp; u < 8; u += NW) {
-        const int j = u >> 2, chunk = u & 3;
-        pd_unit<2, true>(XT(j + 2, j), L(j + 2, j + 1), XT(j + 1, j), nullptr, nullptr, chunk * 8, lane);
-    }
-    __syncthreads();
-    // stage C2: X_{j+2,j} = -X_{j+2,j+2} T_{j+2,j}
-    for (int u = warp; u < 8; u += NW) {
-        const int j = u >> 2, chunk = u & 3;
-        pd_unit<3, true>(XT(j + 2, j), Xd + (j + 2) * PB_SZ, XT(j + 2, j), nullptr, nullptr, chunk * 8, lane, GD(j + 2, j), TILE);
-    }
-    __syncthreads();
-    // stage D: T_30 += L_31 X_10 + L_32 X_20 ; X_30 = -X_33 T_30
-    if (warp < 4) {
-        pd_unit<2, true>(XT(3, 0), L(3, 1), XT(1, 0), L(3, 2), XT(2, 0), warp * 8, lane);
-        __syncwarp();
-        pd_unit<3, true>(XT(3, 0), Xd + 3 * PB_SZ, XT(3, 0), nullptr, nullptr, warp * 8, lane, GD(3, 0), TILE);
-    }
-    PD_CLK();
-    }
-#undef PD_CLK
-    if (sig.n_peers > 0) {
-        // multi-GPU, peer-memory exchange: L_kk / inv(L_kk) are complete in this GPU's memory; tell every peer (they pull)
-        __threadfence_system();
-        __syncthreads();
-        if (tid == 0)
-            for (int pr = 0; pr < sig.n_peers; pr++) atomicAdd_system(sig.peerFlag[pr], 1u);
-    }
-}
-
-__global__ void __launch_bounds__(PDS_THREADS, 2)   // 2: caps the kernel at 128 registers, i.e. half a register file per CTA
-potrf_diag_small_kernel(double* __restrict__ A, int64_t ld, int64_t g0, int64_t n_real, double* __restrict__ Dinv,
-                        int* __restrict__ info, double* __restrict__ Lpack = nullptr, PushArgs sig = PushArgs{},
-                        long long* __restrict__ clk = nullptr) {
-    potrf_diag_body<true>(A, ld, g0, n_real, Dinv, info, Lpack, sig, clk);
-}
-
 // Spin (bounded) until a counter in local memory, bumped by peer GPUs over NVLink, reaches `expected`.
 __device__ __forceinline__ void wait_counter(const unsigned* flag, unsigned expected) {
     const volatile unsigned* f = flag;
@@ -668,7 +386,6 @@ __global__ void mll_terms_kernel(const double* __restrict__ A, int64_t ld, int64
 inline cudaError_t cholesky_configure() {
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD_SMEM)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(potrf_diag_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PDS_SMEM)) != cudaSuccess) return e;
     if ((e = dgemm_nt_configure<128, 64, GM_SUB>()) != cudaSuccess) return e;
     if ((e = dgemm_nt_configure<64, 128, GM_SET>()) != cudaSuccess) return e;
     if ((e = dgemm_nt_configure<64, 128, GM_SET_PUSH>()) != cudaSuccess) return e;
@@ -833,13 +550,7 @@ inline int factor_steps(gb2_handle* h, int k0, int k1, int col_limit) {
         const bool p2p = G > 1 && h->p2p_ready;
         // counters of this block step in the current parity buffer: [0] = diagonal block announced, [1] = panel tiles landed
         const size_t fl = ((size_t)h->p2p_parity * 2) * h->p2p_nbmax + k;
-        // green_sms: the diagonal kernel runs on its own SM partition (stream s_diag); two event edges tie it into the chain
-        cudaStream_t sd = (h->s_diag && G == 1) ? h->s_diag : sp;
-        if (sd != sp) {
-            cudaEvent_t e = pool_event(h, 4 * nb + 8 + 2 * k);
-            cudaEventRecord(e, sp);
-            cudaStreamWaitEvent(sd, e, 0);
-        }
+        cudaStream_t sd = sp;
         trace_stamp(h, sd, k, 0);
         if (owner == me) {
             PushArgs sig{};
@@ -848,15 +559,9 @@ inline int factor_steps(gb2_handle* h, int k0, int k1, int col_limit) {
                     if (r != me) sig.peerFlag[q++] = h->peerFlags[r] + fl;
                 sig.n_peers = G - 1;
             }
-            if (h->opt_small_diag) potrf_diag_small_kernel<<<1, PDS_THREADS, PDS_SMEM, sd>>>(A, ld, g0, h->N, Dk, h->dInfo, Lk, sig);
-            else potrf_diag_kernel<<<1, PD_THREADS, PD_SMEM, sd>>>(A, ld, g0, h->N, Dk, h->dInfo, Lk, sig);
+            potrf_diag_kernel<<<1, PD_THREADS, PD_SMEM, sd>>>(A, ld, g0, h->N, Dk, h->dInfo, Lk, sig);
             launches++;
             trace_stamp(h, sd, k, 1);
-            if (sd != sp) {
-                cudaEvent_t e = pool_event(h, 4 * nb + 9 + 2 * k);
-                cudaEventRecord(e, sd);
-                cudaStreamWaitEvent(sp, e, 0);
-            }
         } else if (p2p) {
             pull_diag_kernel<<<32, 256, 0, sp>>>(h->dFlags + fl, 1u, h->peerDinv[owner] + (int64_t)k * TILE * TILE,
                                                  h->peerLpack[owner] + (int64_t)k * TILE * TILE, Dk, Lk, A + g0 * ld + g0, ld);
@@ -1208,8 +913,8 @@ inline int cholesky_enqueue(gb2_handle* h) {
             g.a_k0 = 0; g.b_row0 = c1 * TILE; g.b_k0 = 0;
             tc::gemm_tf32x3_launch(sm, h->n_sm, h->mPhi, h->mPlo, h->mPhi, h->mPlo, g, (int)cols, launches);
         }
-    } else if (h->opt_fp64_panel > 1 && h->world == 1 && nb > h->opt_fp64_panel) {
-        // Two-level blocking (option "fp64_panel" = pw, off by default).  The plain algorithm applies every 128-column panel to the
+    } else if (h->fp64_panel() > 1 && h->world == 1 && nb > h->fp64_panel() && h->ext_rows == 0) {
+        // Two-level blocking (option "fp64_panel" = pw; default: auto, see gb2_handle::fp64_panel).  The plain algorithm applies every 128-column panel to the
         // whole trailing matrix: N/128 read-modify-write passes of depth 128 (87 % tensor-pipe activity, prologue/epilogue bound).
         // Here pw column blocks are factored as one panel (factor_steps restricted to the panel's own columns, exactly what the
         // tf32 path does), then applied to the trailing matrix by ONE update of depth pw*128 -- split in two so that the next panel
@@ -1222,7 +927,7 @@ inline int cholesky_enqueue(gb2_handle* h) {
             cudaStreamCreateWithPriority(&h->s_bulk2, cudaStreamNonBlocking, lo_p);
         }
         cudaStream_t sb = h->s_bulk2;
-        const int pw2 = h->opt_fp64_panel, ev0 = 6 * nb + 32;
+        const int pw2 = h->fp64_panel(), ev0 = 6 * nb + 32;
         double* A = h->dA;
         int g = 0;
         for (int c0 = 0; c0 < nb; c0 += pw2, g++) {

@@ -284,6 +284,11 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
     const uint32_t b_base = tc::smem_u32(base) + (uint32_t)(BM * 128 + (wn * WN + g) * 128);
 
     uint32_t c_g = 0;        // k-tiles consumed so far (same sequence as the producer's)
+    if (c_cg & 4) {   // diagnostic: hold the first TMA load back by ~20 us
+        const long long t0 = clock64();
+        while (clock64() - t0 < 40000) {}
+        __syncthreads();
+    }
     if (tid == 0) produce(GT_STAGES - 1);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         int bj, kt0; int64_t grow, lrow;
@@ -314,6 +319,8 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
 #pragma unroll
                     for (int ni = 0; ni < NI; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
             }
+            // this warp's generic-proxy reads of the stage are ordered before the async-proxy (TMA) write that refills it
+            if (c_cg & 8) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(empty + st);
         }

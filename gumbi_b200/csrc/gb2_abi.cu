@@ -318,7 +318,6 @@ static F driver_fn(const char* name) {
 extern "C" {
 
 static void p2p_close(gb2_handle* h);
-static void green_close(gb2_handle* h);
 
 int gb2_abi_version(void) { return GB2_ABI_VERSION; }
 
@@ -421,14 +420,12 @@ int gb2_destroy(gb2_handle* h) {
     cudaSetDevice(h->device);
     cudaFree(h->dFitc); cudaFree(h->dSt); cudaFree(h->dFitcScal);
     if (h->dTrace) cudaFree(h->dTrace);
-    if (h->s_diag) cudaStreamDestroy(h->s_diag);
     if (h->s_bulk2) cudaStreamDestroy(h->s_bulk2);
     for (auto st : h->s_aux) if (st) cudaStreamDestroy(st);
     for (auto ev : h->ev_join) if (ev) cudaEventDestroy(ev);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->s_main) cudaStreamDestroy(h->s_main);
     if (h->s_panel) cudaStreamDestroy(h->s_panel);
-    green_close(h);   // after the streams that live in the green contexts
     delete h;
     return 0;
 }
@@ -614,70 +611,6 @@ static int p2p_setup(gb2_handle* h) {
         return 0;
     }
     h->p2p_ready = true;
-    return 0;
-}
-
-// ---- SM partition for the diagonal-panel kernel (CUDA green contexts, driver API resolved through the runtime) ---------------
-// The diagonal kernel needs a whole SM (222 KB of shared memory, 512 x 128 registers); the bulk trailing update keeps every SM
-// full and refills every slot that frees, so without a partition the diagonal kernel of step k waits until the bulk update of
-// step k-1 has drained and the look-ahead overlaps nothing.  With "green_sms" = R the device is split into R SMs for s_diag and
-// the rest for s_main / s_panel (both re-created as green-context streams).  Single GPU only; measurement option, off by default.
-static void green_close(gb2_handle* h) {
-    if (!h->green_a && !h->green_b) return;
-    auto fDestroy = driver_fn<CUresult (*)(CUgreenCtx)>("cuGreenCtxDestroy");
-    if (fDestroy) {
-        if (h->green_a) fDestroy((CUgreenCtx)h->green_a);
-        if (h->green_b) fDestroy((CUgreenCtx)h->green_b);
-    }
-    h->green_a = h->green_b = nullptr;
-}
-
-static int green_setup(gb2_handle* h, int sms) {
-    GB2_ARG(h, h->world == 1, "green_sms is a single-GPU option");
-    GB2_ARG(h, !h->green_a, "green_sms is already active on this handle");
-    GB2_ARG(h, sms >= 8 && sms <= 64 && sms % 8 == 0, "green_sms must be a multiple of 8 in [8, 64]");
-    auto fDeviceGet = driver_fn<CUresult (*)(CUdevice*, int)>("cuDeviceGet");
-    auto fGetRes = driver_fn<CUresult (*)(CUdevice, CUdevResource*, CUdevResourceType)>("cuDeviceGetDevResource");
-    auto fSplit = driver_fn<CUresult (*)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int)>(
-        "cuDevSmResourceSplitByCount");
-    auto fDesc = driver_fn<CUresult (*)(CUdevResourceDesc*, CUdevResource*, unsigned int)>("cuDevResourceGenerateDesc");
-    auto fCreate = driver_fn<CUresult (*)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int)>("cuGreenCtxCreate");
-    auto fStream = driver_fn<CUresult (*)(CUstream*, CUgreenCtx, unsigned int, int)>("cuGreenCtxStreamCreate");
-    if (!fDeviceGet || !fGetRes || !fSplit || !fDesc || !fCreate || !fStream) {
-        h->err = "green contexts are not available in this driver";
-        return -2;
-    }
-    GB2_CUDA(h, cudaSetDevice(h->device));
-    GB2_CUDA(h, cudaFree(nullptr));   // primary context up
-#define GB2_CU(call) do { CUresult r_ = (call); if (r_ != CUDA_SUCCESS) { h->err = std::string(#call) + " failed: CUresult " + std::to_string((int)r_); return -2; } } while (0)
-    CUdevice dev;
-    GB2_CU(fDeviceGet(&dev, h->device));
-    CUdevResource all, part, rest;
-    GB2_CU(fGetRes(dev, &all, CU_DEV_RESOURCE_TYPE_SM));
-    unsigned int groups = 1;
-    GB2_CU(fSplit(&part, &groups, &all, &rest, 0, (unsigned int)sms));
-    if (groups != 1 || rest.sm.smCount == 0) { h->err = "SM split did not yield a partition and a remainder"; return -2; }
-    CUdevResourceDesc da, db;
-    GB2_CU(fDesc(&da, &part, 1));
-    GB2_CU(fDesc(&db, &rest, 1));
-    CUgreenCtx ga, gb;
-    GB2_CU(fCreate(&ga, da, dev, CU_GREEN_CTX_DEFAULT_STREAM));
-    GB2_CU(fCreate(&gb, db, dev, CU_GREEN_CTX_DEFAULT_STREAM));
-    int lo, hi;
-    GB2_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    CUstream sd, sm, sp;
-    GB2_CU(fStream(&sd, ga, CU_STREAM_NON_BLOCKING, hi));
-    GB2_CU(fStream(&sm, gb, CU_STREAM_NON_BLOCKING, lo));
-    GB2_CU(fStream(&sp, gb, CU_STREAM_NON_BLOCKING, hi));
-#undef GB2_CU
-    GB2_CUDA(h, cudaStreamSynchronize(h->s_main));
-    GB2_CUDA(h, cudaStreamSynchronize(h->s_panel));
-    cudaStreamDestroy(h->s_main);
-    cudaStreamDestroy(h->s_panel);
-    h->s_main = (cudaStream_t)sm; h->s_panel = (cudaStream_t)sp; h->s_diag = (cudaStream_t)sd;
-    h->green_a = ga; h->green_b = gb;
-    h->green_sms_a = (int)part.sm.smCount; h->green_sms_b = (int)rest.sm.smCount;
-    h->factorized = false;
     return 0;
 }
 
@@ -1349,28 +1282,11 @@ int gb2_set_option(gb2_handle* h, const char* name, int value) {
         return 0;
     }
     if (!strcmp(name, "fp64_panel")) {   // two-level blocking of the fp64 factorisation: column blocks per panel (0/1 = plain algorithm)
-        GB2_ARG(h, value >= 0 && value <= 16, "fp64_panel must be in [0, 16]");
+        GB2_ARG(h, value >= -1 && value <= 16, "fp64_panel must be in [-1, 16] (-1 = auto)");
         h->opt_fp64_panel = value;
         h->factorized = false;
         return 0;
     }
-    if (!strcmp(name, "small_diag")) {   // small-footprint diagonal-panel kernel (bit-identical results)
-        h->opt_small_diag = value ? 1 : 0;
-        if (value) {
-            // Co-residence needs more than the sum of the footprints: an SM keeps ONE shared-memory carveout while it has resident
-            // CTAs, and the driver sizes it for the kernel that got there first (2 x 93 KB GEMM CTAs -> 196 KB, which leaves 103 KB
-            // beside one of them).  Asking for the maximum carveout on the GEMMs of the factorisation and on the small kernel makes
-            // every SM they touch 228 KB wide, so that 131.6 KB fit beside one GEMM CTA.  (A process-wide hint: function attributes.)
-            GB2_CUDA(h, cudaSetDevice(h->device));
-            const int mx = (int)cudaSharedmemCarveoutMaxShared;
-            GB2_CUDA(h, cudaFuncSetAttribute(potrf_diag_small_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
-            GB2_CUDA(h, cudaFuncSetAttribute(dgemm_nt_kernel<128, 64, GM_SUB>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
-            GB2_CUDA(h, cudaFuncSetAttribute(dgemm_nt_kernel<64, 128, GM_SET>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
-            GB2_CUDA(h, cudaFuncSetAttribute(dgemm_nt_kernel<64, 128, GM_SET_PUSH>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
-        }
-        return 0;
-    }
-    if (!strcmp(name, "green_sms")) return value == 0 ? 0 : green_setup(h, value);
     if (!strcmp(name, "trace")) {   // timeline stamps around the kernels of every block step (gb2_get_trace); measurement aid
         if (!value) { if (h->dTrace) cudaFree(h->dTrace); h->dTrace = nullptr; h->trace_cap = 0; return 0; }
         const int64_t want = (int64_t)TRACE_SLOTS * 4096;     // up to 4096 block steps (N <= 524k)

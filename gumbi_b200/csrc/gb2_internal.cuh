@@ -149,14 +149,14 @@ struct gb2_handle {
     double* ext_At = nullptr; int64_t ext_rows = 0, ext_ld = 0; int ext_ncols = 0;
     // "trace" option: %globaltimer stamps around the kernels of every block step of factor_steps (6 per step), see gb2_get_trace
     unsigned long long* dTrace = nullptr; int64_t trace_cap = 0; int trace_steps = 0;
-    // "green_sms" option: SM partition (CUDA green contexts) -- s_diag runs the diagonal-panel kernel on its own few SMs, s_main and
-    // s_panel are re-created on the remaining ones, so that the 222 KB / 64k-register diagonal kernel never waits for an empty SM
-    cudaStream_t s_diag = nullptr; void* green_a = nullptr; void* green_b = nullptr; int green_sms_a = 0, green_sms_b = 0;
     // two-level blocking of the fp64 factorisation (single GPU): panels of opt_fp64_panel column blocks, one deep DMMA update per panel
-    int opt_fp64_panel = 0; cudaStream_t s_bulk2 = nullptr;
-    int opt_small_diag = 0;      // diagonal-panel kernel variant that fits on an SM beside a GEMM CTA (256 threads, 130 KB) instead of needing an empty SM
+    // -1 = auto: 16 from Np >= 16384 (measured, profiles/r02j/r02k_bench_c4_*: Cholesky at N = 32768 432.6 ms plain, 405 / 390 / 383 / 380 ms
+    // with panels of 2 / 4 / 8 / 16), plain below (N = 8192: 9.21 ms plain, 9.44 / 9.53 with 2 / 4)
+    int opt_fp64_panel = -1; cudaStream_t s_bulk2 = nullptr;
+    int fp64_panel() const { return opt_fp64_panel >= 0 ? opt_fp64_panel : (Np >= 16384 ? 16 : 0); }
     int opt_fused_group = 4;     // fused cold predict: column blocks per bulk update of the prediction rows (1, 2, 4, 8)
-    int opt_solve_streams = 1;   // fp64 predict solve: split the prediction rows over this many concurrent streams (wave-tail filling)
+    int opt_solve_streams = 4;   // fp64 predict solve: split the prediction rows over this many concurrent streams (wave-tail filling);
+                                 // measured (profiles/r02j_bench_*): C2 solve 24.28 / 22.97 / 22.83 ms, C4 345.3 / 339.0 / 336.9 ms with 1 / 2 / 4
     cudaStream_t s_aux[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
 

@@ -243,70 +243,6 @@ def test_timeline_trace_is_ordered(lib_built):
     e.close()
 
 
-def test_sm_partition_for_the_diagonal_kernel_keeps_the_numbers(lib_built):
-    """set_option("green_sms", 8): the diagonal-panel kernel runs on its own SM partition (green contexts), everything else on the
-    remaining SMs -- same kernels, same arithmetic: factor and posterior are bit-identical.  Skipped where the driver lacks the API."""
-    from gumbi_b200 import GPEngine
-    from oracle import gp_oracle as orc
-
-    spec, X, y, Xs = orc.synthetic_problem(900, 3, M_res=15)
-    ref = GPEngine()
-    ref.set_train(X, y)
-    ref.set_kernel(spec)
-    ref.factorize()
-    L0, p0 = ref.get_L(), ref.predict(Xs)
-    ref.close()
-    e = GPEngine()
-    try:
-        e.set_option("green_sms", 8)
-    except RuntimeError as err:
-        e.close()
-        pytest.skip(f"green contexts unavailable: {err}")
-    e.set_train(X, y)
-    e.set_kernel(spec)
-    e.factorize()
-    assert np.array_equal(e.get_L(), L0)
-    p1 = e.predict(Xs)
-    assert np.array_equal(p1[0], p0[0]) and np.array_equal(p1[1], p0[1])
-    mu, var = e.factorize_predict(Xs, True)
-    np.testing.assert_allclose(mu, p0[0], rtol=1e-9, atol=1e-10)
-    with pytest.raises(ValueError):
-        e.set_option("green_sms", 8)                               # already active
-    e.close()
-
-
-def test_small_footprint_diagonal_kernel_is_bit_identical(lib_built):
-    """set_option("small_diag", 1): the 256-thread / 130 KB diagonal-panel kernel performs the same block products in the same
-    order as the default one -> identical factor, identical inverse blocks (seen through the predictions), identical pivot report."""
-    from gumbi_b200 import GPEngine
-    from oracle import gp_oracle as orc
-
-    for n, d in ((900, 3), (127, 1), (515, 2)):
-        spec, X, y, Xs = orc.synthetic_problem(n, d, M_res=15 if d >= 2 else 60)
-        e = GPEngine()
-        e.set_train(X, y)
-        e.set_kernel(spec)
-        e.factorize()
-        L0, v0, p0, m0 = e.get_L(), e.get_v(), e.predict(Xs), e.mll()
-        e.set_option("small_diag", 1)
-        e.factorize()
-        assert np.array_equal(e.get_L(), L0) and np.array_equal(e.get_v(), v0) and e.mll() == m0
-        p1 = e.predict(Xs)
-        assert np.array_equal(p1[0], p0[0]) and np.array_equal(p1[1], p0[1])
-        e.close()
-    spec, X, y, _ = orc.synthetic_problem(200, 2)
-    spec["sigma"] = 0.0
-    spec["jitter"] = 0.0
-    X[150] = X[40]
-    e = GPEngine()
-    e.set_option("small_diag", 1)
-    e.set_train(X, y)
-    e.set_kernel(spec)
-    with pytest.raises(np.linalg.LinAlgError, match="not positive definite"):
-        e.factorize()
-    e.close()
-
-
 @pytest.mark.parametrize("pw", [2, 4])
 def test_two_level_blocking_of_the_fp64_factorisation(lib_built, pw):
     """set_option("fp64_panel", pw): panels of pw column blocks, one deep update per panel (split: next panel's columns / the rest on a

@@ -27,13 +27,9 @@ e.set_train(X, y)
 e.set_kernel(spec)
 for name, opts, fused in (("look-ahead (default)", {}, False), ("look-ahead off", {"lookahead": 0}, False),
                           ("fused cold predict, group 4", {}, True), ("fused cold predict, group 1", {"fused_group": 1}, True),
-                          ("look-ahead + small-footprint diagonal kernel", {"small_diag": 1}, False),
-                          ("fused cold predict, group 4 + small-footprint diagonal kernel", {"small_diag": 1}, True),
-                          # from here on the handle keeps its SM partition (green contexts cannot be undone on a handle)
-                          ("look-ahead + 8 SMs reserved for the diagonal kernel", {"green_sms": 8}, False),
-                          ("fused cold predict, group 4 + 8 SMs reserved", {}, True)):
+                          ("two-level blocking, panel of 4", {"fp64_panel": 4}, False)):
     try:
-        for k, v in {"lookahead": 1, "fused_group": 4, "small_diag": 0, **opts}.items():
+        for k, v in {"lookahead": 1, "fused_group": 4, "fp64_panel": 0, **opts}.items():
             e.set_option(k, v)
     except RuntimeError as err:
         print(json.dumps({"config": name, "unavailable": str(err)}), flush=True)

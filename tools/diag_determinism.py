@@ -58,7 +58,8 @@ def run(N, d, kind, reps, full):
     e.close()
 
 
-CONFIGS = [("cp.async (reference)", {"dgemm_tma": 0}), ("tma: SET products only", {"dgemm_tma": 9})  # 9 & 7 = 1 (the value 1 itself means "all"), ("tma: next-column SUB only", {"dgemm_tma": 2}),
+# dgemm_tma is a usage mask; the value 1 means "all" (= 7), so "SET only" is written 9 (9 & 7 = 1)
+CONFIGS = [("cp.async (reference)", {"dgemm_tma": 0}), ("tma: SET products only", {"dgemm_tma": 9}), ("tma: next-column SUB only", {"dgemm_tma": 2}),
            ("tma: bulk SUB only", {"dgemm_tma": 4}), ("tma: all", {"dgemm_tma": 7})]
 
 if __name__ == "__main__":

@@ -94,8 +94,111 @@ static int check_mode(int reps) {
     return rc;
 }
 
+// "pipeline" mode: the bulk trailing update exactly as the factorisation issues it (same pointer arithmetic into ONE matrix, rb_first,
+// col_off, lower tile list), in three settings:  static = operands untouched between launches;  fresh = the panel (column block k) is
+// re-written by a copy kernel right before each update (same stream);  concurrent = a second stream keeps re-writing column block
+// k+1 (which the update neither reads nor writes) while the update runs.  TMA-staged result vs cp.async result, exact data.
+__global__ void copy_cols_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t ld, int64_t rows, int64_t c0, int ncols) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * ncols; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / ncols, c = c0 + i % ncols;
+        dst[r * ld + c] = src[r * ld + c];
+    }
+}
+__global__ void empty_kernel() {}
+static int pipeline_mode(int reps) {
+    const int64_t nb = 40, Np = nb * 128, ld = Np;            // 5120 x 5120, row stride not a power of two
+    double *M0, *M, *Mref;
+    cudaMalloc(&M0, Np * ld * 8); cudaMalloc(&M, Np * ld * 8); cudaMalloc(&Mref, Np * ld * 8);
+    std::vector<double> h((size_t)Np * ld), ref((size_t)Np * ld), got((size_t)Np * ld);
+    for (size_t i = 0; i < h.size(); i++) h[i] = (double)((i * 2654435761u) >> 8 & 0xffff) / 65536.0 - 0.5;
+    cudaMemcpy(M0, h.data(), h.size() * 8, cudaMemcpyHostToDevice);
+    cudaStream_t s1, s2;
+    cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking); cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
+    dgemm_nt_configure<128, 64, GM_SUB>();
+    int rc = 0;
+    auto update = [&](cudaStream_t s, double* A, int k) {
+        const int64_t g0 = (int64_t)k * 128;
+        const int c2 = (int)(nb - (k + 2));
+        dgemm_nt_launch<128, 64, GM_SUB>(s, A + g0, ld, A + (g0 + 256) * ld + g0, ld, A + g0 + 256, ld, (int64_t)c2 * 128, (int64_t)c2 * 128, 128, 1, 0,
+                                         g0 + 256, k + 2, 1);
+    };
+    const char* names[] = {"static operands", "panel re-written by a copy kernel right before the update", "neighbour column re-written concurrently",
+                           "EMPTY kernel right before the update", "copy kernel writes ANOTHER matrix right before", "copy kernel, stream sync, update",
+                           "panel re-written right before, one CTA per tile", "panel re-written right before, persistent without cross-tile prefetch",
+                           "panel re-written right before, 20 us delay before the first TMA load",
+                           "copy kernel writes ANOTHER matrix right before, consumer-side fence.proxy.async.shared::cta", "panel re-written right before, consumer-side fence"};
+    for (int setting = (reps > 12 ? 4 : 0); setting < 11; setting++) {
+        if (reps > 12 && (setting == 6 || setting == 7 || setting == 8)) continue;
+        size_t bad_total = 0; int bad_runs = 0, runs = 0; bool shown = false;
+        g_dgemm_persistent = setting == 6 ? 0 : (setting == 7 ? 2 : 1);
+        g_dgemm_cg = setting == 8 ? 4 : (setting >= 9 ? 8 : 0);      // bit 2: start-up delay, bit 3: consumer-side proxy fence (diagnostic)
+        for (int k : {0, 1, 3, 7, 12}) {
+            g_dgemm_tma = 0;
+            cudaMemcpy(Mref, M0, Np * ld * 8, cudaMemcpyDeviceToDevice);
+            cudaDeviceSynchronize();
+            update(s1, Mref, k);
+            cudaStreamSynchronize(s1);
+            cudaMemcpy(ref.data(), Mref, Np * ld * 8, cudaMemcpyDeviceToHost);
+            for (int rep = 0; rep < reps; rep++) {
+                g_dgemm_tma = 7;
+                cudaMemcpy(M, M0, Np * ld * 8, cudaMemcpyDeviceToDevice);
+                cudaDeviceSynchronize();
+                if (setting == 1 || (setting >= 5 && setting != 9)) copy_cols_kernel<<<592, 256, 0, s1>>>(M0, M, ld, Np, (int64_t)k * 128, 128);
+                if (setting == 2)
+                    for (int q = 0; q < 40; q++) copy_cols_kernel<<<16, 256, 0, s2>>>(M0, M, ld, Np, (int64_t)(k + 1) * 128, 128);
+                if (setting == 3) empty_kernel<<<592, 256, 0, s1>>>();
+                if (setting == 4 || setting == 9) copy_cols_kernel<<<592, 256, 0, s1>>>(M0, Mref, ld, Np, (int64_t)k * 128, 128);
+                if (setting == 5) cudaStreamSynchronize(s1);
+                update(s1, M, k);
+                cudaError_t e = cudaDeviceSynchronize();
+                if (e != cudaSuccess) { printf("launch failed: %s\n", cudaGetErrorString(e)); return 2; }
+                cudaMemcpy(got.data(), M, Np * ld * 8, cudaMemcpyDeviceToHost);
+                size_t bad = 0;
+                for (size_t i = 0; i < got.size(); i++) bad += got[i] != ref[i];
+                if (bad && !shown) {
+                    shown = true;
+                    int64_t rmin = Np, rmax = -1, cmin = Np, cmax = -1; int pr = 0;
+                    for (size_t i = 0; i < got.size(); i++)
+                        if (got[i] != ref[i]) {
+                            const int64_t r = i / ld, c = i % ld;
+                            rmin = r < rmin ? r : rmin; rmax = r > rmax ? r : rmax; cmin = c < cmin ? c : cmin; cmax = c > cmax ? c : cmax;
+                            if (pr++ < 4) printf("      k=%d (%lld,%lld): got %.10f ref %.10f start %.10f\n", k, (long long)r, (long long)c, got[i], ref[i], h[i]);
+                        }
+                    printf("      first wrong run: %zu entries, rows %lld..%lld, cols %lld..%lld (tile origin col %lld)\n", bad, (long long)rmin, (long long)rmax,
+                           (long long)cmin, (long long)cmax, (long long)((k + 2) * 128));
+                }
+                bad_total += bad; bad_runs += bad != 0; runs++;
+            }
+        }
+        printf("pipeline check (%s): %zu mismatching entries, %d of %d runs wrong\n", names[setting], bad_total, bad_runs, runs);
+        rc |= bad_total != 0;
+    }
+    g_dgemm_persistent = 1; g_dgemm_cg = 0;
+    // two consecutive updates k, k+1 on one stream without host synchronisation in between (the second reads what the first wrote)
+    {
+        size_t bad_total = 0; int bad_runs = 0;
+        for (int rep = 0; rep <= reps; rep++) {
+            g_dgemm_tma = rep == 0 ? 0 : 7;
+            double* T = rep == 0 ? Mref : M;
+            cudaMemcpy(T, M0, Np * ld * 8, cudaMemcpyDeviceToDevice);
+            cudaDeviceSynchronize();
+            for (int k = 0; k < 6; k++) update(s1, T, k);
+            cudaDeviceSynchronize();
+            cudaMemcpy((rep == 0 ? ref : got).data(), T, Np * ld * 8, cudaMemcpyDeviceToHost);
+            if (rep == 0) continue;
+            size_t bad = 0;
+            for (size_t i = 0; i < got.size(); i++) bad += fabs(got[i] - ref[i]) > 1e-9 * (1.0 + fabs(ref[i]));
+            bad_total += bad; bad_runs += bad != 0;
+        }
+        printf("pipeline check (6 back-to-back updates, tolerance 1e-9): %zu mismatching entries, %d of %d runs wrong\n", bad_total, bad_runs, reps);
+        rc |= bad_total != 0;
+    }
+    return rc;
+}
+
 int main(int argc, char** argv) {
     if (argc > 1 && !strcmp(argv[1], "check")) return check_mode(argc > 2 ? atoi(argv[2]) : 20);
+    if (argc > 1 && !strcmp(argv[1], "pipeline")) return pipeline_mode(argc > 2 ? atoi(argv[2]) : 6);
     const int64_t ld = 16384, R = 16384;
     double *A, *B, *C;
     cudaMalloc(&A, R * ld * 8); cudaMalloc(&B, R * ld * 8); cudaMalloc(&C, R * ld * 8);
