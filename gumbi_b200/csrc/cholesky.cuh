@@ -847,7 +847,7 @@ inline int factor_steps_compact(gb2_handle* h, int k0, int k1, int col_limit, in
 // When the loop ends every rank holds the complete factor (each panel was gathered everywhere), so predict() runs locally
 // on whatever slice of the prediction grid the rank is given.
 //
-// GB2_TF32: block columns are grouped in panels of h->opt_tf32_nb blocks (default 4 = 512 columns).  A panel is
+// GB2_TF32: block columns are grouped in panels of h->tf32_nb() blocks (auto: 8 = 1024 columns from Np >= 8192, else 4 = 512 columns).  A panel is
 // factored in fp64 by factor_steps (DMMA), split into tf32 hi/lo pairs, and the whole trailing matrix is updated by ONE
 // tcgen05 split-TF32 SYRK of depth 512 (tf32gemm.cuh) -- 8x fewer passes over the trailing matrix than the 128-wide steps.
 inline int cholesky_enqueue(gb2_handle* h) {

@@ -268,7 +268,12 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
                 if (p_nit <= 0) { p_open = false; p_tile += gridDim.x; continue; }
             }
             const int st = (int)(p_g % GT_STAGES);
-            if (p_g >= (uint32_t)GT_STAGES) tc::mbar_wait(empty + st, (p_g / GT_STAGES - 1) & 1u);
+            if (p_g >= (uint32_t)GT_STAGES) {
+                tc::mbar_wait(empty + st, (p_g / GT_STAGES - 1) & 1u);
+                // the consumers' generic-proxy reads of this stage (ordered before this point by their arrive / this wait) must also be
+                // ordered before the async-proxy write that refills it
+                if (c_cg & 16) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
             unsigned char* dst = base + st * STAGE_BYTES;
             tc::mbar_expect_tx(full + st, STAGE_BYTES);
             tc::tma_load_2d(dst, &mA, a_col0 + (p_kt0 + p_it) * GT_BK, p_arow, full + st);

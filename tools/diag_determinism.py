@@ -58,11 +58,13 @@ def run(N, d, kind, reps, full):
     e.close()
 
 
-# dgemm_tma is a usage mask; the value 1 means "all" (= 7), so "SET only" is written 9 (9 & 7 = 1)
-CONFIGS = [("cp.async (reference)", {"dgemm_tma": 0}), ("tma: SET products only", {"dgemm_tma": 9}), ("tma: next-column SUB only", {"dgemm_tma": 2}),
-           ("tma: bulk SUB only", {"dgemm_tma": 4}), ("tma: all", {"dgemm_tma": 7})]
+# dgemm_tma is a usage mask (4 = the bulk trailing updates only); dgemm_cg bits: 8 = consumers execute fence.proxy.async.shared::cta before
+# releasing a stage, 16 = the producer executes it after acquiring the stage
+CONFIGS = [("cp.async (reference)", {"dgemm_tma": 0}), ("tma bulk, no smem proxy fence", {"dgemm_tma": 4, "dgemm_cg": 0}),
+           ("tma bulk, consumer-side fence", {"dgemm_tma": 4, "dgemm_cg": 8}), ("tma bulk, producer-side fence", {"dgemm_tma": 4, "dgemm_cg": 16}),
+           ("tma bulk, both fences", {"dgemm_tma": 4, "dgemm_cg": 24}), ("tma all, both fences", {"dgemm_tma": 7, "dgemm_cg": 24})]
 
 if __name__ == "__main__":
     sizes = [int(a) for a in sys.argv[1:]] or [16384]
     for n in sizes:
-        run(n, 8, "Matern52", 4, False)
+        run(n, 8, "Matern52", 5, False)
