@@ -387,6 +387,7 @@ inline cudaError_t cholesky_configure() {
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD_SMEM)) != cudaSuccess) return e;
     if ((e = dgemm_nt_configure<128, 64, GM_SUB>()) != cudaSuccess) return e;
+    if ((e = dgemm_nt_configure<64, 128, GM_SUB, GM_BK, GM_STAGES, 32, 64>()) != cudaSuccess) return e;
     if ((e = dgemm_nt_configure<64, 128, GM_SET>()) != cudaSuccess) return e;
     if ((e = dgemm_nt_configure<64, 128, GM_SET_PUSH>()) != cudaSuccess) return e;
     return cudaSuccess;
@@ -940,12 +941,12 @@ inline int cholesky_enqueue(gb2_handle* h) {
             cudaEvent_t eP = pool_event(h, ev0 + 2 * g);
             cudaEventRecord(eP, sm);                                     // panel g complete (factor_steps joined its panel stream)
             if (g > 0) cudaStreamWaitEvent(sm, pool_event(h, ev0 + 2 * (g - 1) + 1), 0);
-            dgemm_nt_launch<128, 64, GM_SUB>(sm, Apan, ld, A + (int64_t)c1 * TILE * ld + (int64_t)c0 * TILE, ld, A + (int64_t)c1 * TILE, ld,
+            dgemm_sub_launch(sm, Apan, ld, A + (int64_t)c1 * TILE * ld + (int64_t)c0 * TILE, ld, A + (int64_t)c1 * TILE, ld,
                                              (int64_t)(nb - c1) * TILE, (int64_t)(c2 - c1) * TILE, kd, 1, 0, (int64_t)c1 * TILE, c1, 1);
             launches++;
             cudaStreamWaitEvent(sb, eP, 0);
             if (c2 < nb) {
-                dgemm_nt_launch<128, 64, GM_SUB>(sb, Apan, ld, A + (int64_t)c2 * TILE * ld + (int64_t)c0 * TILE, ld, A + (int64_t)c2 * TILE, ld,
+                dgemm_sub_launch(sb, Apan, ld, A + (int64_t)c2 * TILE * ld + (int64_t)c0 * TILE, ld, A + (int64_t)c2 * TILE, ld,
                                                  (int64_t)(nb - c2) * TILE, (int64_t)(nb - c2) * TILE, kd, 1, 0, (int64_t)c2 * TILE, c2, 1);
                 launches++;
             }

@@ -229,10 +229,6 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
     if (tid == 0) {
         for (int s = 0; s < GT_STAGES; s++) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        // The operands were written by the preceding kernels with ordinary (generic-proxy) stores; the loads below go through the
-        // async proxy.  Grid completion orders those stores before this kernel in the generic proxy; this fence carries that order
-        // over to the async proxy for global memory.
-        if (c_cg & 2) asm volatile("fence.proxy.async.global;" ::: "memory");
     }
     __syncthreads();
 
@@ -268,12 +264,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
                 if (p_nit <= 0) { p_open = false; p_tile += gridDim.x; continue; }
             }
             const int st = (int)(p_g % GT_STAGES);
-            if (p_g >= (uint32_t)GT_STAGES) {
-                tc::mbar_wait(empty + st, (p_g / GT_STAGES - 1) & 1u);
-                // the consumers' generic-proxy reads of this stage (ordered before this point by their arrive / this wait) must also be
-                // ordered before the async-proxy write that refills it
-                if (c_cg & 16) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            }
+            if (p_g >= (uint32_t)GT_STAGES) tc::mbar_wait(empty + st, (p_g / GT_STAGES - 1) & 1u);
             unsigned char* dst = base + st * STAGE_BYTES;
             tc::mbar_expect_tx(full + st, STAGE_BYTES);
             tc::tma_load_2d(dst, &mA, a_col0 + (p_kt0 + p_it) * GT_BK, p_arow, full + st);
@@ -289,11 +280,6 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
     const uint32_t b_base = tc::smem_u32(base) + (uint32_t)(BM * 128 + (wn * WN + g) * 128);
 
     uint32_t c_g = 0;        // k-tiles consumed so far (same sequence as the producer's)
-    if (c_cg & 4) {   // diagnostic: hold the first TMA load back by ~20 us
-        const long long t0 = clock64();
-        while (clock64() - t0 < 40000) {}
-        __syncthreads();
-    }
     if (tid == 0) produce(GT_STAGES - 1);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         int bj, kt0; int64_t grow, lrow;
@@ -324,8 +310,13 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
 #pragma unroll
                     for (int ni = 0; ni < NI; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
             }
-            // this warp's generic-proxy reads of the stage are ordered before the async-proxy (TMA) write that refills it
-            if (c_cg & 8) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            // Release of the stage.  The fragments were read with ordinary (generic-proxy) shared loads; the stage will be refilled by a
+            // TMA write (async proxy).  Without this fence ptxas schedules the arrive right behind the ISSUE of the last LDS, ahead of
+            // the DMMAs that consume it (cuobjdump of the round-2 build), so the refill could overtake loads still in flight: one warp
+            // then multiplied a few 16-byte chunks of the NEXT k-tile -- about one wrong 8 x 32 patch per 10^5 tiles, enough to break
+            // every large factorisation (profiles/r02e..r02q_*diag*.log, tools/micro_dgemm pipeline).  fence.proxy.async orders this
+            // thread's generic accesses before the async-proxy accesses that follow in the release -> acquire chain.
+            if (!(c_cg & 2)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(empty + st);
         }
@@ -381,12 +372,10 @@ inline MemGetAddressRangeFn mem_range_fn() {
 
 struct TmaOperand { CUtensorMap map; int row0, col0; };
 
-// set_option("dgemm_tma", mask): process-wide switch, see dgemm_tma_try_launch; 1 -> 7.  DEFAULT OFF: stand-alone the TMA-staged
-// kernel is exact (tools/micro_dgemm check, compute-sanitizer racecheck clean) and 7 % faster, but inside the factorisation pipeline
-// it produced intermittently corrupted tiles on the device (profiles/r02e..r02i_*diag*.log); until that is understood the product
-// path stays on the cp.async kernel, which is bit-reproducible run to run.
-inline int g_dgemm_tma = 0;
-inline int g_dgemm_fence = 1;         // set_option("dgemm_fence", 0/1): fence.proxy.async.global before the first TMA load of a CTA
+// set_option("dgemm_tma", mask): process-wide switch (ablation), see dgemm_tma_try_launch; 1 -> 7, 0 = cp.async-staged kernel everywhere
+inline int g_dgemm_tma = 7;
+inline int g_dgemm_fence = 1;         // set_option("dgemm_fence", 0/1): 0 drops the generic->async proxy fence at the release of a stage
+                                      // (reproduces the round-2 corruption; diagnostic only)
 inline int g_dgemm_promo = 1;         // set_option("dgemm_promo", 0/1): L2 promotion 256B / none in the tensor maps (diagnostic)
 inline int g_dgemm_cg = 0;            // set_option("dgemm_cg", 1): read-modify-write epilogue loads C with ld.global.cg (L2 only) -- diagnostic
 inline int g_dgemm_persistent = 1;   // set_option("dgemm_persistent", 0/1/2): 0 = one CTA per tile (ablation), 2 = persistent without cross-tile prefetch
@@ -461,7 +450,7 @@ inline bool dgemm_tma_try_launch(cudaStream_t s, const double* A, int64_t lda, c
     const unsigned grid = (unsigned)(g_dgemm_persistent && n_tiles > slots ? slots : n_tiles);
     dgemm_tma_kernel<BM, BN, MODE><<<grid, 256, dgemm_tma_smem_bytes<BM, BN>(), s>>>(oa.map, ob.map, oa.row0, oa.col0, ob.row0, ob.col0, C, ldc, kdepth,
                                                                                     lower_only, row_off, col_off, rb_first, rb_stride, pa, rb_local_first,
-                                                                                    n_bi, n_bj, g_dgemm_cg | (g_dgemm_fence << 1), g_dgemm_persistent == 2 ? 0 : 1);
+                                                                                    n_bi, n_bj, (g_dgemm_cg & 1) | (g_dgemm_fence ? 0 : 2), g_dgemm_persistent == 2 ? 0 : 1);
     return true;
 }
 
@@ -482,6 +471,19 @@ inline void dgemm_nt_launch(cudaStream_t s, const double* A, int64_t lda, const 
     }
     dgemm_nt_kernel<BM, BN, MODE, BK, STAGES, WM, WN, MINB><<<grid, (BM / WM) * (BN / WN) * 32, dgemm_smem_bytes<BM, BN, BK, STAGES>(), s>>>(
         A, lda, B, ldb, C, ldc, kdepth, lower_only, row_off, col_off, rb_first, rb_stride, pa, rb_local_first);
+}
+
+// C -= A B^T for the DEEP updates (two-level Cholesky, upper levels of the predict solve): from depth g_dgemm_deep on, the same kernel
+// body runs with 64x128 CTA tiles and four warps of 32x64 -- 0.375 instead of 0.5 shared-memory fragment loads per DMMA, the tile
+// shape of the library's own fp64 kernel.  Same k order per output entry, so results are bit-identical to the 128x64 configuration
+// (tools/micro_dgemm: 0 mismatching entries); measured there +2.7 % at depth >= 4096, -5 % at depth 128, hence the threshold.
+inline int g_dgemm_deep = 512;   // set_option("dgemm_deep", depth): 0 = never (ablation)
+inline void dgemm_sub_launch(cudaStream_t s, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t rows,
+                             int64_t cols, int kdepth, int lower_only, int64_t row_off, int64_t col_off, int rb_first = 0, int rb_stride = 1) {
+    if (g_dgemm_deep > 0 && kdepth >= g_dgemm_deep && !(g_dgemm_tma & 4))
+        dgemm_nt_launch<64, 128, GM_SUB, GM_BK, GM_STAGES, 32, 64>(s, A, lda, B, ldb, C, ldc, rows, cols, kdepth, lower_only, row_off, col_off, rb_first, rb_stride);
+    else
+        dgemm_nt_launch<128, 64, GM_SUB>(s, A, lda, B, ldb, C, ldc, rows, cols, kdepth, lower_only, row_off, col_off, rb_first, rb_stride);
 }
 
 }  // namespace gb2

@@ -1307,9 +1307,10 @@ int gb2_set_option(gb2_handle* h, const char* name, int value) {
         return 0;
     }
     if (!strcmp(name, "dgemm_tma")) { g_dgemm_tma = value == 1 ? 7 : (value & 7); h->factorized = false; return 0; }   // ablation (process-wide): 0 = cp.async-staged fp64 GEMM
+    if (!strcmp(name, "dgemm_deep")) { GB2_ARG(h, value >= 0, "dgemm_deep must be >= 0"); g_dgemm_deep = value; return 0; }   // ablation (process-wide)
     if (!strcmp(name, "dgemm_fence")) { g_dgemm_fence = value ? 1 : 0; return 0; }   // diagnostic (process-wide)
     if (!strcmp(name, "dgemm_promo")) { g_dgemm_promo = value ? 1 : 0; return 0; }   // diagnostic (process-wide)
-    if (!strcmp(name, "dgemm_cg")) { g_dgemm_cg = value & 29; return 0; }   // diagnostic (process-wide)
+    if (!strcmp(name, "dgemm_cg")) { g_dgemm_cg = value & 1; return 0; }   // diagnostic (process-wide)
     if (!strcmp(name, "dgemm_persistent")) { g_dgemm_persistent = value; return 0; }   // ablation (process-wide): 0 = one CTA per output tile
     if (!strcmp(name, "kbuild_persist")) { h->opt_kbuild_persist = value ? 1 : 0; h->factorized = false; return 0; }   // ablation: 0 = round-1 strip / per-tile kernels
     if (!strcmp(name, "kbuild_v1")) { h->opt_kbuild_v1 = value ? 1 : 0; h->factorized = false; return 0; }   // ablation: scalar-FMA + libm exp K-build

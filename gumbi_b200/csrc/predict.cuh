@@ -24,7 +24,7 @@ inline void trsm_rec(cudaStream_t s, const double* L, int64_t ld, const double* 
     const int mid = c0 + (c1 - c0 + 1) / 2;
     trsm_rec(s, L, ld, Dinv, At, ldt, Mp, c0, mid, launches, tri);
     const int64_t rows = tri ? std::min<int64_t>(Mp, (int64_t)mid * TILE) : Mp;
-    dgemm_nt_launch<128, 64, GM_SUB>(s, At + (int64_t)c0 * TILE, ldt, L + (int64_t)mid * TILE * ld + (int64_t)c0 * TILE, ld,
+    dgemm_sub_launch(s, At + (int64_t)c0 * TILE, ldt, L + (int64_t)mid * TILE * ld + (int64_t)c0 * TILE, ld,
                                      At + (int64_t)mid * TILE, ldt, rows, (int64_t)(c1 - mid) * TILE, (mid - c0) * TILE, 0, 0, 0);
     launches++;
     trsm_rec(s, L, ld, Dinv, At, ldt, Mp, mid, c1, launches, tri);

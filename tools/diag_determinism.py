@@ -21,7 +21,7 @@ def run(N, d, kind, reps, full):
     e.set_train(X, y)
     e.set_kernel(spec)
     ref = {}
-    base = {"dgemm_tma": 1, "dgemm_persistent": 1, "dgemm_cg": 0, "dgemm_fence": 1, "dgemm_promo": 1, "lookahead": 1, "chain_on_panel": 1, "kbuild_persist": 1}
+    base = {"dgemm_tma": 7, "dgemm_persistent": 1, "dgemm_cg": 0, "dgemm_fence": 1, "dgemm_promo": 1, "lookahead": 1, "chain_on_panel": 1, "kbuild_persist": 1, "fp64_panel": FP64_PANEL}
     for tag, delta in CONFIGS:
         opts = {**base, **delta}
         for k, v in opts.items():
@@ -58,13 +58,14 @@ def run(N, d, kind, reps, full):
     e.close()
 
 
-# dgemm_tma is a usage mask (4 = the bulk trailing updates only); dgemm_cg bits: 8 = consumers execute fence.proxy.async.shared::cta before
-# releasing a stage, 16 = the producer executes it after acquiring the stage
-CONFIGS = [("cp.async (reference)", {"dgemm_tma": 0}), ("tma bulk, no smem proxy fence", {"dgemm_tma": 4, "dgemm_cg": 0}),
-           ("tma bulk, consumer-side fence", {"dgemm_tma": 4, "dgemm_cg": 8}), ("tma bulk, producer-side fence", {"dgemm_tma": 4, "dgemm_cg": 16}),
-           ("tma bulk, both fences", {"dgemm_tma": 4, "dgemm_cg": 24}), ("tma all, both fences", {"dgemm_tma": 7, "dgemm_cg": 24})]
+# dgemm_fence = 0 drops the generic->async proxy fence at the release of a shared-memory stage (the round-2 bug, kept as a control)
+CONFIGS = [("cp.async (reference)", {"dgemm_tma": 0}), ("tma, stage fence (product), plain algorithm", {"fp64_panel": 0}),
+           ("tma, stage fence (product), two-level blocking", {"fp64_panel": 16}),
+           ("tma WITHOUT the stage fence (control), plain algorithm", {"fp64_panel": 0, "dgemm_fence": 0})]
+
+FP64_PANEL = int(os.environ.get("DIAG_FP64_PANEL", "0"))   # 0: the plain algorithm (k = 128 bulk updates, the regime that failed)
 
 if __name__ == "__main__":
     sizes = [int(a) for a in sys.argv[1:]] or [16384]
     for n in sizes:
-        run(n, 8, "Matern52", 5, False)
+        run(n, 8, "Matern52", 8, False)

@@ -125,13 +125,13 @@ static int pipeline_mode(int reps) {
     const char* names[] = {"static operands", "panel re-written by a copy kernel right before the update", "neighbour column re-written concurrently",
                            "EMPTY kernel right before the update", "copy kernel writes ANOTHER matrix right before", "copy kernel, stream sync, update",
                            "panel re-written right before, one CTA per tile", "panel re-written right before, persistent without cross-tile prefetch",
-                           "panel re-written right before, 20 us delay before the first TMA load",
-                           "copy kernel writes ANOTHER matrix right before, consumer-side fence.proxy.async.shared::cta", "panel re-written right before, consumer-side fence"};
+                           "panel re-written right before (repeat)",
+                           "copy kernel writes ANOTHER matrix right before, WITHOUT the stage fence (control)", "panel re-written right before, WITHOUT the stage fence (control)"};
     for (int setting = (reps > 12 ? 4 : 0); setting < 11; setting++) {
         if (reps > 12 && (setting == 6 || setting == 7 || setting == 8)) continue;
         size_t bad_total = 0; int bad_runs = 0, runs = 0; bool shown = false;
         g_dgemm_persistent = setting == 6 ? 0 : (setting == 7 ? 2 : 1);
-        g_dgemm_cg = setting == 8 ? 4 : (setting >= 9 ? 8 : 0);      // bit 2: start-up delay, bit 3: consumer-side proxy fence (diagnostic)
+        g_dgemm_fence = setting >= 9 ? 0 : 1;     // settings 9, 10: WITHOUT the stage-release proxy fence (control: the round-2 bug)
         for (int k : {0, 1, 3, 7, 12}) {
             g_dgemm_tma = 0;
             cudaMemcpy(Mref, M0, Np * ld * 8, cudaMemcpyDeviceToDevice);
@@ -173,7 +173,7 @@ static int pipeline_mode(int reps) {
         printf("pipeline check (%s): %zu mismatching entries, %d of %d runs wrong\n", names[setting], bad_total, bad_runs, runs);
         rc |= bad_total != 0;
     }
-    g_dgemm_persistent = 1; g_dgemm_cg = 0;
+    g_dgemm_persistent = 1; g_dgemm_fence = 1;
     // two consecutive updates k, k+1 on one stream without host synchronisation in between (the second reads what the first wrote)
     {
         size_t bad_total = 0; int bad_runs = 0;
