@@ -643,7 +643,7 @@ inline int factor_steps(gb2_handle* h, int k0, int k1, int col_limit) {
                 if (c2 > 0) {
                     dgemm_nt_launch<128, 64, GM_SUB>(sm, colk, ld, A + (g0 + 2 * TILE) * ld + g0, ld, A + g0 + 2 * TILE, ld,
                                                      (int64_t)c2 * TILE, (int64_t)(col_limit - (k + 2)) * TILE, TILE, 1, 0,
-                                                     g0 + 2 * TILE, f2, G);
+                                                     g0 + 2 * TILE, f2, G, nullptr, -1, h->opt_bulk_persistent);
                     launches++;
                 }
             }
@@ -942,12 +942,12 @@ inline int cholesky_enqueue(gb2_handle* h) {
             cudaEventRecord(eP, sm);                                     // panel g complete (factor_steps joined its panel stream)
             if (g > 0) cudaStreamWaitEvent(sm, pool_event(h, ev0 + 2 * (g - 1) + 1), 0);
             dgemm_sub_launch(sm, Apan, ld, A + (int64_t)c1 * TILE * ld + (int64_t)c0 * TILE, ld, A + (int64_t)c1 * TILE, ld,
-                                             (int64_t)(nb - c1) * TILE, (int64_t)(c2 - c1) * TILE, kd, 1, 0, (int64_t)c1 * TILE, c1, 1);
+                                             (int64_t)(nb - c1) * TILE, (int64_t)(c2 - c1) * TILE, kd, 1, 0, (int64_t)c1 * TILE, c1, 1, h->opt_bulk_persistent);
             launches++;
             cudaStreamWaitEvent(sb, eP, 0);
             if (c2 < nb) {
                 dgemm_sub_launch(sb, Apan, ld, A + (int64_t)c2 * TILE * ld + (int64_t)c0 * TILE, ld, A + (int64_t)c2 * TILE, ld,
-                                                 (int64_t)(nb - c2) * TILE, (int64_t)(nb - c2) * TILE, kd, 1, 0, (int64_t)c2 * TILE, c2, 1);
+                                                 (int64_t)(nb - c2) * TILE, (int64_t)(nb - c2) * TILE, kd, 1, 0, (int64_t)c2 * TILE, c2, 1, h->opt_bulk_persistent);
                 launches++;
             }
             cudaEventRecord(pool_event(h, ev0 + 2 * g + 1), sb);

@@ -430,7 +430,7 @@ inline bool tma_operand(const double* ptr, int64_t ld, int box_rows, TmaOperand&
 template <int BM, int BN, int MODE>
 inline bool dgemm_tma_try_launch(cudaStream_t s, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t rows,
                                  int64_t cols, int kdepth, int lower_only, int64_t row_off, int64_t col_off, int rb_first, int rb_stride,
-                                 const PushArgs& pa, int rb_local_first) {
+                                 const PushArgs& pa, int rb_local_first, int persistent) {
     TmaOperand oa, ob;
     // g_dgemm_tma is a bit mask (diagnostic): 1 = the in-place SET products (panel solves, solve leaves), 2 = SUB updates one
     // 128-column block wide (next-column updates), 4 = all other SUB updates
@@ -443,11 +443,13 @@ inline bool dgemm_tma_try_launch(cudaStream_t s, const double* A, int64_t lda, c
             return false;
         configured = true;
     }
-    // persistent: at most two CTAs per SM walk the tile list (row tile fastest, so concurrent CTAs share the B tile in L2)
+    // persistent: at most two CTAs per SM walk the tile list (row tile fastest, so concurrent CTAs share the B tile in L2).  Callers whose
+    // launch overlaps a latency-critical chain on another stream (the bulk updates of the factorisation) pass persistent = 0: a
+    // persistent grid holds every SM until it ends, one CTA per tile lets the chain's kernels in as tiles retire
     const int n_bi = (int)(rows / BM), n_bj = (int)(cols / BN);
     const int64_t n_tiles = (int64_t)n_bi * n_bj;
     const int slots = 2 * tma_sm_count();
-    const unsigned grid = (unsigned)(g_dgemm_persistent && n_tiles > slots ? slots : n_tiles);
+    const unsigned grid = (unsigned)(g_dgemm_persistent && persistent && n_tiles > slots ? slots : n_tiles);
     dgemm_tma_kernel<BM, BN, MODE><<<grid, 256, dgemm_tma_smem_bytes<BM, BN>(), s>>>(oa.map, ob.map, oa.row0, oa.col0, ob.row0, ob.col0, C, ldc, kdepth,
                                                                                     lower_only, row_off, col_off, rb_first, rb_stride, pa, rb_local_first,
                                                                                     n_bi, n_bj, (g_dgemm_cg & 1) | (g_dgemm_fence ? 0 : 2), g_dgemm_persistent == 2 ? 0 : 1);
@@ -459,14 +461,14 @@ template <int BM, int BN, int MODE, int BK = GM_BK, int STAGES = GM_STAGES, int 
 inline void dgemm_nt_launch(cudaStream_t s, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                             int64_t ldc, int64_t rows, int64_t cols, int kdepth, int lower_only, int64_t row_off,
                             int64_t col_off, int rb_first = 0, int rb_stride = 1, const PushArgs* push = nullptr,
-                            int rb_local_first = -1) {
+                            int rb_local_first = -1, int persistent = 1) {
     if (rows <= 0 || cols <= 0 || kdepth <= 0) return;
     dim3 grid((unsigned)(rows / BM), (unsigned)(cols / BN));
     PushArgs pa{};
     if (push) pa = *push;
     if constexpr (BK == GM_BK && STAGES == GM_STAGES && WM == 32 && WN == 32 && MINB == 2) {   // the product instantiations
         if (dgemm_tma_try_launch<BM, BN, MODE>(s, A, lda, B, ldb, C, ldc, rows, cols, kdepth, lower_only, row_off, col_off, rb_first, rb_stride, pa,
-                                               rb_local_first))
+                                               rb_local_first, persistent))
             return;
     }
     dgemm_nt_kernel<BM, BN, MODE, BK, STAGES, WM, WN, MINB><<<grid, (BM / WM) * (BN / WN) * 32, dgemm_smem_bytes<BM, BN, BK, STAGES>(), s>>>(
@@ -479,11 +481,13 @@ inline void dgemm_nt_launch(cudaStream_t s, const double* A, int64_t lda, const 
 // (tools/micro_dgemm: 0 mismatching entries); measured there +2.7 % at depth >= 4096, -5 % at depth 128, hence the threshold.
 inline int g_dgemm_deep = 512;   // set_option("dgemm_deep", depth): 0 = never (ablation)
 inline void dgemm_sub_launch(cudaStream_t s, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t rows,
-                             int64_t cols, int kdepth, int lower_only, int64_t row_off, int64_t col_off, int rb_first = 0, int rb_stride = 1) {
+                             int64_t cols, int kdepth, int lower_only, int64_t row_off, int64_t col_off, int rb_first = 0, int rb_stride = 1,
+                             int persistent = 1) {
     if (g_dgemm_deep > 0 && kdepth >= g_dgemm_deep && !(g_dgemm_tma & 4))
         dgemm_nt_launch<64, 128, GM_SUB, GM_BK, GM_STAGES, 32, 64>(s, A, lda, B, ldb, C, ldc, rows, cols, kdepth, lower_only, row_off, col_off, rb_first, rb_stride);
     else
-        dgemm_nt_launch<128, 64, GM_SUB>(s, A, lda, B, ldb, C, ldc, rows, cols, kdepth, lower_only, row_off, col_off, rb_first, rb_stride);
+        dgemm_nt_launch<128, 64, GM_SUB>(s, A, lda, B, ldb, C, ldc, rows, cols, kdepth, lower_only, row_off, col_off, rb_first, rb_stride, nullptr, -1,
+                                         persistent);
 }
 
 }  // namespace gb2

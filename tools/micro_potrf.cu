@@ -40,27 +40,5 @@ int main() {
         }
     printf("max|LL^T-A| = %.3e  max|inv(L) L - I| = %.3e\n", e1, e2);
 
-    // small-footprint twin (256 threads, 130 KB): same products in the same order -> must be bit-identical
-    cudaFuncSetAttribute(potrf_diag_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PDS_SMEM);
-    std::vector<double> L2(n * n), D2(n * n);
-    for (int rep = 0; rep < 3; rep++) {
-        cudaMemcpy(dA, A.data(), n * n * 8, cudaMemcpyHostToDevice);
-        cudaMemset(dD, 0, n * n * 8);
-        cudaMemset(dClk, 0, 64 * 8);
-        potrf_diag_small_kernel<<<1, PDS_THREADS, PDS_SMEM>>>(dA, n, 0, n, dD, dInfo, nullptr, PushArgs{}, dClk);
-        cudaError_t e = cudaDeviceSynchronize();
-        if (e != cudaSuccess) { printf("small: error %s\n", cudaGetErrorString(e)); return 1; }
-        cudaMemcpy(clk, dClk, 64 * 8, cudaMemcpyDeviceToHost);
-        long long tot = 0;
-        printf("small rep %d:", rep);
-        for (int i = 1; i < 64 && clk[i]; i++) { printf(" %lld", clk[i] - clk[i - 1]); tot = clk[i] - clk[0]; }
-        printf("  total %lld cycles\n", tot);
-    }
-    cudaMemcpy(L2.data(), dA, n * n * 8, cudaMemcpyDeviceToHost);
-    cudaMemcpy(D2.data(), dD, n * n * 8, cudaMemcpyDeviceToHost);
-    size_t badL = 0, badD = 0;
-    for (int i = 0; i < n; i++)
-        for (int j = 0; j <= i; j++) { badL += L2[i * n + j] != L[i * n + j]; badD += D2[i * n + j] != D[i * n + j]; }
-    printf("small vs full kernel: mismatching entries  L %zu  inv(L) %zu\n", badL, badD);
     return 0;
 }
