@@ -10,7 +10,7 @@ under "warm".
   value : steps timed with CUDA events on the handle's stream, training inputs + grid already resident in HBM.
   e2e   : the same step through the plugin class (ArrayGP.build_model -> find_MAP(point=) -> predict) with HOST numpy
           buffers: H2D of X, y and the grid and D2H of mean/var happen inside the timed region every step.
-  roofline      : the dominant kernel, dgemm_nt_kernel (DMMA fp64), measured on the predict triangular solve which
+  roofline      : the dominant kernel, dgemm_tma_kernel (TMA-staged DMMA fp64), measured on the predict triangular solve which
                   consists of that kernel only: N^2 M' flop / solve_ms.
   roofline_cholesky / roofline_kbuild: N^3/3 flop over the whole factorisation (per GPU); lower-triangle bytes over the K-build.
   cpu_baseline  : oracle/gp_oracle.py (numpy/scipy restatement of the PyMC path) on the host cores, bounded sample.
@@ -367,6 +367,7 @@ def device_arm(torch, dev, args, workload, precision, steps, warmup, rank, local
         step_dev()
     phase = {k: 0.0 for k in ("prep_ms", "kbuild_ms", "cholesky_ms", "kstar_ms", "solve_ms", "reduce_ms")}
     launches = 0
+    launches_predict = 0
     sampler = ClockSampler(local_rank) if sample_clocks else None
     barrier()
     if sampler and rank == 0:
@@ -379,6 +380,7 @@ def device_arm(torch, dev, args, workload, precision, steps, warmup, rank, local
         for k in phase:
             phase[k] += tm[k]
         launches += int(tm["launches_factorize"] + tm["launches_predict"])
+        launches_predict = int(tm["launches_predict"])
     eng.mark(1)
     ms_total = eng.elapsed_ms(0, 1)
     barrier()
@@ -401,7 +403,7 @@ def device_arm(torch, dev, args, workload, precision, steps, warmup, rank, local
     torch.cuda.empty_cache()
     return {"spec": spec, "X": X, "y": y, "Xs": Xs, "desc": desc, "N": N, "D_in": D_in, "M": M, "lo": lo, "hi": hi, "shard": shard,
             "ms_step": ms_step, "value": M / (ms_step * 1e-3), "phase": phase, "launches": launches, "wall_ms": wall_ms / steps,
-            "clocks": clocks, "warm_ms": warm_ms, "mu": mu_dev, "var": var_dev}
+            "clocks": clocks, "warm_ms": warm_ms, "mu": mu_dev, "var": var_dev, "launches_predict": launches_predict}
 
 
 def rooflines(r, precision, world, peaks, dgemm_peak, dgemm_sustained, copy_gbs, workload):
@@ -416,10 +418,12 @@ def rooflines(r, precision, world, peaks, dgemm_peak, dgemm_sustained, copy_gbs,
                 "fp64 kind, DMMA is the fp64 tensor path)")
     tf32_peak = peaks["bf16_tflops"] / 2.0
     if precision == "fp64":
-        solve_launches = 2 * nblk - 1
+        # GEMM launches of one predict solve: everything the predict call launches except prep, K*-build and the reduction
+        # (4 row slabs in concurrent streams by default, each with its own recursion of 2 * nblk - 1 products)
+        solve_launches = max(1, r.get("launches_predict", 2 * nblk + 2) - 3)
         tr = measured_traffic(f"{workload}:fp64:solve") or {}
         roofline = {
-            "kernel": "dgemm_nt_kernel (DMMA m8n8k4 fp64) in the predict triangular solve L^-1 K(X,X*)",
+            "kernel": "dgemm_tma_kernel (TMA-staged DMMA m8n8k4 fp64) in the predict triangular solve L^-1 K(X,X*)",
             "bound": "tensor", "achieved": solve_tflops, "peak": dgemm_peak, "unit": "TFLOP/s", "frac": solve_tflops / dgemm_peak,
             "peak_source": fp64_src, "peak_sustained": dgemm_sustained, "frac_of_sustained": solve_tflops / dgemm_sustained,
             "algorithmic_flop_per_step": float(N) * N * Ml, "launches_per_step": solve_launches,

@@ -914,7 +914,7 @@ inline int cholesky_enqueue(gb2_handle* h) {
             g.a_k0 = 0; g.b_row0 = c1 * TILE; g.b_k0 = 0;
             tc::gemm_tf32x3_launch(sm, h->n_sm, h->mPhi, h->mPlo, h->mPhi, h->mPlo, g, (int)cols, launches);
         }
-    } else if (h->fp64_panel() > 1 && h->world == 1 && nb > h->fp64_panel() && h->ext_rows == 0) {
+    } else if (h->fp64_panel() > 1 && nb > h->fp64_panel() && h->ext_rows == 0) {   // (the storage-sharded mode returned above)
         // Two-level blocking (option "fp64_panel" = pw; default: auto, see gb2_handle::fp64_panel).  The plain algorithm applies every 128-column panel to the
         // whole trailing matrix: N/128 read-modify-write passes of depth 128 (87 % tensor-pipe activity, prologue/epilogue bound).
         // Here pw column blocks are factored as one panel (factor_steps restricted to the panel's own columns, exactly what the
@@ -930,6 +930,11 @@ inline int cholesky_enqueue(gb2_handle* h) {
         cudaStream_t sb = h->s_bulk2;
         const int pw2 = h->fp64_panel(), ev0 = 6 * nb + 32;
         double* A = h->dA;
+        // multi-GPU (replicated storage): every rank holds the whole factored panel (its tiles were pushed / all-gathered block step by
+        // block step) and updates the row blocks it owns -- first owned block >= c and their count, as in the tf32 branch above
+        const int G = h->world, me = h->rank;
+        auto first_owned = [&](int c) { return c + (((me - c) % G) + G) % G; };
+        auto count_owned = [&](int f) { return f < nb ? (nb - f + G - 1) / G : 0; };
         int g = 0;
         for (int c0 = 0; c0 < nb; c0 += pw2, g++) {
             const int c1 = c0 + pw2 < nb ? c0 + pw2 : nb;
@@ -941,13 +946,17 @@ inline int cholesky_enqueue(gb2_handle* h) {
             cudaEvent_t eP = pool_event(h, ev0 + 2 * g);
             cudaEventRecord(eP, sm);                                     // panel g complete (factor_steps joined its panel stream)
             if (g > 0) cudaStreamWaitEvent(sm, pool_event(h, ev0 + 2 * (g - 1) + 1), 0);
-            dgemm_sub_launch(sm, Apan, ld, A + (int64_t)c1 * TILE * ld + (int64_t)c0 * TILE, ld, A + (int64_t)c1 * TILE, ld,
-                                             (int64_t)(nb - c1) * TILE, (int64_t)(c2 - c1) * TILE, kd, 1, 0, (int64_t)c1 * TILE, c1, 1, h->opt_bulk_persistent);
-            launches++;
+            const int f1 = first_owned(c1), n1 = count_owned(f1);
+            if (n1 > 0) {
+                dgemm_sub_launch(sm, Apan, ld, A + (int64_t)c1 * TILE * ld + (int64_t)c0 * TILE, ld, A + (int64_t)c1 * TILE, ld, (int64_t)n1 * TILE,
+                                 (int64_t)(c2 - c1) * TILE, kd, 1, 0, (int64_t)c1 * TILE, f1, G, h->opt_bulk_persistent);
+                launches++;
+            }
             cudaStreamWaitEvent(sb, eP, 0);
-            if (c2 < nb) {
-                dgemm_sub_launch(sb, Apan, ld, A + (int64_t)c2 * TILE * ld + (int64_t)c0 * TILE, ld, A + (int64_t)c2 * TILE, ld,
-                                                 (int64_t)(nb - c2) * TILE, (int64_t)(nb - c2) * TILE, kd, 1, 0, (int64_t)c2 * TILE, c2, 1, h->opt_bulk_persistent);
+            const int f2 = first_owned(c2), n2 = count_owned(f2);
+            if (c2 < nb && n2 > 0) {
+                dgemm_sub_launch(sb, Apan, ld, A + (int64_t)c2 * TILE * ld + (int64_t)c0 * TILE, ld, A + (int64_t)c2 * TILE, ld, (int64_t)n2 * TILE,
+                                 (int64_t)(nb - c2) * TILE, kd, 1, 0, (int64_t)c2 * TILE, f2, G, h->opt_bulk_persistent);
                 launches++;
             }
             cudaEventRecord(pool_event(h, ev0 + 2 * g + 1), sb);
