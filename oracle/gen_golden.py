@@ -24,10 +24,21 @@ REF = "/root/reference"
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
-def import_reference():
-    """Stub the absent third-party imports, then import gumbi from the read-only reference tree."""
+def reference_root():
+    """Where the UNMODIFIED reference package can be imported from: the read-only source tree in the build container, else the
+    dependency-less install ``baseline/_ref`` (``pip install --no-deps --target baseline/_ref <copy of /root/reference>``; git-ignored,
+    travels to the GPU box with the snapshot).  None if neither exists."""
+    for cand in (REF, os.path.join(ROOT, "baseline", "_ref")):
+        if os.path.isdir(os.path.join(cand, "gumbi")):
+            return cand
+    return None
+
+
+def import_reference(ref=None):
+    """Stub the absent third-party imports, then import gumbi from the reference tree (or its install, see reference_root)."""
     if "gumbi" in sys.modules:
         return sys.modules["gumbi"]
+    ref = ref or reference_root() or REF
 
     def stub(name):
         m = types.ModuleType(name)
@@ -46,7 +57,7 @@ def import_reference():
     if isinstance(getattr(sys.modules.get("gpytorch.priors.prior"), "Prior", None), MagicMock):
         sys.modules["gpytorch.priors.prior"].Prior = type("Prior", (), {})
     sys.dont_write_bytecode = True
-    sys.path.insert(0, REF)
+    sys.path.insert(0, ref)
     import warnings
 
     with warnings.catch_warnings():

@@ -11,7 +11,7 @@ import pytest
 from conftest import ROOT, load_golden
 
 REF = "/root/reference"
-pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "gumbi")), reason="reference tree not present (GPU box)")
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "gumbi")), reason="reference tree not present (the GPU box runs tests/test_dropin_gpu.py against baseline/_ref instead)")
 
 
 @pytest.fixture(scope="module")
