@@ -486,62 +486,6 @@ inline int factor_steps(gb2_handle* h, int k0, int k1, int col_limit) {
     }
     auto first_owned_after = [&](int k, int r) { return k + 1 + (((r - (k + 1)) % G) + G) % G; };   // smallest block > k owned by r
     auto count_from = [&](int first) { return first < nb ? (nb - first + G - 1) / G : 0; };
-    if (G == 1 && two && h->opt_fastdiag) {
-        // ABLATION (off by default; set_option("fastdiag", 1)): on paper this schedule shortens the critical path, measured on B200 it
-        // is slower (C2 Cholesky 10.45 ms vs 9.26 ms): the three cross-stream event edges per block step cost more than the two
-        // small launches save.  Kept so that the measurement can be repeated.
-        // Single-GPU schedule with a short critical path.  What gates the next diagonal block is only the row block right below
-        // the current one, so that part leaves the bulk kernels and rides the high-priority stream behind the diagonal kernel:
-        //   [panel] potrf_diag(k)
-        //   [panel] L[k+1,k] = A[k+1,k] inv(L_kk)^T          (2 CTAs)      \  the "row fix": ~10 us instead of the 20 + 17 us of the
-        //   [panel] A[k+1,k+1] -= L[k+1,k] L[k+1,k]^T        (2 CTAs)      /   full panel solve + next-column update
-        //   [main]  panel solve rows >= k+2  ->  next-column update rows >= k+2  ->  rest of the trailing matrix
-        // Events: P(k) diagonal block done, R(k) row fix done, C(k) trailing update k done (index 3k, 3k+1, 3k+2).
-        for (int k = k0; k < k1; k++) {
-            const int64_t g0 = (int64_t)k * TILE;
-            const int64_t below = Np - g0 - TILE;
-            double* Dk = h->dDinv + (int64_t)k * TILE * TILE;
-            potrf_diag_kernel<<<1, PD_THREADS, PD_SMEM, sp>>>(A, ld, g0, h->N, Dk, h->dInfo, nullptr);
-            launches++;
-            if (below <= 0) break;
-            cudaEvent_t eP = pool_event(h, 3 * k), eR = pool_event(h, 3 * k + 1), eC = pool_event(h, 3 * k + 2);
-            cudaEventRecord(eP, sp);
-            double* colk = A + g0;
-            // row fix needs column k / the diagonal block k+1 as left by trailing update k-1
-            if (k > k0) cudaStreamWaitEvent(sp, pool_event(h, 3 * (k - 1) + 2), 0);
-            dgemm_nt_launch<64, 128, GM_SET>(sp, colk, ld, Dk, TILE, colk, ld, TILE, TILE, TILE, 0, 0, 0, k + 1, 1);
-            launches++;
-            if (k + 1 < col_limit) {
-                dgemm_nt_launch<128, 64, GM_SUB>(sp, colk, ld, A + (g0 + TILE) * ld + g0, ld, A + g0 + TILE, ld, TILE, TILE, TILE, 1, 0,
-                                                 g0 + TILE, k + 1, 1);
-                launches++;
-            }
-            cudaEventRecord(eR, sp);
-            cudaStreamWaitEvent(sm, eP, 0);
-            const int c2 = nb - (k + 2);   // row blocks >= k+2
-            if (c2 > 0) {
-                dgemm_nt_launch<64, 128, GM_SET>(sm, colk, ld, Dk, TILE, colk, ld, (int64_t)c2 * TILE, TILE, TILE, 0, 0, 0, k + 2, 1);
-                launches++;
-                cudaStreamWaitEvent(sm, eR, 0);
-                if (k + 1 < col_limit) {
-                    dgemm_nt_launch<128, 64, GM_SUB>(sm, colk, ld, A + (g0 + TILE) * ld + g0, ld, A + g0 + TILE, ld, (int64_t)c2 * TILE, TILE,
-                                                     TILE, 0, 0, g0 + TILE, k + 2, 1);
-                    launches++;
-                }
-                if (k + 2 < col_limit) {
-                    dgemm_nt_launch<128, 64, GM_SUB>(sm, colk, ld, A + (g0 + 2 * TILE) * ld + g0, ld, A + g0 + 2 * TILE, ld,
-                                                     (int64_t)c2 * TILE, (int64_t)(col_limit - (k + 2)) * TILE, TILE, 1, 0,
-                                                     g0 + 2 * TILE, k + 2, 1);
-                    launches++;
-                }
-            }
-            cudaEventRecord(eC, sm);
-        }
-        cudaEvent_t e = pool_event(h, 3 * nb + 1);
-        cudaEventRecord(e, sp);
-        cudaStreamWaitEvent(sm, e, 0);
-        return launches;
-    }
     for (int k = k0; k < k1; k++) {
         const int64_t g0 = (int64_t)k * TILE;
         const int64_t below = Np - g0 - TILE;

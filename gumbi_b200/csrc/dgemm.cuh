@@ -211,7 +211,7 @@ template <int BM, int BN, int MODE, int MINB = 2>
 __global__ void __launch_bounds__(256, MINB)
 dgemm_tma_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mB, int a_row0, int a_col0, int b_row0, int b_col0,
                  double* C, int64_t ldc, int kdepth, int lower_only, int64_t row_off, int64_t col_off, int rb_first, int rb_stride,
-                 PushArgs push, int rb_local_first, int n_bi, int n_bj, int c_cg, int xprefetch) {
+                 PushArgs push, int rb_local_first, int n_bi, int n_bj, int flags, int xprefetch) {
     constexpr int WM = 32, WN = 32, MI = WM / 8, NI = WN / 8;
     constexpr int STAGE_BYTES = (BM + BN) * 128;
     constexpr int TPB = TILE / BM;
@@ -316,7 +316,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
             // then multiplied a few 16-byte chunks of the NEXT k-tile -- about one wrong 8 x 32 patch per 10^5 tiles, enough to break
             // every large factorisation (profiles/r02e..r02q_*diag*.log, tools/micro_dgemm pipeline).  fence.proxy.async orders this
             // thread's generic accesses before the async-proxy accesses that follow in the release -> acquire chain.
-            if (!(c_cg & 2)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (!(flags & 2)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(empty + st);
         }
@@ -328,7 +328,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
             for (int ni = 0; ni < NI; ni++) {
                 double2* p = reinterpret_cast<double2*>(Cg + (int64_t)mi * 8 * ldc + ni * 8);
                 if (MODE == GM_SUB) {
-                    double2 c = (c_cg & 1) ? __ldcg(p) : *p;
+                    double2 c = *p;
                     c.x -= acc[mi][ni][0];
                     c.y -= acc[mi][ni][1];
                     *p = c;
@@ -376,8 +376,6 @@ struct TmaOperand { CUtensorMap map; int row0, col0; };
 inline int g_dgemm_tma = 7;
 inline int g_dgemm_fence = 1;         // set_option("dgemm_fence", 0/1): 0 drops the generic->async proxy fence at the release of a stage
                                       // (reproduces the round-2 corruption; diagnostic only)
-inline int g_dgemm_promo = 1;         // set_option("dgemm_promo", 0/1): L2 promotion 256B / none in the tensor maps (diagnostic)
-inline int g_dgemm_cg = 0;            // set_option("dgemm_cg", 1): read-modify-write epilogue loads C with ld.global.cg (L2 only) -- diagnostic
 inline int g_dgemm_persistent = 1;   // set_option("dgemm_persistent", 0/1/2): 0 = one CTA per tile (ablation), 2 = persistent without cross-tile prefetch
 inline int tma_sm_count() {
     static int n = 0;
@@ -398,12 +396,10 @@ inline bool tma_operand(const double* ptr, int64_t ld, int box_rows, TmaOperand&
     const int64_t rows = (int64_t)(size / sizeof(double)) / ld;
     if (rows < 1 || off / ld > 0x7fffffff) return false;
     struct Key { uintptr_t base; size_t size; int64_t ld; int box; bool operator==(const Key& o) const { return base == o.base && size == o.size && ld == o.ld && box == o.box; } };
-    box_rows |= g_dgemm_promo ? 0 : (1 << 20);   // separate cache entries per promotion setting
     struct Hash { size_t operator()(const Key& k) const { return (size_t)k.base * 1315423911u ^ k.size ^ ((size_t)k.ld << 7) ^ (size_t)k.box; } };
     static std::unordered_map<Key, CUtensorMap, Hash> cache;
     static std::mutex mu;
     const Key key{(uintptr_t)basep, size, ld, box_rows};
-    box_rows &= (1 << 20) - 1;
     {
         std::lock_guard<std::mutex> lk(mu);
         auto itc = cache.find(key);
@@ -414,8 +410,7 @@ inline bool tma_operand(const double* ptr, int64_t ld, int box_rows, TmaOperand&
             cuuint32_t box[2] = {(cuuint32_t)GT_BK, (cuuint32_t)box_rows};
             cuuint32_t estr[2] = {1, 1};
             if (encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)(uintptr_t)basep, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       CU_TENSOR_MAP_SWIZZLE_128B, g_dgemm_promo ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                 return false;
             if (cache.size() > 4096) cache.clear();   // handles come and go (tests): bound the cache
             itc = cache.emplace(key, m).first;
@@ -449,10 +444,12 @@ inline bool dgemm_tma_try_launch(cudaStream_t s, const double* A, int64_t lda, c
     const int n_bi = (int)(rows / BM), n_bj = (int)(cols / BN);
     const int64_t n_tiles = (int64_t)n_bi * n_bj;
     const int slots = 2 * tma_sm_count();
-    const unsigned grid = (unsigned)(g_dgemm_persistent && persistent && n_tiles > slots ? slots : n_tiles);
+    // persistent: 0 = one CTA per tile, 1 = two CTAs per SM, > 1 = that many CTAs (a grid that leaves some SMs to other streams)
+    const int64_t cap = persistent > 1 ? persistent : slots;
+    const unsigned grid = (unsigned)(g_dgemm_persistent && persistent && n_tiles > cap ? cap : n_tiles);
     dgemm_tma_kernel<BM, BN, MODE><<<grid, 256, dgemm_tma_smem_bytes<BM, BN>(), s>>>(oa.map, ob.map, oa.row0, oa.col0, ob.row0, ob.col0, C, ldc, kdepth,
                                                                                     lower_only, row_off, col_off, rb_first, rb_stride, pa, rb_local_first,
-                                                                                    n_bi, n_bj, (g_dgemm_cg & 1) | (g_dgemm_fence ? 0 : 2), g_dgemm_persistent == 2 ? 0 : 1);
+                                                                                    n_bi, n_bj, g_dgemm_fence ? 0 : 2, g_dgemm_persistent == 2 ? 0 : 1);
     return true;
 }
 

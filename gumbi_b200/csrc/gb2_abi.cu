@@ -736,7 +736,6 @@ static int factorize_impl(gb2_handle* h, const ExtPredict& x) {
     if (x.M > 0) {
         GB2_ARG(h, !h->compact, "gb2_factorize_predict is not available in the storage-sharded mode");
         GB2_ARG(h, h->precision == GB2_FP64, "gb2_factorize_predict is fp64 only");
-        GB2_ARG(h, !h->opt_fastdiag, "gb2_factorize_predict is not available with the fastdiag ablation");
         GB2_ARG(h, Mp * Np * (int64_t)sizeof(double) <= ((int64_t)8 << 30), "too many prediction points for one fused pass (use gb2_factorize + gb2_predict)");
         if ((rc = ensure(h, h->dAt, h->At_cap, Mp * Np))) return rc;
         if ((rc = ensure(h, h->dFs, h->Fs_cap, (int64_t)std::max(1, h->kp.n_feat) * Mp))) return rc;
@@ -1299,7 +1298,6 @@ int gb2_set_option(gb2_handle* h, const char* name, int value) {
         h->opt_fused_group = value;
         return 0;
     }
-    if (!strcmp(name, "fastdiag")) { h->opt_fastdiag = value ? 1 : 0; return 0; }   // ablation: Cholesky critical-path fast path
     if (!strcmp(name, "chain_on_panel")) { h->opt_chain_on_panel = value ? 1 : 0; return 0; }   // ablation: Cholesky stream choreography
     if (!strcmp(name, "kbuild_occ")) {   // register bound of the strip K-build: 3 or 4 resident CTAs per SM
         GB2_ARG(h, value == 3 || value == 4, "kbuild_occ must be 3 or 4");
@@ -1307,11 +1305,9 @@ int gb2_set_option(gb2_handle* h, const char* name, int value) {
         return 0;
     }
     if (!strcmp(name, "dgemm_tma")) { g_dgemm_tma = value == 1 ? 7 : (value & 7); h->factorized = false; return 0; }   // ablation (process-wide): 0 = cp.async-staged fp64 GEMM
-    if (!strcmp(name, "bulk_persistent")) { h->opt_bulk_persistent = value ? 1 : 0; return 0; }   // ablation: persistent grids for the factorisation's bulk updates
+    if (!strcmp(name, "bulk_persistent")) { GB2_ARG(h, value >= 0 && value <= 4096, "bulk_persistent must be in [0, 4096]"); h->opt_bulk_persistent = value; return 0; }   // ablation: persistent grids for the factorisation's bulk updates
     if (!strcmp(name, "dgemm_deep")) { GB2_ARG(h, value >= 0, "dgemm_deep must be >= 0"); g_dgemm_deep = value; return 0; }   // ablation (process-wide)
     if (!strcmp(name, "dgemm_fence")) { g_dgemm_fence = value ? 1 : 0; return 0; }   // diagnostic (process-wide)
-    if (!strcmp(name, "dgemm_promo")) { g_dgemm_promo = value ? 1 : 0; return 0; }   // diagnostic (process-wide)
-    if (!strcmp(name, "dgemm_cg")) { g_dgemm_cg = value & 1; return 0; }   // diagnostic (process-wide)
     if (!strcmp(name, "dgemm_persistent")) { g_dgemm_persistent = value; return 0; }   // ablation (process-wide): 0 = one CTA per output tile
     if (!strcmp(name, "kbuild_persist")) { h->opt_kbuild_persist = value ? 1 : 0; h->factorized = false; return 0; }   // ablation: 0 = round-1 strip / per-tile kernels
     if (!strcmp(name, "kbuild_v1")) { h->opt_kbuild_v1 = value ? 1 : 0; h->factorized = false; return 0; }   // ablation: scalar-FMA + libm exp K-build

@@ -143,9 +143,9 @@ struct gb2_handle {
     int* dKbCtr = nullptr;        // its work counters (self-resetting)
     int opt_kbuild_occ = 4;
     int opt_chain_on_panel = 1;   // Cholesky: keep the next-column update on the panel stream (no cross-stream hop on the chain)
-    int opt_fastdiag = 0;    // single GPU: "row-fix" schedule for the next diagonal block (cholesky.cuh); measured slower, kept as ablation
     int opt_lookahead = 1;
-    int opt_bulk_persistent = 0;   // bulk trailing updates of the factorisation as persistent grids (1) or one CTA per tile (0, see dgemm_tma_try_launch)
+    int opt_bulk_persistent = 0;   // bulk trailing updates of the factorisation: one CTA per tile (0), persistent grid of 2 CTAs per SM (1), or a
+                                   // persistent grid of this many CTAs (> 1: leaves SMs to the chain's kernels), see dgemm_tma_try_launch
     // fused cold predict (gb2_factorize_predict): prediction points ride along as ext_rows extra rows of the factor (row-major, ld ext_ld)
     double* ext_At = nullptr; int64_t ext_rows = 0, ext_ld = 0; int ext_ncols = 0;
     // "trace" option: %globaltimer stamps around the kernels of every block step of factor_steps (6 per step), see gb2_get_trace

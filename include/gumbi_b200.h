@@ -193,16 +193,19 @@ int gb2_dist_allgather_dev(gb2_handle* h, const double* dsend, double* drecv, in
  *                        rank).  Must be set identically on all ranks before gb2_factorize.  fp64 only.
  *   "p2p"           1|0  multi-GPU panel exchange through NVLink peer mappings (default) or NCCL broadcast + all-gather
  *   "tf32_nb"       0..16  GB2_TF32 factor-panel width in 128-column blocks (0 = auto); "tf32_leaf" 1..16 fp64 leaf width of the solve
- *   "lookahead"     1|0  panel look-ahead on a second stream;  "fastdiag", "kbuild_v1": ablations
- *   "solve_streams" 1..4 fp64 predict solve: row slabs of the prediction points on this many concurrent streams (default 1)
+ *   "lookahead"     1|0  panel look-ahead on a second stream;  "chain_on_panel", "kbuild_v1", "kbuild_persist", "kbuild_occ": ablations
+ *   "solve_streams" 1..4 fp64 predict solve: row slabs of the prediction points on this many concurrent streams (default 4)
  *   "fused_group"   1|2|4|8  gb2_factorize_predict: column blocks per bulk update of the prediction rows (default 4)
  *   "trace"         0|1  record the per-step timeline read by gb2_get_trace (measurement aid, off by default)
- *   "fp64_panel"    0..16  single GPU, fp64: two-level blocking -- panels of this many 128-column blocks are factored with updates
- *                        restricted to the panel, then applied to the trailing matrix by one update of depth 128*value (default 0: off)
- *   "small_diag"    0|1  diagonal-panel kernel variant of 256 threads / 130 KB that can share an SM with a GEMM CTA (the default
- *                        one needs an empty SM: 512 x 128 registers, 222 KB); same products in the same order -> bit-identical results
- *   "green_sms"     8..64 (multiple of 8)  single GPU: give the diagonal-panel kernel its own SM partition (CUDA green contexts) so that
- *                        it never waits for the bulk trailing update to free a whole SM; experimental, off by default, cannot be undone */
+ *   "fp64_panel"    -1..16  fp64 two-level blocking -- panels of this many 128-column blocks are factored with updates restricted to the
+ *                        panel, then applied to the trailing matrix by one update of depth 128*value (-1 = auto: 16 from padded N >= 16384,
+ *                        plain algorithm below; 0 = always plain)
+ *   "bulk_persistent" 0|1|n  bulk trailing updates of the factorisation: one CTA per tile (0, default), persistent grid (1), or a persistent
+ *                        grid of n CTAs
+ *   process-wide ablations of the fp64 GEMM: "dgemm_tma" usage mask (7 = TMA-staged kernel everywhere, default; 0 = cp.async kernel),
+ *   "dgemm_persistent" 0|1|2, "dgemm_deep" depth threshold of the 64x128 tile variant of the cp.async kernel, "dgemm_fence" 1|0
+ *   (0 removes the generic->async proxy fence at the release of a shared-memory stage: reproduces the round-2 race, diagnostic only)
+ * Environment: GB2_OPTS="name=value,..." applies options to every handle of the process at gb2_create (measurement scripts).  */
 int gb2_set_option(gb2_handle* h, const char* name, int value);
 
 #ifdef __cplusplus

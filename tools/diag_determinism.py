@@ -21,7 +21,7 @@ def run(N, d, kind, reps, full):
     e.set_train(X, y)
     e.set_kernel(spec)
     ref = {}
-    base = {"dgemm_tma": 7, "dgemm_persistent": 1, "dgemm_cg": 0, "dgemm_fence": 1, "dgemm_promo": 1, "lookahead": 1, "chain_on_panel": 1, "kbuild_persist": 1, "fp64_panel": FP64_PANEL}
+    base = {"dgemm_tma": 7, "dgemm_persistent": 1, "dgemm_fence": 1, "lookahead": 1, "chain_on_panel": 1, "kbuild_persist": 1, "fp64_panel": FP64_PANEL}
     for tag, delta in CONFIGS:
         opts = {**base, **delta}
         for k, v in opts.items():
