@@ -207,11 +207,11 @@ constexpr int GT_BK = 16;
 template <int BM, int BN>
 constexpr size_t dgemm_tma_smem_bytes() { return (size_t)GT_STAGES * (BM + BN) * 128 + 1024 /*alignment slack*/ + 128 /*barriers*/; }
 
-template <int BM, int BN, int MODE, int MINB = 2>
+template <int BM, int BN, int MODE, bool FENCE = true, int MINB = 2>
 __global__ void __launch_bounds__(256, MINB)
 dgemm_tma_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mB, int a_row0, int a_col0, int b_row0, int b_col0,
                  double* C, int64_t ldc, int kdepth, int lower_only, int64_t row_off, int64_t col_off, int rb_first, int rb_stride,
-                 PushArgs push, int rb_local_first, int n_bi, int n_bj, int flags, int xprefetch) {
+                 PushArgs push, int rb_local_first, int n_bi, int n_bj, int xprefetch) {
     constexpr int WM = 32, WN = 32, MI = WM / 8, NI = WN / 8;
     constexpr int STAGE_BYTES = (BM + BN) * 128;
     constexpr int TPB = TILE / BM;
@@ -316,7 +316,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
             // then multiplied a few 16-byte chunks of the NEXT k-tile -- about one wrong 8 x 32 patch per 10^5 tiles, enough to break
             // every large factorisation (profiles/r02e..r02q_*diag*.log, tools/micro_dgemm pipeline).  fence.proxy.async orders this
             // thread's generic accesses before the async-proxy accesses that follow in the release -> acquire chain.
-            if (!(flags & 2)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (FENCE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // FENCE = false: the round-2 race, compiled as a control only
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(empty + st);
         }
@@ -434,7 +434,8 @@ inline bool dgemm_tma_try_launch(cudaStream_t s, const double* A, int64_t lda, c
     if (kdepth % GT_BK != 0 || !tma_operand(A, lda, BM, oa) || !tma_operand(B, ldb, BN, ob)) return false;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(dgemm_tma_kernel<BM, BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgemm_tma_smem_bytes<BM, BN>()) != cudaSuccess)
+        if (cudaFuncSetAttribute(dgemm_tma_kernel<BM, BN, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgemm_tma_smem_bytes<BM, BN>()) != cudaSuccess ||
+            cudaFuncSetAttribute(dgemm_tma_kernel<BM, BN, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgemm_tma_smem_bytes<BM, BN>()) != cudaSuccess)
             return false;
         configured = true;
     }
@@ -447,9 +448,15 @@ inline bool dgemm_tma_try_launch(cudaStream_t s, const double* A, int64_t lda, c
     // persistent: 0 = one CTA per tile, 1 = two CTAs per SM, > 1 = that many CTAs (a grid that leaves some SMs to other streams)
     const int64_t cap = persistent > 1 ? persistent : slots;
     const unsigned grid = (unsigned)(g_dgemm_persistent && persistent && n_tiles > cap ? cap : n_tiles);
-    dgemm_tma_kernel<BM, BN, MODE><<<grid, 256, dgemm_tma_smem_bytes<BM, BN>(), s>>>(oa.map, ob.map, oa.row0, oa.col0, ob.row0, ob.col0, C, ldc, kdepth,
-                                                                                    lower_only, row_off, col_off, rb_first, rb_stride, pa, rb_local_first,
-                                                                                    n_bi, n_bj, g_dgemm_fence ? 0 : 2, g_dgemm_persistent == 2 ? 0 : 1);
+    const int xprefetch = g_dgemm_persistent == 2 ? 0 : 1;
+    if (g_dgemm_fence)
+        dgemm_tma_kernel<BM, BN, MODE, true><<<grid, 256, dgemm_tma_smem_bytes<BM, BN>(), s>>>(oa.map, ob.map, oa.row0, oa.col0, ob.row0, ob.col0, C, ldc, kdepth,
+                                                                                              lower_only, row_off, col_off, rb_first, rb_stride, pa,
+                                                                                              rb_local_first, n_bi, n_bj, xprefetch);
+    else   // control: the kernel WITHOUT the stage-release proxy fence (set_option("dgemm_fence", 0)), see DESIGN.md section 7a
+        dgemm_tma_kernel<BM, BN, MODE, false><<<grid, 256, dgemm_tma_smem_bytes<BM, BN>(), s>>>(oa.map, ob.map, oa.row0, oa.col0, ob.row0, ob.col0, C, ldc, kdepth,
+                                                                                               lower_only, row_off, col_off, rb_first, rb_stride, pa,
+                                                                                               rb_local_first, n_bi, n_bj, xprefetch);
     return true;
 }
 
