@@ -525,6 +525,7 @@ inline int factor_steps(gb2_handle* h, int k0, int k1, int col_limit) {
         if (below > 0) {
             const int f1 = first_owned_after(k, me), c1 = count_from(f1);         // owned blocks > k
             double* colk = A + g0;                                                   // column block k, row 0
+            bool defer_wait = false;
             if (p2p) {
                 // panel solve fused with its exchange: tiles are stored locally and into every peer's factor over NVLink
                 if (c1 > 0) {
@@ -535,9 +536,14 @@ inline int factor_steps(gb2_handle* h, int k0, int k1, int col_limit) {
                     dgemm_nt_launch<64, 128, GM_SET_PUSH>(sp, colk, ld, Dk, TILE, colk, ld, (int64_t)c1 * TILE, TILE, TILE, 0, 0, 0, f1, G, &push);
                     launches++;
                 }
-                // every other rank pushes (its owned blocks below k) x (128/64 row tiles) CTAs' worth of tiles into this GPU
+                // every other rank pushes (its owned blocks below k) x (128/64 row tiles) CTAs' worth of tiles into this GPU.
+                // The rank that owns block k+1 does not need them for the chain: its next-column update reads only rows it owns (and
+                // L[k+1,k], which it owns too), and diag(k+1) only that update -- so there the wait moves off the panel stream and gates
+                // just the bulk update on the main stream (defer_wait): the chain  diag(k) -> pull -> own panel rows -> next column ->
+                // diag(k+1)  no longer includes the slowest peer's push.
                 const unsigned expected = (unsigned)(2 * ((nb - (k + 1)) - c1));
-                if (expected > 0) {
+                defer_wait = expected > 0 && two && h->opt_chain_on_panel && h->opt_defer_wait && (k + 1) % G == me && k + 1 < nb;
+                if (expected > 0 && !defer_wait) {
                     wait_counter_kernel<<<1, 32, 0, sp>>>(h->dFlags + fl + h->p2p_nbmax, expected);
                     launches++;
                 }
@@ -566,6 +572,10 @@ inline int factor_steps(gb2_handle* h, int k0, int k1, int col_limit) {
                 cudaEvent_t e = pool_event(h, 2 * k);
                 cudaEventRecord(e, sp);
                 cudaStreamWaitEvent(sm, e, 0);
+            }
+            if (defer_wait) {   // the peers' tiles of column k: needed by the bulk update only (see above)
+                wait_counter_kernel<<<1, 32, 0, sm>>>(h->dFlags + fl + h->p2p_nbmax, (unsigned)(2 * ((nb - (k + 1)) - c1)));
+                launches++;
             }
             if (chain && k > k0) cudaStreamWaitEvent(sp, pool_event(h, 2 * (k - 1) + 1), 0);   // bulk update k-1 touched column k+1
             // next panel column first: A[i, k+1] -= L[i,k] L[k+1,k]^T for owned i >= k+1

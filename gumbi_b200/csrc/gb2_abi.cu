@@ -1305,6 +1305,7 @@ int gb2_set_option(gb2_handle* h, const char* name, int value) {
         return 0;
     }
     if (!strcmp(name, "dgemm_tma")) { g_dgemm_tma = value == 1 ? 7 : (value & 7); h->factorized = false; return 0; }   // ablation (process-wide): 0 = cp.async-staged fp64 GEMM
+    if (!strcmp(name, "defer_wait")) { h->opt_defer_wait = value ? 1 : 0; return 0; }   // ablation (multi-GPU chain)
     if (!strcmp(name, "bulk_persistent")) { GB2_ARG(h, value >= 0 && value <= 4096, "bulk_persistent must be in [0, 4096]"); h->opt_bulk_persistent = value; return 0; }   // ablation: persistent grids for the factorisation's bulk updates
     if (!strcmp(name, "dgemm_deep")) { GB2_ARG(h, value >= 0, "dgemm_deep must be >= 0"); g_dgemm_deep = value; return 0; }   // ablation (process-wide)
     if (!strcmp(name, "dgemm_fence")) { g_dgemm_fence = value ? 1 : 0; return 0; }   // diagnostic (process-wide)

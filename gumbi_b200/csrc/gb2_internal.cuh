@@ -144,6 +144,7 @@ struct gb2_handle {
     int opt_kbuild_occ = 4;
     int opt_chain_on_panel = 1;   // Cholesky: keep the next-column update on the panel stream (no cross-stream hop on the chain)
     int opt_lookahead = 1;
+    int opt_defer_wait = 1;        // multi-GPU: on the owner of block k+1 the wait for the peers' tiles of column k gates only the bulk update
     int opt_bulk_persistent = 0;   // bulk trailing updates of the factorisation: one CTA per tile (0), persistent grid of 2 CTAs per SM (1), or a
                                    // persistent grid of this many CTAs (> 1: leaves SMs to the chain's kernels), see dgemm_tma_try_launch
     // fused cold predict (gb2_factorize_predict): prediction points ride along as ext_rows extra rows of the factor (row-major, ld ext_ld)

@@ -107,11 +107,29 @@ def main():
     if rank == 0:
         print(json.dumps({"non_pd_verdict_identical_on_all_ranks": same, "message": msgs[0]}), flush=True)
     ok &= same
+    # a full distributed find_MAP through the plugin class: every rank drives the same L-BFGS-B over the collective objective and must
+    # end at the SAME point after the SAME number of evaluations (rank 0's value / gradient are broadcast, gumbi_b200/map.py)
+    eng.close(); ref.close()
+    if prec == "fp64" and not shard and os.environ.get("GB2_DIST_P2P", "1") == "1":
+        from gumbi_b200 import ArrayGP
+
+        spec, X, y, Xs = synthetic_problem(700, 2)
+        gp = ArrayGP(X, y, ["x0", "x1"], device=local_rank, distributed=True)
+        gp.build_model()
+        MAP = gp.find_MAP(options={"maxiter": 12})
+        key = (tuple(np.round(np.asarray(MAP["ls_total"], dtype=np.float64), 14).tolist()), round(float(MAP["σ"]), 14), int(gp.map_evals))
+        keys = [None] * world
+        dist.all_gather_object(keys, key)
+        same_map = all(k == keys[0] for k in keys)
+        mu_m, _ = gp.predict(Xs[:64], with_noise=True)
+        if rank == 0:
+            print(json.dumps({"find_MAP_identical_on_all_ranks": same_map, "n_eval": keys[0][2], "ls": keys[0][0]}), flush=True)
+        ok &= same_map and bool(np.all(np.isfinite(mu_m)))
+        gp.engine.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("DIST_CHECK", "OK" if int(flag.item()) == 1 else "FAILED", flush=True)
-    eng.close(); ref.close()
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) == 1 else 1)
 
