@@ -10,6 +10,7 @@
 #include <random>
 #include <vector>
 #include "../gumbi_b200/csrc/kbuild_persist.cuh"
+#include "kbuild_persist_r02t.cuh"   // the v4 kernel of round-2 call t, frozen: same-box comparison arm
 
 using namespace gb2;
 static bool g_one = false;
@@ -102,12 +103,33 @@ template <int KIND, int KS, int NCG, int OCC>
 static float time_persist(const KParams& kp, KB4Args a, int n_sm, int strip, int reps) {
     CK(cudaFuncSetAttribute(kbuild_persist_kernel<true, KIND, KS, NCG, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kb4_smem_bytes<KS, NCG>()));
     a.strip = strip;
+    kb4_set_constants(a, kp.t[0].kind);
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     for (int i = 0; i < 2; i++) kbuild_persist_kernel<true, KIND, KS, NCG, OCC><<<n_sm * OCC, KB_THREADS, kb4_smem_bytes<KS, NCG>()>>>(kp, a);
     CK(cudaDeviceSynchronize());
     CK(cudaEventRecord(e0));
     for (int i = 0; i < reps; i++) kbuild_persist_kernel<true, KIND, KS, NCG, OCC><<<n_sm * OCC, KB_THREADS, kb4_smem_bytes<KS, NCG>()>>>(kp, a);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    return ms / reps;
+}
+
+template <int KIND, int KS, int NCG>
+static float time_persist_r02t(const KParams& kp, const KB4Args& a, int n_sm, int strip, int reps) {
+    KB4OArgs o{};
+    o.Fi = a.Fi; o.stride_i = a.stride_i; o.n_i = a.n_i; o.Fj = a.Fj; o.stride_j = a.stride_j; o.n_j = a.n_j; o.Ci = a.Ci; o.Cj = a.Cj; o.Btab = a.Btab;
+    o.y = a.y; o.out = a.out; o.ld = a.ld; o.n_row_tiles = a.n_row_tiles; o.n_col_tiles = a.n_col_tiles; o.strip = strip;
+    o.own_stride = 1; o.own_rank = 0; o.compact = 0; o.ctr = a.ctr;
+    CK(cudaFuncSetAttribute(kbuild_persist_r02t_kernel<true, KIND, KS, NCG, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kb4o_smem_bytes<KS, NCG>()));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 2; i++) kbuild_persist_r02t_kernel<true, KIND, KS, NCG, 4><<<n_sm * 4, KB_THREADS, kb4o_smem_bytes<KS, NCG>()>>>(kp, o);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < reps; i++) kbuild_persist_r02t_kernel<true, KIND, KS, NCG, 4><<<n_sm * 4, KB_THREADS, kb4o_smem_bytes<KS, NCG>()>>>(kp, o);
     CK(cudaEventRecord(e1));
     CK(cudaDeviceSynchronize());
     float ms;
@@ -178,6 +200,10 @@ static void run_case(int64_t n, int d, int P, int n_sm) {
     KB4Args a{};
     a.Fi = dF; a.stride_i = Np; a.n_i = N; a.Fj = dF; a.stride_j = Np; a.n_j = N; a.Ci = dC; a.Cj = dC; a.Btab = dBtab; a.y = dy; a.out = dA; a.ld = Np;
     a.n_row_tiles = a.n_col_tiles = (int)(Np / KB_T); a.own_stride = 1; a.own_rank = 0; a.compact = 0; a.ctr = dCtr;
+    if (!g_one) {
+        const float mo = time_persist_r02t<KIND, KS, NCG>(kp, a, n_sm, 8, reps);
+        printf("   v4 (round-2 call t) persistent kernel, strip 8 occ4: %.3f ms %.0f GB/s\n", mo, bytes / mo / 1e6);
+    }
     if (g_one) {   // profiling mode: the product configuration only
         const float m4 = time_persist<KIND, KS, NCG, KB4_OCC>(kp, a, n_sm, 8, 3);
         printf("   persistent strip 8 occ%d %.3f ms %.0f GB/s\n", KB4_OCC, m4, bytes / m4 / 1e6);
@@ -226,6 +252,7 @@ int main(int argc, char** argv) {
         std::vector<double> t2(KB4_TAB);
         for (int j = 0; j < KB4_TAB; j++) t2[j] = std::exp2((double)j / KB4_TAB);
         CK(cudaMemcpyToSymbol(g_exp2_tab2k, t2.data(), KB4_TAB * sizeof(double)));
+        CK(cudaMemcpyToSymbol(g_exp2_tab2k_r02t, t2.data(), KB4_TAB * sizeof(double)));
     }
     g_one = argc > 2;
     const int n_sm = prop.multiProcessorCount;
