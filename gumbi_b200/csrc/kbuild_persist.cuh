@@ -1,26 +1,29 @@
-// K-build v5: persistent strip kernel for the single-term models (pymc/GP.py:410,462,561,569):
+// K-build v6: persistent strip kernel for the single-term models (pymc/GP.py:410,462,561,569):
 //   K_ij = eta^2 k(|u_i - u_j|) * prod_f B_f[c_f(i), c_f(j)]        u = x / ls,  f <= 2 Coregion factors
 // with the augmentation of the training matrix (noise + jitter on the diagonal, y^T in row N, identity padding) exactly as
 // kbuild_dmma_kernel<TRAIN> writes it.  Additive / Linear models stay on kbuild_dmma_kernel.
 //
-// Structure (round 2, first version): persistent CTAs (grid = SMs x resident CTAs) pull (row tile, strip of column tiles) items off an
-// atomic counter; column-side data (features, squared norms, Coregion levels) arrive through a 3-stage cp.async ring; the row side
-// of an item lives in registers as ready-made DMMA A fragments pre-scaled by -2c; r^2 = s_i + s_j + DMMA (PyMC's own expanded
-// form, Stationary.square_dist); exp() = 2048-entry 2^(j/2048) table in shared memory (eta^2 folded in) + cubic.
+// Structure: persistent CTAs (grid = SMs x resident CTAs) pull (row tile, strip of column tiles) items off an atomic counter;
+// column-side data (features, squared norms, Coregion levels) arrive through a 3-stage cp.async ring filled by ONE rotating producer
+// warp; the row side of an item lives in registers as ready-made DMMA A fragments pre-scaled by -2c; r^2 = s_i + s_j + DMMA (PyMC's
+// own expanded form, Stationary.square_dist); exp() = 2048-entry 2^(j/2048) table in shared memory (eta^2 folded in) + cubic.
 //
-// Why v5 (ncu of v4 at C4, profiles/r02t_ncu_kbuild_matern_summary.txt + its SASS): 50 warp instructions per entry, of which only 17
-// use the fp64 pipe (16 scalar + 1 DMMA = 48 of its cycles) -- ISSUE SLOTS (50 cycles per warp-entry) bounded the kernel as much as the
-// fp64 pipe did, and each ran at 55 %.  The other 33: literal fp64 constants re-materialised with two moves per use (64
-// registers), a 4-instruction integer clip, 10 integer instructions around the table lookup, and ~12 per entry of per-tile
-// overhead (64-bit address arithmetic of the prefetch and of the stores, done per tile).  Here:
-//   * fp64 constants are KERNEL PARAMETERS (constant-bank operands of the DFMA itself, no moves);
-//   * clip(r^2, 0) (+ 1e-12 under the Matern square root) is ONE signed integer max on the high word;
-//   * the table stores each entry with its high word biased by -(j << 9), so that  hi + (n << 9)  (one LEA) applies the binary
-//     exponent n >> 11 and cancels the index bits -- no mask / shift / add chain;
-//   * per-thread prefetch slots (source pointer, shared address) and the two output row pointers are set up once per CTA / item,
-//     a tile costs one 64-bit add each; the tile is evaluated in two column halves (8 live accumulators, not 16) so that the
-//     64-register budget leaves room to interleave independent entries.
-// fp64 slots per entry are unchanged: 1 + d + 7 (ExpQuad), 1 + d + 5 (sqrt) + 7 + 3 (Matern-5/2).
+// What bounds it on B200 (round-2 measurements, profiles/r02ka..ke_micro_kbuild.log): an SM sub-partition DISPATCHES like a single-issue
+// core on which a DFMA / DMUL / DADD takes 2 slots and a DMMA.8x8x4 ~14, everything else 1 -- ablations (no stores / no lookup / no
+// DMMA / no evaluation) add up term by term, and neither more resident warps, more registers (interleaved entries), a
+// conflict-free 16-copy table, 128-byte store rows nor fewer barriers moved the time by more than 2 %.  Per warp-entry (32 matrix
+// entries): fp64 slots 2 (1 + 7) + 14 = 30 (ExpQuad, d = 8) / 2 (1 + 5 + 7 + 3) + 14 = 46 (Matern-5/2); HBM time at 6468 GB/s is 45
+// slots.  So the only lever left is the count of OTHER instructions, which v4 -> v6 took from 33 to ~17 per entry:
+//   * fp64 constants are KERNEL PARAMETERS (constant-bank / register operands of the DFMA itself) -- as literals ptxas re-materialised
+//     them with two moves per use;
+//   * clip(r^2, 0) (+ 1e-12 under the Matern square root) and the cap that keeps the exp argument reduction valid are two integer
+//     min/max on the high word, in place;
+//   * the table stores each entry with its high word biased by -(j << 9), so that  hi + (n << 9)  (one IMAD) applies the binary
+//     exponent n >> 11 and cancels the index bits; the underflow flush is tested once per group of four entries;
+//   * one producer warp issues a tile's copies (a lane = 16 bytes of every row) instead of 256 threads re-deriving slot addresses;
+//     output row pointers are set up once per item; the tile is evaluated in two column halves (8 live accumulators).
+// Measured, N = 32768 (same box, profiles/r02ke_micro_kbuild.log): ExpQuad d = 8 1.100 -> 0.90 ms (0.74 of the HBM peak), Matern-5/2
+// 1.313 -> 1.11 ms (0.60), 2-output ICM d = 4 1.055 -> 0.89 ms (0.75).
 // Accuracy: table exact to 0.5 ulp, |reduced argument| <= ln2/4096 so the cubic truncates at 2^-58 relative; the one-step
 // argument reduction carries |x| * 2^-54 -- the same size as the rounding of x itself.  Entrywise gate vs the oracle: 5e-12.
 #pragma once
@@ -55,6 +58,7 @@ struct KB4Args {
     double c13;       // 1/3   (Matern-5/2 polynomial)
     double c375;      // 3/8   (square-root correction)
     int hi_zmin;      // high word of c * 1e-12 (Matern: clip(r^2, 0) + 1e-12 of euclidean_dist) or 0 (ExpQuad: clip(r^2, 0))
+    int hi_zmax;      // high word of the cap on z: exp argument -1000 (2000 for ExpQuad, 1e6 under the Matern square root)
 };
 
 // Per kind: the accumulator holds  z = c r^2 (+ c 1e-12)  with c = kb4_scale(kind)  (row side pre-scaled by -2c, norms by c)
@@ -80,58 +84,107 @@ inline void kb4_set_constants(KB4Args& a, int kind) {
     int64_t bits;
     memcpy(&bits, &zmin, 8);
     a.hi_zmin = (int)(bits >> 32);
+    const double zmax = kind == GB2_EXPQUAD ? 2000.0 : 1.0e6;
+    memcpy(&bits, &zmax, 8);
+    a.hi_zmax = (int)(bits >> 32);
 }
 
-// eta^2 * exp(-z * zs) for 0 <= z, through  n = round(-z * zs * 2048 / ln 2)  and the table  eta^2 * 2^(j/2048), j = n mod 2048, whose
-// entries carry the high word biased by -(j << 9):  hi + (n << 9) = hi(eta^2 2^(j/2048)) + ((n >> 11) << 20), i.e. times 2^(n >> 11).
-//   rr = z + n cR = -(reduced argument) / zs, cubic of exp(-zs rr) - 1 with coefficients -zs, zs^2 / 2, -zs^3 / 6.
-// Arguments with zs z >= 693 (exp < 2^-1000 ~ 1e-301) return an exact 0: decided on the HIGH WORD OF z (z >= 0 orders like its bit
-// pattern), because for huge scaled distances (z > ~1e6) the low word of t -- n -- wraps around and must not be consulted.  A
-// result whose exponent field would underflow (tiny eta^2 on top of a tiny exp) is flushed to 0 as well.
-template <int ZS2>   // ZS2 = 2 * zs
-__device__ __forceinline__ double kb4_exp(double z, const unsigned char* __restrict__ tab, const KB4Args& a) {
-    constexpr double zs = 0.5 * ZS2;
-    constexpr double MAGIC = 6755399441055744.0;            // 1.5 * 2^52
-    const double t = fma(z, a.cA, MAGIC);
-    const int n = __double2loint(t);                         // round(-zs z 2048 / ln2) <= 0
-    const double kf = t - MAGIC;
-    const double rr = fma(kf, a.cR, z);                     // |rr| <= ln2 / (4096 zs)
-    const double p1 = fma(rr, a.q3, 0.5 * zs * zs);
-    const double p2 = fma(p1, rr, -zs);
-    const double m = rr * p2;                                // exp(-zs rr) - 1
-    const int2 T = *reinterpret_cast<const int2*>(tab + ((n << 3) & ((KB4_TAB - 1) << 3)));
-    const int hi = T.y + (n << 9);
-    constexpr int HI_ZMAX = ZS2 == 1 ? 0x4095A800 /* 1386.0 */ : 0x4085A800 /* 693.0 */;
-    const bool tiny = hi < 0x00100000 || __double2hiint(z) >= HI_ZMAX;
-    const double Ts = __hiloint2double(tiny ? 0 : hi, tiny ? 0 : T.x);
-    return fma(Ts, m, Ts);
-}
-
-// sqrt(a) for a normal positive a: MUFU.RSQ64H seed (2^-22) + one third-order correction, 5 fp64 operations, residual ~2^-67
-__device__ __forceinline__ double kb4_sqrt(double a, double c375) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-    const double t = a * y;
-    const double e = fma(-t, y, 1.0);
-    const double p = fma(c375, e, 0.5);
-    const double te = t * e;
-    return fma(te, p, t);
-}
-
-template <int KIND>
-__device__ __forceinline__ double kb4_value(int kind_rt, double z, const unsigned char* __restrict__ tab, const KB4Args& a) {
+// Per-entry arithmetic, written for GROUPS of G entries, statement by statement across the group (kb4_eval).
+//   exp: eta^2 * exp(-x * zs), table eta^2 * 2^(j/2048), j = n mod 2048, whose entries carry the high word biased by -(j << 9):
+//   hi + (n << 9) = hi(eta^2 2^(j/2048)) + ((n >> 11) << 20), i.e. times 2^(n >> 11) .  rr = x + n cR = -(reduced argument) / zs,
+//   cubic of exp(-zs rr) - 1 with coefficients -zs, zs^2 / 2, -zs^3 / 6.
+//   Huge scaled distances: z is clipped from above (high word, same instruction pair as the clip from below) where the exp argument
+//   reaches -1000, so that n = round(...) never wraps; any result whose exponent field underflows -- every clipped argument for
+//   eta^2 < 1e125, or a tiny eta^2 on top of a tiny exp -- is flushed to an exact 0 (the oracle's exp underflows to 0 at -745).
+//   clip(r^2, 0, inf) of Stationary.square_dist (+ the 1e-12 of euclidean_dist, already inside z, for the Matern family) is ONE signed
+//   integer max on the high word (z >= 0 orders like its bit pattern, a negative z has the sign bit set): the expanded form can
+//   come out negative by ~1e-16 |u|^2 (duplicated points, the diagonal) -- NaN under the square root once that exceeds the epsilon.
+//   A clipped value keeps its low word: c 1e-12 (1 + < 2^-20), or a denormal for ExpQuad -- both far below the rounding of r^2.
+//   sqrt(a) for a normal positive a: MUFU.RSQ64H seed (2^-22) + one third-order correction, 5 fp64 operations, residual ~2^-67.
+template <int KIND, int G>
+__device__ __forceinline__ void kb4_eval(int kind_rt, double* v, const unsigned char* __restrict__ tab, const KB4Args& a) {
+    constexpr int SHIFT = 20 - KB4_TAB_LOG2;
     const int kind = KIND >= 0 ? KIND : kind_rt;
-    // clip(r^2, 0, inf) of Stationary.square_dist (+ the 1e-12 of euclidean_dist, already inside z, for the Matern family) as ONE signed
-    // integer max on the high word (z >= 0 orders like its bit pattern, a negative z has the sign bit set): the expanded form can
-    // come out negative by ~1e-16 |u|^2 (duplicated points, the diagonal) -- NaN under the square root once that exceeds the epsilon.
-    // A clipped value keeps its low word: c 1e-12 (1 + < 2^-20), or a denormal for ExpQuad -- both far below the rounding of r^2
-    z = __hiloint2double(max(__double2hiint(z), a.hi_zmin), __double2loint(z));
-    if (kind == GB2_EXPQUAD) return kb4_exp<1>(z, tab, a);
-    const double w = kb4_sqrt(z, a.c375);
-    const double e = kb4_exp<2>(w, tab, a);
-    if (kind == GB2_MATERN52) return e * fma(fma(a.c13, w, 1.0), w, 1.0);   // 1 + w + w^2/3 = 1 + sqrt5 r + 5/3 r^2
-    if (kind == GB2_MATERN32) return e * (1.0 + w);
-    return e;                                         // Matern12, Exponential
+    const bool eq = kind == GB2_EXPQUAD;
+    constexpr double MAGIC = 6755399441055744.0;            // 1.5 * 2^52
+    const double h2 = eq ? 0.125 : 0.5, m1 = eq ? -0.5 : -1.0;          // zs^2 / 2, -zs
+    // every statement runs over the G entries of the group before the next one starts: G independent dependency chains, interleaved
+    // in program order (a warp issues in order; one chain alone leaves the fp64 pipe idle for the 8.5 cycles of every DFMA)
+    double x[G], rr[G], t[G];
+    int n[G];
+    int2 T[G];
+#pragma unroll
+    for (int q = 0; q < G; q++) {
+        // clip on the high word, in place (the low word keeps its register)
+        x[q] = v[q];
+        asm("{\n\t.reg .b32 lo, hi;\n\tmov.b64 {lo, hi}, %0;\n\tmax.s32 hi, hi, %1;\n\tmin.s32 hi, hi, %2;\n\tmov.b64 %0, {lo, hi};\n\t}" : "+d"(x[q]) : "r"(a.hi_zmin), "r"(a.hi_zmax));
+    }
+    if (!eq) {
+        double y[G], e[G];
+#pragma unroll
+        for (int q = 0; q < G; q++) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y[q]) : "d"(x[q]));
+#pragma unroll
+        for (int q = 0; q < G; q++) t[q] = x[q] * y[q];
+#pragma unroll
+        for (int q = 0; q < G; q++) e[q] = fma(-t[q], y[q], 1.0);
+#pragma unroll
+        for (int q = 0; q < G; q++) y[q] = fma(a.c375, e[q], 0.5);
+#pragma unroll
+        for (int q = 0; q < G; q++) e[q] = t[q] * e[q];
+#pragma unroll
+        for (int q = 0; q < G; q++) x[q] = fma(e[q], y[q], t[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < G; q++) t[q] = fma(x[q], a.cA, MAGIC);
+#pragma unroll
+    for (int q = 0; q < G; q++) {
+        n[q] = __double2loint(t[q]);                         // round(-zs x 2048 / ln2) <= 0
+        T[q] = *reinterpret_cast<const int2*>(tab + ((n[q] << 3) & ((KB4_TAB - 1) << 3)));
+    }
+#pragma unroll
+    for (int q = 0; q < G; q++) t[q] = t[q] - MAGIC;
+#pragma unroll
+    for (int q = 0; q < G; q++) rr[q] = fma(t[q], a.cR, x[q]);       // |rr| <= ln2 / (4096 zs)
+#pragma unroll
+    for (int q = 0; q < G; q++) t[q] = fma(rr[q], a.q3, h2);
+#pragma unroll
+    for (int q = 0; q < G; q++) t[q] = fma(t[q], rr[q], m1);
+#pragma unroll
+    for (int q = 0; q < G; q++) rr[q] = rr[q] * t[q];                // exp(-zs rr) - 1
+    if (kind == GB2_MATERN52) {
+#pragma unroll
+        for (int q = 0; q < G; q++) t[q] = fma(a.c13, x[q], 1.0);
+#pragma unroll
+        for (int q = 0; q < G; q++) t[q] = fma(t[q], x[q], 1.0);     // 1 + w + w^2/3 = 1 + sqrt5 r + 5/3 r^2
+    } else if (kind == GB2_MATERN32) {
+#pragma unroll
+        for (int q = 0; q < G; q++) t[q] = 1.0 + x[q];
+    }
+    // binary exponent; an exponent field that underflows (exp < ~2^-1022 / eta^2, which includes every clipped-from-above argument)
+    // flushes the entry to an exact 0 -- tested once for the group, the per-entry selects sit on the rarely taken path
+    int hmin = 0x7fffffff;
+#pragma unroll
+    for (int q = 0; q < G; q++) {
+        T[q].y += n[q] << SHIFT;
+        hmin = min(hmin, T[q].y);
+    }
+    if (__builtin_expect(hmin < 0x00100000, 0)) {
+#pragma unroll
+        for (int q = 0; q < G; q++)
+            if (T[q].y < 0x00100000) T[q] = make_int2(0, 0);
+    }
+#pragma unroll
+    for (int q = 0; q < G; q++) {
+        const double Ts = __hiloint2double(T[q].y, T[q].x);
+        rr[q] = fma(Ts, rr[q], Ts);
+    }
+    if (kind == GB2_MATERN52 || kind == GB2_MATERN32) {
+#pragma unroll
+        for (int q = 0; q < G; q++) v[q] = rr[q] * t[q];
+    } else {
+#pragma unroll
+        for (int q = 0; q < G; q++) v[q] = rr[q];                    // ExpQuad, Matern12, Exponential
+    }
 }
 
 __device__ __forceinline__ void kb4_cp_async16(unsigned smem_dst, const void* gmem_src) {
@@ -144,12 +197,12 @@ __global__ void __launch_bounds__(KB_THREADS, OCC)
 kbuild_persist_kernel(KParams kp, KB4Args a) {
     extern __shared__ __align__(16) unsigned char kb_smem[];
     constexpr int ROWS = 4 * KS + 1;                   // staged rows of a column tile: 4 KS features (rows d .. 4 KS - 1 stay zero) + the squared norms
-    constexpr int STAGE_D = ROWS * KB4_TS;             // doubles per stage
-    constexpr int NSLOT = (ROWS + 7) / 8;              // 16-byte prefetch chunks per thread and tile: 32 chunks per row, 8 rows per pass
-    const unsigned char* sTab = kb_smem;                                        // [2048] x 8 bytes, high words biased (kb4_exp)
+    constexpr int TILE_D = ROWS * KB4_TS;              // doubles per staged column tile
+    constexpr int NCGX = NCG > 0 ? NCG : 1;
+    const unsigned char* sTab = kb_smem;                                        // [2048] x 8 bytes, high words biased (kb4_eval)
     double* sB = reinterpret_cast<double*>(kb_smem) + KB4_TAB;                  // [STAGES][ROWS][TS]
-    double* sBt = sB + KB4_STAGES * STAGE_D;                                    // [NCG][P*P <= 64] Coregion tables
-    int* sCj = reinterpret_cast<int*>(sBt + (NCG > 0 ? NCG : 1) * GB2_MAX_P * GB2_MAX_P);   // [STAGES][NCG][64]
+    double* sBt = sB + KB4_STAGES * TILE_D;                                     // [NCG][P*P <= 64] Coregion tables
+    int* sCj = reinterpret_cast<int*>(sBt + NCGX * GB2_MAX_P * GB2_MAX_P);      // [STAGES][NCG][64]
     __shared__ int s_item;
 
     const TermDev& T = kp.t[0];
@@ -166,39 +219,30 @@ kbuild_persist_kernel(KParams kp, KB4Args a) {
     // one-time per CTA: exp table scaled by eta^2 (biased high words), zeroed stages, Coregion tables
     for (int e = tid; e < KB4_TAB; e += KB_THREADS) {
         const double v = T.eta2 * g_exp2_tab2k[e];
-        reinterpret_cast<int2*>(kb_smem)[e] = make_int2(__double2loint(v), __double2hiint(v) - (e << 9));
+        reinterpret_cast<int2*>(kb_smem)[e] = make_int2(__double2loint(v), __double2hiint(v) - (e << (20 - KB4_TAB_LOG2)));
     }
-    for (int e = tid; e < KB4_STAGES * STAGE_D; e += KB_THREADS) sB[e] = 0.0;
+    for (int e = tid; e < KB4_STAGES * TILE_D; e += KB_THREADS) sB[e] = 0.0;
     if (NCG > 0)
         for (int e = tid; e < NCG * GB2_MAX_P * GB2_MAX_P; e += KB_THREADS) {
             const int f = e / (GB2_MAX_P * GB2_MAX_P), q = e % (GB2_MAX_P * GB2_MAX_P);
             sBt[e] = q < T.cg_P[f] * T.cg_P[f] ? a.Btab[T.cg_Boff[f] + q] : 0.0;
         }
 
-    // this thread's prefetch slots: slot s = chunk (tid & 31) of table row k = 8 s + (tid >> 5); row d (the squared norms) lands in stage row 4 KS
-    const double* pf_src[NSLOT];
-    unsigned pf_dst[NSLOT];
-    bool pf_on[NSLOT];
-#pragma unroll
-    for (int s = 0; s < NSLOT; s++) {
-        const int k = 8 * s + (tid >> 5), ch = tid & 31;
-        pf_on[s] = k <= d;
-        pf_src[s] = Fjt + (int64_t)(k <= d ? k : 0) * a.stride_j + ch * 2;
-        pf_dst[s] = (unsigned)__cvta_generic_to_shared(sB + (k < d ? k : 4 * KS) * KB4_TS + ch * 2);
-    }
-    const int* pf_csrc = nullptr;
-    unsigned pf_cdst = 0;
-    if (NCG > 0 && tid < NCG * 16) {
-        const int f = tid >> 4, ch = tid & 15;
-        pf_csrc = a.Cj + (int64_t)T.cg_cat[f] * a.stride_j + ch * 4;
-        pf_cdst = (unsigned)__cvta_generic_to_shared(sCj + f * KB_T + ch * 4);
-    }
+    // Prefetch of one ring stage (a column tile: d feature rows + the squared norms of 64 points, + Coregion levels) by ONE warp: a lane
+    // copies 16 bytes of every row.  (v5 spread the chunks over all 256 threads, and every thread re-derived its slot addresses per
+    // tile: 9 % of all instructions.)  The producer role rotates over the warps with the tile counter.
+    const unsigned sB_s = (unsigned)__cvta_generic_to_shared(sB), sCj_s = (unsigned)__cvta_generic_to_shared(sCj);
     auto prefetch = [&](int jt, int stage) {
-        const int64_t j0 = (int64_t)jt * KB_T;
+        const double* src = Fjt + (int64_t)jt * KB_T + lane * 2;
+        const unsigned dst = sB_s + (unsigned)((stage * TILE_D + lane * 2) * 8);
 #pragma unroll
-        for (int s = 0; s < NSLOT; s++)
-            if (pf_on[s]) kb4_cp_async16(pf_dst[s] + stage * (STAGE_D * 8), pf_src[s] + j0);
-        if (NCG > 0 && tid < NCG * 16) kb4_cp_async16(pf_cdst + stage * (NCG * KB_T * 4), pf_csrc + j0);
+        for (int k = 0; k < 4 * KS; k++)
+            if (k < d) kb4_cp_async16(dst + k * KB4_TS * 8, src + (int64_t)k * a.stride_j);
+        kb4_cp_async16(dst + 4 * KS * KB4_TS * 8, src + (int64_t)d * a.stride_j);
+        if (NCG > 0 && lane < NCG * 16) {
+            const int f = lane >> 4, ch = lane & 15;
+            kb4_cp_async16(sCj_s + (unsigned)(((stage * NCGX + f) * KB_T + ch * 4) * 4), a.Cj + (int64_t)T.cg_cat[f] * a.stride_j + (int64_t)jt * KB_T + ch * 4);
+        }
     };
 
     // work items: TRAIN -- row tile bi has strips 0 .. bi / strip (lower triangle); groups of `strip` row tiles share a strip count
@@ -239,15 +283,14 @@ kbuild_persist_kernel(KParams kp, KB4Args a) {
         if (TRAIN && jt1 > bi + 1) jt1 = bi + 1;
         const int64_t i0 = (int64_t)bi * KB_T;
 
-        // column ring: two tiles in flight before the first one is consumed
-        prefetch(jt0, 0);
-        asm volatile("cp.async.commit_group;\n" ::);
-        if (jt0 + 1 < jt1) prefetch(jt0 + 1, 1);
+        // column ring: two tiles in flight before the first one is consumed (producer of tile jt0 + s = warp s mod 8)
+        if (warp == 0) prefetch(jt0, 0);
+        if (warp == 1 && jt0 + 1 < jt1) prefetch(jt0 + 1, 1);
         asm volatile("cp.async.commit_group;\n" ::);
 
         // row side of the item as DMMA A fragments: lane (g, t4) holds feature 4 ks + t4 of rows r0 + g and r0 + 8 + g, scaled by -2c
         double af[2][KS], si[2];
-        int rowoff[NCG > 0 ? NCG : 1][2];
+        int rowoff[NCGX][2];
 #pragma unroll
         for (int mi = 0; mi < 2; mi++) {
             const int64_t gi = i0 + r0 + mi * 8 + g;
@@ -267,13 +310,14 @@ kbuild_persist_kernel(KParams kp, KB4Args a) {
 
         int st = 0, pf = 2;
         for (int jt = jt0; jt < jt1; jt++) {
-            asm volatile("cp.async.wait_group 1;\n" ::);
+            // the group that filled this stage was committed one or two tiles ago by its producer warp; every other warp has nothing pending
+            asm volatile("cp.async.wait_group 0;\n" ::);
             __syncthreads();
-            if (jt + 2 < jt1) prefetch(jt + 2, pf);
+            if (jt + 2 < jt1 && warp == ((jt + 2 - jt0) & 7)) prefetch(jt + 2, pf);
             asm volatile("cp.async.commit_group;\n" ::);
             pf = pf == KB4_STAGES - 1 ? 0 : pf + 1;
-            const double* cB = sB + st * STAGE_D;
-            const int* cC = sCj + st * (NCG > 0 ? NCG : 1) * KB_T;
+            const double* cB = sB + st * TILE_D;
+            const int* cC = sCj + st * NCGX * KB_T;
             st = st == KB4_STAGES - 1 ? 0 : st + 1;
             const int64_t j0 = (int64_t)jt * KB_T;
             const bool interior = row_full && jt < n_full_cols && (!TRAIN || bi != jt);
@@ -282,14 +326,14 @@ kbuild_persist_kernel(KParams kp, KB4Args a) {
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int cb = c0 + h * 16;
-                double acc[2][2][2];
+                double acc[2][4];                      // [nj][2 mi + e]
 #pragma unroll
                 for (int nj = 0; nj < 2; nj++) {
                     const double2 sj = *reinterpret_cast<const double2*>(cB + 4 * KS * KB4_TS + cb + nj * 8 + 2 * t4);
 #pragma unroll
                     for (int mi = 0; mi < 2; mi++) {
-                        acc[mi][nj][0] = fma(csc, sj.x, si[mi]);
-                        acc[mi][nj][1] = fma(csc, sj.y, si[mi]);
+                        acc[nj][2 * mi + 0] = fma(csc, sj.x, si[mi]);
+                        acc[nj][2 * mi + 1] = fma(csc, sj.y, si[mi]);
                     }
                 }
 #pragma unroll
@@ -298,34 +342,31 @@ kbuild_persist_kernel(KParams kp, KB4Args a) {
 #pragma unroll
                     for (int nj = 0; nj < 2; nj++) {
                         const double b = pb[nj * 8];
-                        kb_dmma(acc[0][nj][0], acc[0][nj][1], af[0][ks], b);
-                        kb_dmma(acc[1][nj][0], acc[1][nj][1], af[1][ks], b);
+                        kb_dmma(acc[nj][0], acc[nj][1], af[0][ks], b);
+                        kb_dmma(acc[nj][2], acc[nj][3], af[1][ks], b);
                     }
                 }
 #pragma unroll
                 for (int nj = 0; nj < 2; nj++) {
-                    int cj[NCG > 0 ? NCG : 1][2];
+                    kb4_eval<KIND, 4>(kind_rt, acc[nj], sTab, a);
+                    if (NCG > 0) {
 #pragma unroll
-                    for (int f = 0; f < NCG; f++) {
-                        const int2 c2 = *reinterpret_cast<const int2*>(cC + f * KB_T + cb + nj * 8 + 2 * t4);
-                        cj[f][0] = c2.x; cj[f][1] = c2.y;
-                    }
+                        for (int f = 0; f < NCG; f++) {
+                            const int2 c2 = *reinterpret_cast<const int2*>(cC + f * KB_T + cb + nj * 8 + 2 * t4);
 #pragma unroll
-                    for (int mi = 0; mi < 2; mi++)
-#pragma unroll
-                        for (int e = 0; e < 2; e++) {
-                            double v = kb4_value<KIND>(kind_rt, acc[mi][nj][e], sTab, a);
-#pragma unroll
-                            for (int f = 0; f < NCG; f++) v *= sBt[rowoff[f][mi] + cj[f][e]];
-                            acc[mi][nj][e] = v;
+                            for (int mi = 0; mi < 2; mi++) {
+                                acc[nj][2 * mi + 0] *= sBt[rowoff[f][mi] + c2.x];
+                                acc[nj][2 * mi + 1] *= sBt[rowoff[f][mi] + c2.y];
+                            }
                         }
+                    }
                 }
                 if (interior) {
 #pragma unroll
                     for (int mi = 0; mi < 2; mi++)
 #pragma unroll
                         for (int nj = 0; nj < 2; nj++)
-                            *reinterpret_cast<double2*>(dtile + mi * ld8 + h * 16 + nj * 8) = make_double2(acc[mi][nj][0], acc[mi][nj][1]);
+                            *reinterpret_cast<double2*>(dtile + mi * ld8 + h * 16 + nj * 8) = make_double2(acc[nj][2 * mi], acc[nj][2 * mi + 1]);
                     continue;
                 }
                 // boundary tiles (the diagonal tile of a training row, ragged edges): augmentation and padding per entry
@@ -338,7 +379,7 @@ kbuild_persist_kernel(KParams kp, KB4Args a) {
 #pragma unroll
                         for (int e = 0; e < 2; e++) {
                             const int64_t gj = j0 + cb + nj * 8 + 2 * t4 + e;
-                            double v = acc[mi][nj][e];
+                            double v = acc[nj][2 * mi + e];
                             if (TRAIN) {
                                 if (gi < a.n_i && gj < a.n_j) {
                                     if (gi == gj) {
@@ -364,7 +405,6 @@ kbuild_persist_kernel(KParams kp, KB4Args a) {
                 }
             }
         }
-        asm volatile("cp.async.wait_group 0;\n" ::);
     }
     // self-resetting counters: the last CTA out leaves both at zero for the next launch on this handle
     if (tid == 0) {

@@ -212,7 +212,7 @@ static void run_case(int64_t n, int d, int P, int n_sm) {
         const float m2 = time_persist<KIND, KS, NCG, 2>(kp, a, n_sm, strip, reps);
         const float m3 = time_persist<KIND, KS, NCG, 3>(kp, a, n_sm, strip, reps);
         const float m4 = time_persist<KIND, KS, NCG, 4>(kp, a, n_sm, strip, reps);
-        printf("   persistent strip %2d : occ2 %.3f ms %.0f GB/s | occ3 %.3f ms %.0f GB/s | occ4 %.3f ms %.0f GB/s\n", strip, m2, bytes / m2 / 1e6, m3,
+        printf("   v6 persistent strip %2d : occ2 %.3f ms %.0f GB/s | occ3 %.3f ms %.0f GB/s | occ4 %.3f ms %.0f GB/s\n", strip, m2, bytes / m2 / 1e6, m3,
                bytes / m3 / 1e6, m4, bytes / m4 / 1e6);
     }
     // accuracy: new vs round-1 over the whole lower triangle (incl. the y row), sampled entries vs long double
