@@ -450,7 +450,7 @@ def rooflines(r, precision, world, peaks, dgemm_peak, dgemm_sustained, copy_gbs,
                          "aggregate_fp64_equivalent_tflops": chol_tflops, "algorithmic_flop_per_step": N ** 3,
                          "peak_source": f"half of the bf16 GEMM peak of {peaks['source']}",
                          "note": "upper bound on the tensor work: the fp64 panel factorisations (DMMA) are inside the timed phase and counted as tf32 products"}
-    roofline_kb = {"kernel": "kbuild_persist_kernel<TRAIN> (single-term models) / kbuild_dmma_kernel (Linear, additive models)", "bound": "hbm",
+    roofline_kb = {"kernel": "kbuild_persist_kernel<TRAIN> v6 (single-term models: C2, C3, C4) / kbuild_dmma_kernel (Linear, additive models)", "bound": "hbm",
                    "achieved": kb_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": kb_gbs / peaks["hbm_gbs"], "peak_source": peaks["source"],
                    "algorithmic_bytes_per_launch": kb_bytes / world, "avg_launch_ms": phase["kbuild_ms"],
                    "traffic": (measured_traffic(f"{workload}:kbuild") or {}).get("dram_bytes_per_launch") if world == 1 else None,
@@ -577,7 +577,7 @@ def run_ours(args):
     also = None
     if world == 1 and not args.no_also:
         also = {}
-        for name, wl, prec in (("c2_fp64", "c2", "fp64"), ("c4_tf32", "c4", "tf32"), ("c4_fp64", "c4", "fp64")):
+        for name, wl, prec in (("c2_fp64", "c2", "fp64"), ("c3_fp64", "c3", "fp64"), ("c4_tf32", "c4", "tf32"), ("c4_fp64", "c4", "fp64")):
             if wl == args.workload and prec == precision:
                 continue
             try:
