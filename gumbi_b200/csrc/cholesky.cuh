@@ -23,8 +23,12 @@ namespace gb2 {
 //   trsm32    one warp per sub-block below, lane r owns row r: x <- x L_pp^-T by forward substitution (axpy form)
 //   inv32     one warp, lane c owns column c of inv(L_pp)
 //   update    C_ij -= L_ip L_jp^T as 32x32x32 block products on DMMA, split in 8-column units over all 16 warps
-// and then the inverse of the 128x128 factor is assembled from the four 32x32 inverses with block products
+// and the inverse of the 128x128 factor is assembled from the four 32x32 inverses with block products
 //   X_ij = -X_ii ( sum_{k=j..i-1} L_ik X_kj ).
+// The assembly and the write-back of the factor do NOT follow the factorisation (round 1: 12 k + 3 k of the kernel's 67 k cycles): every
+// product is issued as soon as its operands are final, on the warps that idle while warp 0 runs a 32-column pivot chain (6.7 k cycles,
+// 15 idle warps) or the 32x32 substitutions (3.5 k cycles) -- see the schedule at the side-work lambdas.  Only  X_3j = -X_33 T_3j
+// (one round of 12 independent units) remains behind the last diagonal inverse.
 // Columns with global index >= n_real (the y row of the augmented system and the identity padding) get pivot 1.
 // A non-positive pivot records info = global column + 1 (first one wins) and is replaced by 1 so that the rest of the
 // pipeline stays finite; the host turns info into LinAlgError.
@@ -140,6 +144,41 @@ potrf_diag_kernel(double* __restrict__ A, int64_t ld, int64_t g0, int64_t n_real
     __syncthreads();
     PD_CLK();
 
+    // ---- side work: inverse assembly and factor write-back, spread over the warps the factorisation leaves idle --------------------------
+    //   T_ij (transposed) lives where X_ij will go; a unit only ever touches its own 8 columns of a sub-block, so in-place steps are race-free.
+    //   A(j):  T_ij  = L_ij X_jj            (i > j)        operands final after the substitutions of step j
+    //   B(j):  X_{j+1,j} = -X_{j+1,j+1} T_{j+1,j}          after the diagonal inverse of step j+1
+    //   C1(j): T_{j+2,j} += L_{j+2,j+1} X_{j+1,j}          after B(j)
+    //   C2(j): X_{j+2,j} = -X_{j+2,j+2} T_{j+2,j}          after C1(j) and the diagonal inverse of step j+2
+    //   D1:    T_30 += L_31 X_10 + L_32 X_20               after B(0), C2(0)
+    //   last:  X_3j = -X_33 T_3j                           after the diagonal inverse of step 3
+    // Schedule (sub-phases are the __syncthreads-separated parts of a step: pivot chain | substitutions | block update):
+    //   step 1 pivot chain : A(0)                  step 1 substitutions: write-back of column block 0
+    //   step 2 pivot chain : A(1), B(0)            step 2 substitutions: C1(0), write-back of column block 1      step 2 block update: C2(0), B(1)
+    //   step 3 pivot chain : C1(1), D1, A(2)       step 3 substitutions: write-back of column block 2 and of block (3,3)
+    // Side work next to a pivot chain or a substitution runs only on the 12 warps of the other three sub-partitions (warp & 3 != 0): units
+    // on warps 4, 8, 12 share warp 0's dispatch port and stretched the pivot chains from 6.1 k to 8.0 k cycles (profiles/r02pa_micro_potrf.log).
+    auto XT = [&](int i, int j) { return Xt + pd_blk(i, j) * PB_SZ; };
+    auto L = [&](int i, int j) { return Lb + pd_blk(i, j) * PB_SZ; };
+    auto GD = [&](int i, int j) { return Dinv + (int64_t)(i * PB) * TILE + j * PB; };
+    auto unitA = [&](int j, int u) { const int i = j + 1 + (u >> 2); pd_unit<1, true>(XT(i, j), L(i, j), XT(j, j), nullptr, nullptr, (u & 3) * 8, lane); };
+    auto unitB = [&](int j, int u) { pd_unit<3, true>(XT(j + 1, j), Xd + (j + 1) * PB_SZ, XT(j + 1, j), nullptr, nullptr, u * 8, lane, GD(j + 1, j), TILE); };
+    auto unitC1 = [&](int j, int u) { pd_unit<2, true>(XT(j + 2, j), L(j + 2, j + 1), XT(j + 1, j), nullptr, nullptr, u * 8, lane); };
+    auto unitC2 = [&](int j, int u) { pd_unit<3, true>(XT(j + 2, j), Xd + (j + 2) * PB_SZ, XT(j + 2, j), nullptr, nullptr, u * 8, lane, GD(j + 2, j), TILE); };
+    const bool side = (warp & 3) != 0;
+    const int sidx = (warp >> 2) * 3 + (warp & 3) - 1;          // 0 .. 11 over the side warps
+    // write-back of the final sub-blocks (i, j), i = i_first .. 3, of column block j (lower triangle only) by workers k0 .. k0 + nw - 1 (k = this worker)
+    auto store_col = [&](int j, int i_first, int k, int nw) {
+        for (int pr = k; pr < (4 - i_first) * PB; pr += nw) {
+            const int i = i_first + (pr >> 5), r = pr & 31;
+            if (i != j || lane <= r) {
+                const double v = Lb[pd_blk(i, j) * PB_SZ + r * PB_LD + lane];
+                Ab[(int64_t)(i * PB + r) * ld + j * PB + lane] = v;
+                if (Lpack) Lpack[(i * PB + r) * TILE + j * PB + lane] = v;   // contiguous copy for the multi-GPU broadcast
+            }
+        }
+    };
+
     for (int p = 0; p < 4; p++) {
         double* Lpp = Lb + pd_blk(p, p) * PB_SZ;
         // ---- potrf32: warp 0, lane r owns row r.  The next pivot's 1/sqrt is started before the column broadcast of
@@ -187,11 +226,19 @@ potrf_diag_kernel(double* __restrict__ A, int64_t ld, int64_t g0, int64_t n_real
             double* wr = Lpp + lane * PB_LD;
 #pragma unroll
             for (int c = 0; c < PB; c++) wr[c] = (c <= lane) ? a[c] : 0.0;
+        } else if (side && p == 1) {
+            unitA(0, sidx);
+        } else if (side && p == 2) {
+            if (sidx < 8) unitA(1, sidx); else unitB(0, sidx - 8);
+        } else if (side && p == 3) {
+            if (sidx < 4) unitC1(1, sidx);
+            else if (sidx < 8) pd_unit<2, true>(XT(3, 0), L(3, 1), XT(1, 0), L(3, 2), XT(2, 0), (sidx - 4) * 8, lane);   // D1
+            else unitA(2, sidx - 8);
         }
         __syncthreads();
         PD_CLK();
 
-        // ---- inv32 (warp 0: column `lane` of inv(L_pp)) || trsm32 (warps 1..3-p: rows of the sub-blocks below)
+        // ---- inv32 (warp 0: column `lane` of inv(L_pp)) || trsm32 (warps 1..3-p: rows of the sub-blocks below) || side work
         if (warp == 0) {
             double b[PB];
 #pragma unroll
@@ -203,14 +250,14 @@ potrf_diag_kernel(double* __restrict__ A, int64_t ld, int64_t g0, int64_t n_real
                 for (int r = k + 1; r < PB; r++) b[r] = fma(-Lpp[r * PB_LD + k], b[k], b[r]);
             }
             double* X = Xd + p * PB_SZ;
-            double* XT = Xt + pd_blk(p, p) * PB_SZ;
+            double* XTp = Xt + pd_blk(p, p) * PB_SZ;
             double* G = Dinv + (int64_t)(p * PB) * TILE + p * PB;
 #pragma unroll
             for (int r = 0; r < PB; r++) {       // X[r][c = lane]; exact zeros above the diagonal
                 X[r * PB_LD + lane] = b[r];
                 G[r * TILE + lane] = b[r];
             }
-            double2* wt = reinterpret_cast<double2*>(XT + lane * PB_LD);
+            double2* wt = reinterpret_cast<double2*>(XTp + lane * PB_LD);
 #pragma unroll
             for (int q = 0; q < PB / 2; q++) wt[q] = make_double2(b[2 * q], b[2 * q + 1]);
         } else if (warp <= 3 - p) {
@@ -229,12 +276,18 @@ potrf_diag_kernel(double* __restrict__ A, int64_t ld, int64_t g0, int64_t n_real
             double2* wr = reinterpret_cast<double2*>(Lip + lane * PB_LD);
 #pragma unroll
             for (int q = 0; q < PB / 2; q++) wr[q] = make_double2(x[2 * q], x[2 * q + 1]);
+        } else if (side && p == 1) {
+            if (sidx >= 3) store_col(0, 0, sidx - 3, 9);
+        } else if (side && p == 2) {
+            if (sidx >= 3 && sidx < 7) unitC1(0, sidx - 3); else if (sidx >= 7) store_col(1, 1, sidx - 7, 5);
+        } else if (side && p == 3) {
+            if (sidx < 8) store_col(2, 2, sidx, 8); else store_col(3, 3, sidx - 8, 4);      // block (3,3): final since the pivot chain of this step
         }
         __syncthreads();
         PD_CLK();
 
-        // ---- trailing update inside the block: C_ij -= L_ip L_jp^T for p < j <= i, 4 column units per product
-        {
+        // ---- trailing update inside the block: C_ij -= L_ip L_jp^T for p < j <= i, 4 column units per product (|| side work at step 2)
+        if (p < 3) {
             const int m = 3 - p;                      // sub-blocks below
             const int n_units = m * (m + 1) / 2 * 4;
             for (int u = warp; u < n_units; u += NW) {
@@ -245,62 +298,18 @@ potrf_diag_kernel(double* __restrict__ A, int64_t ld, int64_t g0, int64_t n_real
                 pd_unit<0, false>(Lb + pd_blk(i, j) * PB_SZ, Lb + pd_blk(i, p) * PB_SZ, Lb + pd_blk(j, p) * PB_SZ, nullptr,
                                   nullptr, chunk * 8, lane);
             }
-        }
-        __syncthreads();
-        PD_CLK();
-    }
-
-    // ---- factor back to global (lower triangle only); overlaps with stage A below (Lb is read-only from here on)
-#pragma unroll
-    for (int q = 0; q < PD_NBLK * PB / NW; q++) {
-        const int pr = warp + q * NW, b = pr >> 5, r = pr & 31;
-        const int bi = (b >= 6) ? 3 : (b >= 3) ? 2 : (b >= 1) ? 1 : 0;
-        const int bj = b - bi * (bi + 1) / 2;
-        if (bi != bj || lane <= r) {
-            const double v = Lb[b * PB_SZ + r * PB_LD + lane];
-            Ab[(int64_t)(bi * PB + r) * ld + bj * PB + lane] = v;
-            if (Lpack) Lpack[(bi * PB + r) * TILE + bj * PB + lane] = v;   // contiguous copy for the multi-GPU broadcast
+            if (p == 2 && warp >= 4 && warp < 12) {   // the update itself occupies warps 0..3 here
+                if (warp <= 7) unitC2(0, warp - 4); else unitB(1, warp - 8);
+            }
+            __syncthreads();
+            PD_CLK();
         }
     }
-    PD_CLK();
 
-    // ---- assemble inv(L):  X_ij = -X_ii T_ij,  T_ij = sum_{k=j..i-1} L_ik X_kj.  T_ij lives (transposed) where X_ij
-    // will go; a unit only ever touches its own 8 columns of a sub-block, so the in-place steps are race-free.
-    auto XT = [&](int i, int j) { return Xt + pd_blk(i, j) * PB_SZ; };
-    auto L = [&](int i, int j) { return Lb + pd_blk(i, j) * PB_SZ; };
-    auto GD = [&](int i, int j) { return Dinv + (int64_t)(i * PB) * TILE + j * PB; };
-    // stage A: T_ij = L_ij X_jj for all i > j (6 products, 24 units)
-    for (int u = warp; u < 24; u += NW) {
-        const int op = u >> 2, chunk = u & 3;
-        const int i = op < 1 ? 1 : (op < 3 ? 2 : 3);
-        const int j = op - (i == 1 ? 0 : (i == 2 ? 1 : 3));
-        pd_unit<1, true>(XT(i, j), L(i, j), XT(j, j), nullptr, nullptr, chunk * 8, lane);
-    }
-    __syncthreads();
-    // stage B: X_{j+1,j} = -X_{j+1,j+1} T_{j+1,j}
-    for (int u = warp; u < 12; u += NW) {
-        const int j = u >> 2, chunk = u & 3;
-        pd_unit<3, true>(XT(j + 1, j), Xd + (j + 1) * PB_SZ, XT(j + 1, j), nullptr, nullptr, chunk * 8, lane, GD(j + 1, j), TILE);
-    }
-    __syncthreads();
-    // stage C1: T_{j+2,j} += L_{j+2,j+1} X_{j+1,j}
-    for (int u = warp; u < 8; u += NW) {
-        const int j = u >> 2, chunk = u & 3;
-        pd_unit<2, true>(XT(j + 2, j), L(j + 2, j + 1), XT(j + 1, j), nullptr, nullptr, chunk * 8, lane);
-    }
-    __syncthreads();
-    // stage C2: X_{j+2,j} = -X_{j+2,j+2} T_{j+2,j}
-    for (int u = warp; u < 8; u += NW) {
-        const int j = u >> 2, chunk = u & 3;
-        pd_unit<3, true>(XT(j + 2, j), Xd + (j + 2) * PB_SZ, XT(j + 2, j), nullptr, nullptr, chunk * 8, lane, GD(j + 2, j), TILE);
-    }
-    __syncthreads();
-    // stage D: T_30 += L_31 X_10 + L_32 X_20 ; X_30 = -X_33 T_30
-    if (warp < 4) {
-        pd_unit<2, true>(XT(3, 0), L(3, 1), XT(1, 0), L(3, 2), XT(2, 0), warp * 8, lane);
-        __syncwarp();
-        pd_unit<3, true>(XT(3, 0), Xd + 3 * PB_SZ, XT(3, 0), nullptr, nullptr, warp * 8, lane, GD(3, 0), TILE);
-    }
+    // ---- what depends on the last diagonal inverse: X_32 = -X_33 T_32, X_31 = -X_33 T_31, X_30 = -X_33 T_30
+    if (warp < 4) unitB(2, warp);
+    else if (warp < 8) unitC2(1, warp - 4);
+    else if (warp < 12) pd_unit<3, true>(XT(3, 0), Xd + 3 * PB_SZ, XT(3, 0), nullptr, nullptr, (warp - 8) * 8, lane, GD(3, 0), TILE);
     PD_CLK();
 #undef PD_CLK
     if (sig.n_peers > 0) {
